@@ -1,0 +1,168 @@
+"""Pins the C oracle (oracle/liboracle.so) against the known-answer vectors held by the reference's own unit tests.
+Citations are relative to /root/reference/test/unit."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+from _libs import KEYS, MAXLEVEL, oracle, orc_decode, orc_scalar
+from _util import OctreeMaker, node_range
+
+KT = ["u32", "u64"]
+
+
+def pad(kt, prefix, length):
+    return prefix << (3 * MAXLEVEL[kt] - length)
+
+
+@pytest.mark.parametrize("kt", KT)
+def test_imorton3d(kt):  # sfc/morton.cpp:26-34
+    shift = MAXLEVEL[kt] - 3
+    assert orc_scalar("imorton", kt, 5 << shift, 3 << shift, 6 << shift) == pad(kt, 0b101011110, 9)
+
+
+def test_decode_morton():  # sfc/morton.cpp:42-73
+    assert orc_decode("decode_morton", "u32", 340) == (5, 2, 4)
+    m = (1 << 21) - 1
+    assert orc_decode("decode_morton", "u64", 0x7FFFFFFFFFFFFFFF) == (m, m, m)
+    assert orc_decode("decode_morton", "u64", 0x1249249241249249)[2] == (1 << 21) - 512 - 1
+    assert orc_decode("decode_morton", "u64", 0b0111 << 60) == (1 << 20, 1 << 20, 1 << 20)
+    assert orc_decode("decode_morton", "u64", 0b0011 << 60) == (0, 1 << 20, 1 << 20)
+
+
+@pytest.mark.parametrize("kt", KT)
+def test_hilbert_first_order_curve(kt):  # sfc/hilbert.cpp:84-112
+    hilbert_to_morton = [0, 1, 3, 2, 6, 7, 5, 4]
+    L1 = (1 << MAXLEVEL[kt]) // 2
+    for xi in range(2):
+        for yi in range(2):
+            for zi in range(2):
+                for off in (0, L1 - 1):
+                    key = orc_scalar("ihilbert", kt, L1 * xi + off, L1 * yi + off, L1 * zi + off)
+                    octant = (key >> (3 * (MAXLEVEL[kt] - 1))) & 7
+                    assert hilbert_to_morton[octant] == 4 * xi + 2 * yi + zi
+
+
+@pytest.mark.parametrize("kt", KT)
+def test_hilbert_continuity(kt):  # sfc/hilbert.cpp:121-145
+    for level in range(1, MAXLEVEL[kt]):
+        for octant in range(8 if level > 1 else 7):
+            last = (octant + 1) * node_range(kt, level) - 1
+            a = orc_decode("decode_hilbert", kt, last)
+            b = orc_decode("decode_hilbert", kt, last + 1)
+            assert sum(abs(int(p) - int(q)) for p, q in zip(a, b)) == 1
+
+
+@pytest.mark.parametrize("kt", KT)
+def test_hilbert_inversion(kt):  # sfc/hilbert.cpp:154-182
+    rng = np.random.default_rng(0)
+    m = 1 << MAXLEVEL[kt]
+    for x, y, z in rng.integers(0, m, size=(1000, 3)):
+        key = orc_scalar("ihilbert", kt, int(x), int(y), int(z))
+        assert orc_decode("decode_hilbert", kt, key) == (x, y, z)
+    for x, y, z in [(0, 0, 0), (m - 1, m - 1, m - 1), (m - 1, 0, 0), (0, m - 1, 0), (0, 0, m - 1)]:
+        key = orc_scalar("ihilbert", kt, x, y, z)
+        assert orc_decode("decode_hilbert", kt, key) == (x, y, z)
+
+
+@pytest.mark.parametrize("kt", KT)
+def test_count_tree_nodes(kt):  # tree/csarray.cpp:57-76
+    tree = OctreeMaker(kt).divide().divide(0).make_tree()
+    t = [int(v) for v in tree]
+    keys = np.array([t[1], t[1], t[1] + 10, t[1] + 100, t[2] - 1, t[2] + 1, t[11], t[11] + 2, t[12], t[12] + 1000,
+                     t[12] + 2000, t[13] - 10, t[13], t[13] + 1], dtype=KEYS[kt])
+    counts = oracle().compute_node_counts(kt, tree, keys)
+    assert counts.tolist() == [0, 5, 1, 0, 0, 0, 0, 0, 0, 0, 0, 2, 4, 2, 0]
+
+
+@pytest.mark.parametrize("kt", KT)
+def test_count_first_last_node(kt):  # tree/csarray.cpp:80-98 (spanning tree {0,1,2^(3L)-1,2^(3L)} restated directly)
+    tree = OctreeMaker(kt)
+    path = []
+    for _ in range(MAXLEVEL[kt]):
+        tree.divide(*path)
+        path.append(0)
+    path = []
+    for lvl in range(MAXLEVEL[kt]):
+        if lvl:
+            tree.divide(*path)
+        path.append(7)
+    leaves = tree.make_tree()
+    assert leaves[1] == 1 and leaves[-2] == node_range(kt, 0) - 1
+    keys = np.array([0, 0, node_range(kt, 0) - 1, node_range(kt, 0) - 1], dtype=KEYS[kt])
+    counts = oracle().compute_node_counts(kt, leaves, keys)
+    ref = np.zeros(leaves.size - 1, dtype=np.uint32)
+    ref[0] = ref[-1] = 2
+    assert np.array_equal(counts, ref)
+
+
+@pytest.mark.parametrize("kt", KT)
+def test_rebalance_decision(kt):  # tree/csarray.cpp:108-122
+    tree = OctreeMaker(kt).divide().divide(0).make_tree()
+    counts = np.array([1, 1, 1, 0, 0, 0, 0, 0, 2, 3, 4, 5, 6, 7, 8], dtype=np.uint32)
+    ops, converged = oracle().rebalance_decision(kt, tree, counts, 4)
+    assert ops.tolist() == [1, 0, 0, 0, 0, 0, 0, 0, 1, 1, 1, 8, 8, 8, 8]
+    assert not converged
+
+
+@pytest.mark.parametrize("kt", KT)
+def test_rebalance_tree(kt):  # tree/csarray.cpp:193-206
+    lib = oracle().lib
+    tree = OctreeMaker(kt).divide().divide(0).make_tree()
+    ops = np.array([1, 0, 0, 0, 0, 0, 0, 0, 1, 8, 1, 1, 1, 1, 8, 0], dtype=np.int32)
+    new = np.zeros(64, dtype=KEYS[kt])
+    f = getattr(lib, "orc_rebalance_tree_" + kt)
+    f.restype = C.c_int
+    n = f(tree.ctypes.data_as(C.c_void_p), C.c_int(15), ops.ctypes.data_as(C.c_void_p), new.ctypes.data_as(C.c_void_p))
+    ref = OctreeMaker(kt).divide().divide(2).divide(7).make_tree()
+    assert n == ref.size - 1
+    assert np.array_equal(new[:n + 1], ref)
+
+
+@pytest.mark.parametrize("kt", KT)
+def test_octree_connectivity_and_upsweep(kt):  # tree/octree.cpp:27-74 (checkConnectivity) and :349-371 (upsweep)
+    leaves = OctreeMaker(kt).divide().divide(0).divide(0, 2).divide(3).make_tree()
+    o = oracle()
+    t = o.build_octree(kt, leaves)
+    nn, ni = t["numNodes"], t["numInternal"]
+    assert ni == (leaves.size - 2) // 7
+    co, par, pf = t["childOffsets"], t["parents"], t["prefixes"]
+    assert np.all(np.diff(pf.astype(np.uint64)) > 0)  # level-major, key-minor order
+    for i in range(nn):
+        if co[i]:
+            plen = int(pf[i]).bit_length() - 1
+            for s in range(8):
+                c = co[i] + s
+                assert par[(c - 1) // 8] == i
+                assert int(pf[c]).bit_length() - 1 == plen + 3
+                assert int(pf[c]) >> 3 == int(pf[i]) and int(pf[c]) & 7 == s
+        else:
+            leaf = t["internalToLeaf"][i]
+            assert 0 <= leaf < t["numLeaves"]
+            assert t["leafToInternal"][ni + leaf] == i
+    counts = np.zeros(nn, dtype=np.uint32)
+    counts[t["leafToInternal"][ni:]] = 1
+    o._fn("upsweep_counts_" + kt)(t["levelRange"].ctypes.data_as(C.c_void_p), co.ctypes.data_as(C.c_void_p),
+                                  counts.ctypes.data_as(C.c_void_p))
+    assert counts.tolist() == [29, 15, 1, 1, 8, 1, 1, 1, 1, 1, 1, 8] + [1] * 21
+
+
+@pytest.mark.parametrize("kt", KT)
+def test_compute_octree_invariants(kt):  # tree/csarray.cpp:303-348 (random Gaussian keys, invariants + counts)
+    rng = np.random.default_rng(3)
+    nr = node_range(kt, 0)
+    g = rng.normal(nr / 2, nr / 5, 120000)
+    keys = g[(g >= 0) & (g < nr - 1)][:100000].astype(KEYS[kt])
+    keys.sort()
+    for bucket in (64, 1024, 10000):
+        leaves, counts = oracle().compute_octree(kt, keys, bucket)
+        assert leaves[0] == 0 and int(leaves[-1]) == nr
+        d = np.diff(leaves.astype(np.uint64)).astype(np.uint64)
+        assert np.all(d > 0)
+        for v in np.unique(d):  # every node range is a power of 8
+            v = int(v)
+            assert v & (v - 1) == 0 and (v.bit_length() - 1) % 3 == 0
+        assert counts.sum() == keys.size
+        assert counts.max() <= bucket
+        ref = np.searchsorted(keys, leaves[1:], side="left") - np.searchsorted(keys, leaves[:-1], side="left")
+        assert np.array_equal(counts, ref.astype(np.uint32))
