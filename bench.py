@@ -1,0 +1,384 @@
+#!/usr/bin/env python
+"""Benchmark of the Cornerstone domain-sync hot path on B200 (BASELINE.json metric:
+"Mparticles/s, Domain::sync + findNeighbors").
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--n PARTICLES_PER_GPU]
+
+One "step" = one pass of the hot path over one batch of synthetic particles:
+SFC keys -> key+index sort -> fused x,y,z,h gather -> leaf-array update -> internal-tree link -> node centres ->
+layout -> radius neighbour search.  At N=1 the workload is BASELINE.json configs[1] (64 Mi uniform particles, 64-bit
+Hilbert keys, double).  For N>1 every rank processes its own 64 Mi shard (weak scaling).
+
+Prints ONE JSON line (rank 0).  `value` is measured with inputs resident in HBM; `e2e` goes through the same C-ABI
+calls but starts from pinned HOST buffers and ends with the results' D2H copies inside the timed region.
+`--impl reference` times the reference's own CPU implementation (oracle/_ref, the unmodified reference headers; the
+C oracle port if that library is absent) on a bounded sample of the same workload.
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.join(ROOT, "cornerstone-octree_b200"))
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+METRIC = "Mparticles/s, Domain::sync + findNeighbors"
+UNIT = "Mparticles/s"
+BUCKET = 64
+NG0 = 100
+NGMAX = 150
+FALLBACK_HBM_GBS = 6650.0  # /opt/skills/guides/B200_PROFILING.md fallback
+
+
+def hbm_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            d = json.load(open(p))
+            for k in ("hbm_gbs", "hbm_gb_s", "hbm_copy_gbs"):
+                if k in d:
+                    return float(d[k]), "measured"
+        except Exception:
+            pass
+    return FALLBACK_HBM_GBS, "fallback"
+
+
+def h_for(n, ng):
+    import numpy as np
+    return 0.5 * float(np.cbrt(3.0 * ng / (4 * np.pi * n)))
+
+
+# ------------------------------------------------------------------------------------------------ clocks
+class ClockSampler:
+    FIELDS = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index = index
+        self.samples = []
+        self.proc = None
+        self.thread = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.FIELDS,
+                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+        except Exception:
+            self.proc = None
+            return
+        self.thread = threading.Thread(target=self._read, daemon=True)
+        self.thread.start()
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.samples.append([f.strip() for f in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for s in self.samples:
+            if len(s) < 6:
+                continue
+            try:
+                sm.append(float(s[0]))
+                mx.append(float(s[1]))
+            except ValueError:
+                continue
+            for nme, v in zip(names, s[2:6]):
+                if v.lower().startswith("active"):
+                    reasons.add(nme)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------------ reference arm (CPU)
+def run_reference(args):
+    """the reference's own CPU path (Domain::sync x2 + findNeighbors) on a bounded sample of the workload"""
+    import numpy as np
+
+    import _libs
+
+    n = args.ref_n
+    rng = np.random.default_rng(42)
+    x, y, z = (rng.random(n) for _ in range(3))
+    h = np.full(n, h_for(n, NG0))
+    lim, bnd = (0, 1, 0, 1, 0, 1), (0, 0, 0)
+    cores = os.cpu_count()
+    values = []
+    kind = "reference" if _libs.ref_lib() is not None else "port"
+    for it in range(args.warmup_ref + args.steps_ref):
+        t0 = time.perf_counter()
+        if kind == "reference":
+            out = _libs.ref_domain_run("u64d", 1, BUCKET, BUCKET, 0.5, lim, bnd, x, y, z, h, [0, n], num_syncs=1,
+                                       ngmax=NGMAX)[0]
+            dt = out["t_sync"][0] + out["t_neighbors"]
+        else:
+            orc = _libs.oracle()
+            keys = orc.sfc_keys("u64d", 0, x, y, z, lim, bnd)
+            order = np.arange(n, dtype=np.uint32)
+            orc.sort_by_key("u64", keys, order)
+            xs, ys, zs = x[order], y[order], z[order]
+            leaves, counts = orc.compute_octree("u64", keys, BUCKET)
+            tree = orc.build_octree("u64", leaves)
+            cen, siz = orc.node_fp_centers("u64d", tree["prefixes"], lim, bnd)
+            layout = np.zeros(leaves.size, dtype=np.uint32)
+            layout[1:] = np.cumsum(counts)
+            orc.find_neighbors("u64d", xs, ys, zs, h, 0, n, lim, bnd, tree, leaves, layout, cen, siz, NGMAX)
+            dt = time.perf_counter() - t0
+        if it >= args.warmup_ref:
+            values.append(n / dt / 1e6)
+    v = statistics.median(values)
+    sample = f"{n} uniform particles (of the 64Mi workload), first Domain::sync + findNeighbors ngmax={NGMAX}, 1 rank"
+    return {"value": v, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample}
+
+
+# ------------------------------------------------------------------------------------------------ our arm
+class HotPath:
+    """the stage pipeline on one GPU; all buffers are allocated once and reused across steps"""
+
+    def __init__(self, n, device):
+        import torch
+
+        from cstone_b200 import capi
+
+        self.capi, self.torch, self.n, self.dev = capi, torch, n, device
+        self.lim, self.bnd = (0, 1, 0, 1, 0, 1), (0, 0, 0)
+        self.stage_ms = {}
+        self.leaves = None
+
+    def _timed(self, name, fn):
+        torch = self.torch
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        out = fn()
+        e1.record()
+        self._events.append((name, e0, e1))
+        return out
+
+    def step(self, x, y, z, h, want_neighbors=True):
+        capi, torch, n = self.capi, self.torch, self.n
+        self._events = []
+        keys = torch.zeros(n, dtype=torch.uint64, device=self.dev)
+        self._timed("keys", lambda: capi.compute_sfc_keys(x, y, z, keys, self.lim, self.bnd))
+        order = self._timed("sequence", lambda: capi.sequence(0, n, self.dev))
+        self._timed("sort", lambda: capi.sort_by_key(keys, order))
+        sx, sy, sz, sh = self._timed("gather", lambda: capi.gather4(order, [x, y, z, h]))
+        leaves, counts = self._timed("csarray", lambda: capi.compute_octree(keys, BUCKET))
+        tree = self._timed("link", lambda: capi.Octree(leaves))
+        cen, siz = self._timed("centers", lambda: capi.compute_geo_centers(tree.prefixes, torch.float64, self.lim,
+                                                                            self.bnd))
+        layout = self._timed("layout", lambda: capi.exclusive_scan(
+            torch.cat([counts, torch.zeros(1, dtype=torch.uint32, device=self.dev)])))
+        nb = nc = None
+        if want_neighbors:
+            if not hasattr(self, "nb"):
+                self.nb = torch.empty(n * NGMAX, dtype=torch.uint32, device=self.dev)
+                self.nc = torch.empty(n, dtype=torch.uint32, device=self.dev)
+            nb, nc = self._timed("neighbors", lambda: capi.find_neighbors(sx, sy, sz, sh, 0, n, self.lim, self.bnd,
+                                                                          tree, layout, cen, siz, NGMAX, self.nb,
+                                                                          self.nc))
+        self.num_leaves = tree.num_leaves
+        return keys, (sx, sy, sz, sh), nc
+
+    def collect(self):
+        for name, e0, e1 in self._events:
+            self.stage_ms.setdefault(name, []).append(e0.elapsed_time(e1))
+
+
+def run_ours(args):
+    import numpy as np
+    import torch
+
+    from cstone_b200 import capi
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (no CPU fallback exists)")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=dev)
+
+    n = args.n
+    g = torch.Generator(device=dev)
+    g.manual_seed(42 + rank)
+    x, y, z = (torch.rand(n, dtype=torch.float64, device=dev, generator=g) for _ in range(3))
+    h = torch.full((n,), h_for(n, NG0), dtype=torch.float64, device=dev)
+    hx, hy, hz, hh = (t.cpu().pin_memory() for t in (x, y, z, h))
+    out_host = [torch.empty(n, dtype=torch.float64).pin_memory() for _ in range(4)]
+    keys_host = torch.empty(n, dtype=torch.uint64).pin_memory()
+    nc_host = torch.empty(n, dtype=torch.uint32).pin_memory()
+
+    hp = HotPath(n, dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(ms):
+        if world > 1:
+            t = torch.tensor([ms], dtype=torch.float64, device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            return float(t.item())
+        return ms
+
+    # ---- device-resident timing
+    for _ in range(args.warmup):
+        hp.step(x, y, z, h)
+    barrier()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    launches0 = capi.kernel_launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for _ in range(args.steps):
+        hp.step(x, y, z, h)
+        hp_events = hp._events
+        hp.all_events = getattr(hp, "all_events", []) + [hp_events]
+    e1.record()
+    barrier()
+    clocks = sampler.stop()
+    launches = capi.kernel_launch_count() - launches0
+    ms_total = max_over_ranks(e0.elapsed_time(e1))
+    for evs in hp.all_events:
+        hp._events = evs
+        hp.collect()
+    ms_per_step = ms_total / args.steps
+    value = world * n / (ms_per_step * 1e-3) / 1e6
+
+    # ---- end to end: pinned host inputs -> device -> pipeline -> results back on the host
+    def e2e_step():
+        dx, dy, dz, dh = (t.to(dev, non_blocking=True) for t in (hx, hy, hz, hh))
+        keys, sorted_arrays, nc = hp.step(dx, dy, dz, dh)
+        keys_host.copy_(keys, non_blocking=True)
+        for o, s in zip(out_host, sorted_arrays):
+            o.copy_(s, non_blocking=True)
+        nc_host.copy_(nc, non_blocking=True)
+
+    e2e_steps = max(1, min(args.steps, 3))
+    e2e_step()
+    barrier()
+    e0.record()
+    for _ in range(e2e_steps):
+        e2e_step()
+    e1.record()
+    barrier()
+    e2e_ms = max_over_ranks(e0.elapsed_time(e1)) / e2e_steps
+    e2e_value = world * n / (e2e_ms * 1e-3) / 1e6
+    h2d = 4 * 8 * n
+    d2h = 4 * 8 * n + 8 * n + 4 * n
+
+    if rank != 0:
+        return None
+
+    # ---- per-stage rooflines (algorithmic bytes per particle: SURVEY.md §8d / DESIGN.md)
+    peak, peak_kind = hbm_peak()
+    nl = hp.num_leaves
+    alg_bytes = {
+        "keys": 40.0 * n,
+        "sort": 200.0 * n,
+        "gather": 68.0 * n,
+        "neighbors": None,
+    }
+    stages = {}
+    for name, ms in hp.stage_ms.items():
+        med = statistics.median(ms)
+        entry = {"ms": round(med, 4)}
+        if alg_bytes.get(name):
+            entry["achieved_gbs"] = round(alg_bytes[name] / (med * 1e-3) / 1e9, 1)
+            entry["frac"] = round(entry["achieved_gbs"] / peak, 4)
+        stages[name] = entry
+    mean_nc = float(nc_host[: 1 << 20].to(torch.int64).sum()) / float(1 << 20)
+    nb_bytes = (4.0 * min(mean_nc, NGMAX) + 4 + 32) * n
+    stages["neighbors"]["achieved_gbs"] = round(nb_bytes / (stages["neighbors"]["ms"] * 1e-3) / 1e9, 1)
+    stages["neighbors"]["frac"] = round(stages["neighbors"]["achieved_gbs"] / peak, 4)
+    stages["neighbors"]["note"] = "traversal + FP64 distance tests; output-write floor used as algorithmic bytes"
+
+    dom = "sort"  # dominant HBM-bound kernel group of Domain::sync (histogram + 8 onesweep passes)
+    roofline = {"bound": "hbm", "kernel": "onesweepKernel<u64,values> x8 + radixHistogramKernel",
+                "achieved": stages[dom]["achieved_gbs"], "peak": peak, "unit": "GB/s", "frac": stages[dom]["frac"],
+                "traffic": None, "peak_source": peak_kind,
+                "algorithmic_bytes_per_particle": 200, "launch_ms": stages[dom]["ms"]}
+
+    line = {
+        "metric": METRIC, "value": round(value, 2), "unit": UNIT, "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": round(ms_per_step, 3), "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "u64 keys / f64 coordinates", "data": "synthetic",
+        "config": {"workload": f"{n} uniform-random particles per GPU, 64-bit Hilbert, double, bucketSize={BUCKET}: "
+                               f"keys+sort+gather+tree build+link+findNeighbors(ng~{NG0}, ngmax={NGMAX})",
+                   "particles_per_gpu": n, "l2_policy": "inputs (>=512 MB per array) exceed the 126 MB L2",
+                   "parallelism": f"sfc-shards x{world}", "leaves": nl, "mean_neighbors": round(mean_nc, 2)},
+        "e2e": {"value": round(e2e_value, 2), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                "ms_per_step": round(e2e_ms, 3),
+                "note": "neighbour lists stay in HBM for the device-side consumer; keys, x,y,z,h and counts return"},
+        "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "stages": stages,
+    }
+    return line
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--n", type=int, default=64 * 1024 * 1024, help="particles per GPU")
+    ap.add_argument("--ref-n", type=int, default=4 * 1024 * 1024, help="CPU sample size")
+    ap.add_argument("--steps-ref", type=int, default=1)
+    ap.add_argument("--warmup-ref", type=int, default=0)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+
+    rank = int(os.environ.get("RANK", "0"))
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        args.steps_ref = max(1, min(args.steps, 3))
+        args.warmup_ref = min(args.warmup, 1)
+        cb = run_reference(args)
+        line = {"impl": "reference", "metric": METRIC, "value": round(cb["value"], 4), "unit": UNIT,
+                "n_gpus": args.gpus, "steps": args.steps_ref, "warmup": args.warmup_ref, "higher_is_better": True,
+                "scaling": "weak", "vs_baseline": None, "dtype": "u64 keys / f64 coordinates", "data": "synthetic",
+                "ms_per_step": round(args.ref_n / cb["value"] / 1e3, 3),
+                "config": {"workload": "64Mi uniform-random particles, 64-bit Hilbert, double, bucketSize=64 "
+                                       "(bounded CPU sample, see cpu_baseline.sample)"},
+                "cpu_baseline": cb,
+                "e2e": {"value": round(cb["value"], 4), "unit": UNIT, "h2d_bytes_per_step": 0,
+                        "d2h_bytes_per_step": 0}}
+        print(json.dumps(line), flush=True)
+        return
+
+    line = run_ours(args)
+    if line is None:
+        return
+    if args.gpus == 1 and not args.no_cpu_baseline:
+        try:
+            line["cpu_baseline"] = run_reference(args)
+        except Exception as e:  # the checker being unavailable must not hide the GPU numbers
+            line["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": os.cpu_count(), "kind": "unavailable",
+                                    "sample": str(e)[:200]}
+    print(json.dumps(line), flush=True)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,460 @@
+/* Stable key+index LSD radix sort for sm_100a ("onesweep": one histogram pass, then one fused
+ * rank+look-back+scatter pass per 8-bit digit), plus sequence/gather helpers.
+ *
+ * Replaces cstone::sortByKey(Gpu,...) = cub::DeviceRadixSort::SortPairs (reference primitives/primitives_gpu.cu:310-356),
+ * sequence (:56-63) and the gather kernels (:74-90).  Results are fully specified (stable ascending order), so
+ * parity is bit-exact against the CPU std::stable_sort path (primitives/gather.hpp:42-67).
+ *
+ * Per digit pass, a 512-thread CTA owns one tile of keys (dynamic tile ids, so predecessors are always resident):
+ *   warp-striped load -> per-warp digit ranks with match.any (stable: rank order == input order)
+ *   -> CTA digit histogram -> publish AGGREGATE -> decoupled look-back over predecessor tiles -> publish INCLUSIVE
+ *   -> keys/values staged in shared memory in locally sorted order -> run-coalesced stores.
+ * Algorithmic traffic: K (histogram read) + passes * 2 * (K + 4) bytes per element (200 B for u64 keys + u32 index).
+ */
+#include <algorithm>
+
+#include "common.cuh"
+#include "cstone_b200.h"
+
+namespace csb
+{
+
+namespace
+{
+
+constexpr int RADIX_BITS   = 8;
+constexpr int RADIX        = 1 << RADIX_BITS;
+constexpr int SORT_THREADS = 512;
+constexpr int SORT_WARPS   = SORT_THREADS / 32;
+
+constexpr uint32_t FLAG_AGG   = 1u << 30;
+constexpr uint32_t FLAG_INCL  = 2u << 30;
+constexpr uint32_t FLAG_MASK  = 3u << 30;
+constexpr uint32_t VALUE_MASK = ~FLAG_MASK;
+
+template<class K>
+struct SortCfg
+{
+    static constexpr int passes = sizeof(K);                   // 8-bit digits over all key bits
+    static constexpr int ipt    = sizeof(K) == 8 ? 12 : 16;    // items per thread
+    static constexpr int tile   = SORT_THREADS * ipt;
+    static constexpr size_t smemBytes =
+        size_t(tile) * sizeof(K) + size_t(tile) * 4 + size_t(SORT_WARPS) * RADIX * 4 + RADIX * 4 + 64 * 4;
+};
+
+/* ---------------------------------------------------------------- histogram of all digit places */
+
+template<class K>
+__global__ void __launch_bounds__(512) radixHistogramKernel(const K* __restrict__ keys, size_t n, uint32_t* globalHist)
+{
+    constexpr int P = SortCfg<K>::passes;
+    __shared__ uint32_t hist[P * RADIX];
+    for (int i = threadIdx.x; i < P * RADIX; i += blockDim.x)
+        hist[i] = 0;
+    __syncthreads();
+
+    size_t tid      = size_t(blockIdx.x) * blockDim.x + threadIdx.x;
+    size_t nthreads = size_t(gridDim.x) * blockDim.x;
+    for (size_t i = tid; i < n; i += nthreads)
+    {
+        K key = keys[i];
+#pragma unroll
+        for (int p = 0; p < P; ++p)
+        {
+            atomicAdd(&hist[p * RADIX + unsigned((key >> (RADIX_BITS * p)) & (RADIX - 1))], 1u);
+        }
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < P * RADIX; i += blockDim.x)
+    {
+        uint32_t c = hist[i];
+        if (c) { atomicAdd(&globalHist[i], c); }
+    }
+}
+
+//! one 256-thread block per digit place: in-place exclusive scan of the 256 bin counts
+__global__ void __launch_bounds__(RADIX) scanHistogramKernel(uint32_t* globalHist)
+{
+    __shared__ uint32_t warpSums[RADIX / 32];
+    uint32_t* h   = globalHist + blockIdx.x * RADIX;
+    unsigned lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    uint32_t v    = h[threadIdx.x];
+    uint32_t incl = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1)
+    {
+        uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= unsigned(o)) { incl += t; }
+    }
+    if (lane == 31) { warpSums[warp] = incl; }
+    __syncthreads();
+    uint32_t off = 0;
+    for (unsigned w = 0; w < warp; ++w)
+        off += warpSums[w];
+    h[threadIdx.x] = off + incl - v;
+}
+
+/* ---------------------------------------------------------------- one digit pass */
+
+template<class K, bool HAS_VALUES>
+__global__ void __launch_bounds__(SORT_THREADS, 2) onesweepKernel(const K* __restrict__ keysIn,
+                                                                  K* __restrict__ keysOut,
+                                                                  const uint32_t* __restrict__ valsIn,
+                                                                  uint32_t* __restrict__ valsOut,
+                                                                  size_t n,
+                                                                  int shift,
+                                                                  const uint32_t* __restrict__ digitBase,
+                                                                  volatile uint32_t* tileStates,
+                                                                  uint32_t* tileCounter)
+{
+    using Cfg          = SortCfg<K>;
+    constexpr int IPT  = Cfg::ipt;
+    constexpr int TILE = Cfg::tile;
+
+    extern __shared__ __align__(16) unsigned char smemRaw[];
+    K* keysS           = reinterpret_cast<K*>(smemRaw);
+    uint32_t* valsS    = reinterpret_cast<uint32_t*>(keysS + TILE);
+    uint32_t* warpHist = valsS + TILE;                  // [SORT_WARPS][RADIX]
+    uint32_t* binBase  = warpHist + SORT_WARPS * RADIX; // [RADIX] global base minus local offset
+    uint32_t* scratch  = binBase + RADIX;               // [64]
+
+    const unsigned tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+
+    if (tid == 0) { scratch[32] = atomicAdd(tileCounter, 1u); }
+    for (int i = tid; i < SORT_WARPS * RADIX; i += SORT_THREADS)
+        warpHist[i] = 0;
+    __syncthreads();
+    const uint32_t tileIdx = scratch[32];
+    const size_t tileBase  = size_t(tileIdx) * TILE;
+    const uint32_t tileCount = uint32_t(min(size_t(TILE), n - tileBase));
+
+    /* ---- load (warp-striped: element order == (warp, item, lane) order) */
+    K key[IPT];
+    const size_t warpBase = tileBase + size_t(warp) * 32 * IPT + lane;
+#pragma unroll
+    for (int i = 0; i < IPT; ++i)
+    {
+        size_t idx = warpBase + size_t(i) * 32;
+        key[i]     = idx < n ? keysIn[idx] : K(~K(0));
+    }
+
+    /* ---- stable ranks within the warp per digit */
+    uint32_t rank[IPT];
+    uint32_t* wh = warpHist + warp * RADIX;
+#pragma unroll
+    for (int i = 0; i < IPT; ++i)
+    {
+        unsigned d      = unsigned((key[i] >> shift) & (RADIX - 1));
+        unsigned peers  = __match_any_sync(0xffffffffu, d);
+        unsigned leader = __ffs(peers) - 1;
+        unsigned below  = __popc(peers & ((1u << lane) - 1u));
+        uint32_t pre    = 0;
+        if (lane == leader)
+        {
+            pre   = wh[d];
+            wh[d] = pre + __popc(peers);
+        }
+        __syncwarp();
+        pre     = __shfl_sync(0xffffffffu, pre, leader);
+        rank[i] = pre + below;
+    }
+    __syncthreads();
+
+    /* ---- CTA histogram: exclusive scan over warps per digit, then exclusive scan over digits */
+    uint32_t binCount = 0, incl = 0;
+    if (tid < RADIX)
+    {
+        uint32_t running = 0;
+#pragma unroll
+        for (int w = 0; w < SORT_WARPS; ++w)
+        {
+            uint32_t t              = warpHist[w * RADIX + tid];
+            warpHist[w * RADIX + tid] = running;
+            running += t;
+        }
+        binCount = running;
+        incl     = binCount;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1)
+        {
+            uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= unsigned(o)) { incl += t; }
+        }
+        if (lane == 31) { scratch[warp] = incl; }
+    }
+    __syncthreads();
+    if (tid < RADIX)
+    {
+        uint32_t off = 0;
+        for (unsigned w = 0; w < warp; ++w)
+            off += scratch[w];
+        uint32_t binOffset = off + incl - binCount; // position of this digit's run in the locally sorted tile
+
+        /* ---- decoupled look-back */
+        volatile uint32_t* myState = tileStates + size_t(tileIdx) * RADIX + tid;
+        uint32_t exclusive         = 0;
+        if (tileIdx == 0) { *myState = FLAG_INCL | binCount; }
+        else
+        {
+            *myState = FLAG_AGG | binCount;
+            for (long long t = (long long)tileIdx - 1; t >= 0; --t)
+            {
+                volatile uint32_t* p = tileStates + size_t(t) * RADIX + tid;
+                uint32_t s;
+                do
+                {
+                    s = *p;
+                } while ((s & FLAG_MASK) == 0);
+                exclusive += s & VALUE_MASK;
+                if (s & FLAG_INCL) { break; }
+            }
+            *myState = FLAG_INCL | (exclusive + binCount);
+        }
+        binBase[tid] = digitBase[tid] + exclusive - binOffset;
+#pragma unroll
+        for (int w = 0; w < SORT_WARPS; ++w)
+            warpHist[w * RADIX + tid] += binOffset;
+    }
+    __syncthreads();
+
+    /* ---- stage keys in locally sorted order */
+#pragma unroll
+    for (int i = 0; i < IPT; ++i)
+    {
+        unsigned d = unsigned((key[i] >> shift) & (RADIX - 1));
+        rank[i] += wh[d];
+        keysS[rank[i]] = key[i];
+    }
+    __syncthreads();
+
+    /* ---- run-coalesced key stores */
+    for (uint32_t j = tid; j < tileCount; j += SORT_THREADS)
+    {
+        K k        = keysS[j];
+        unsigned d = unsigned((k >> shift) & (RADIX - 1));
+        keysOut[uint32_t(binBase[d] + j)] = k; // 32-bit wrap-around is intended
+    }
+
+    if constexpr (HAS_VALUES)
+    {
+#pragma unroll
+        for (int i = 0; i < IPT; ++i)
+        {
+            size_t idx = warpBase + size_t(i) * 32;
+            if (idx < n) { valsS[rank[i]] = valsIn[idx]; }
+        }
+        __syncthreads();
+        for (uint32_t j = tid; j < tileCount; j += SORT_THREADS)
+        {
+            unsigned d = unsigned((keysS[j] >> shift) & (RADIX - 1));
+            valsOut[uint32_t(binBase[d] + j)] = valsS[j];
+        }
+    }
+}
+
+template<class K>
+size_t sortTempBytes(size_t n)
+{
+    using Cfg       = SortCfg<K>;
+    size_t numTiles = (n + Cfg::tile - 1) / Cfg::tile;
+    size_t words    = size_t(Cfg::passes) * RADIX      // digit histograms
+                   + 64                                // tile counters (one per pass)
+                   + size_t(Cfg::passes) * numTiles * RADIX; // look-back states
+    return words * sizeof(uint32_t) + 256;
+}
+
+template<class K>
+int sortByKey(K* keys, uint32_t* values, size_t n, K* keyBuf, uint32_t* valueBuf, void* tmp, size_t tmpBytes,
+              cudaStream_t stream)
+{
+    using Cfg = SortCfg<K>;
+    if (n < 2) { return 0; }
+    CSB_REQUIRE(n < (size_t(1) << 30), "sort_by_key supports fewer than 2^30 elements");
+    CSB_REQUIRE(tmpBytes >= sortTempBytes<K>(n), "sort_by_key temp storage too small");
+    CSB_REQUIRE(keyBuf != nullptr && (values == nullptr || valueBuf != nullptr), "sort_by_key needs double buffers");
+
+    static bool attrSet[64][2] = {};
+    int dev                    = 0;
+    CSB_CHECK(cudaGetDevice(&dev));
+    CSB_REQUIRE(dev < 64, "device ordinal too large");
+    if (!attrSet[dev][0])
+    {
+        CSB_CHECK(cudaFuncSetAttribute(onesweepKernel<K, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       int(Cfg::smemBytes)));
+        CSB_CHECK(cudaFuncSetAttribute(onesweepKernel<K, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       int(Cfg::smemBytes)));
+        attrSet[dev][0] = true;
+    }
+    int numSm = 0;
+    CSB_CHECK(cudaDeviceGetAttribute(&numSm, cudaDevAttrMultiProcessorCount, dev));
+
+    size_t numTiles      = (n + Cfg::tile - 1) / Cfg::tile;
+    uint32_t* hist       = reinterpret_cast<uint32_t*>((reinterpret_cast<uintptr_t>(tmp) + 255) & ~uintptr_t(255));
+    uint32_t* counters   = hist + Cfg::passes * RADIX;
+    uint32_t* tileStates = counters + 64;
+    size_t zeroBytes     = (size_t(Cfg::passes) * RADIX + 64 + size_t(Cfg::passes) * numTiles * RADIX) * 4;
+    CSB_CHECK(cudaMemsetAsync(hist, 0, zeroBytes, stream));
+
+    unsigned histGrid = unsigned(std::min<size_t>(size_t(numSm) * 4, (n + 511) / 512));
+    radixHistogramKernel<K><<<histGrid, 512, 0, stream>>>(keys, n, hist);
+    CSB_LAUNCH_CHECK();
+    scanHistogramKernel<<<Cfg::passes, RADIX, 0, stream>>>(hist);
+    CSB_LAUNCH_CHECK();
+
+    K* kin         = keys;
+    K* kout        = keyBuf;
+    uint32_t* vin  = values;
+    uint32_t* vout = valueBuf;
+    for (int p = 0; p < Cfg::passes; ++p)
+    {
+        if (values)
+        {
+            onesweepKernel<K, true><<<unsigned(numTiles), SORT_THREADS, Cfg::smemBytes, stream>>>(
+                kin, kout, vin, vout, n, p * RADIX_BITS, hist + p * RADIX, tileStates + size_t(p) * numTiles * RADIX,
+                counters + p);
+        }
+        else
+        {
+            onesweepKernel<K, false><<<unsigned(numTiles), SORT_THREADS, Cfg::smemBytes, stream>>>(
+                kin, kout, nullptr, nullptr, n, p * RADIX_BITS, hist + p * RADIX,
+                tileStates + size_t(p) * numTiles * RADIX, counters + p);
+        }
+        CSB_LAUNCH_CHECK();
+        std::swap(kin, kout);
+        std::swap(vin, vout);
+    }
+    // passes is even for both key widths, so the sorted data is back in keys/values
+    static_assert(Cfg::passes % 2 == 0);
+    return 0;
+}
+
+/* ---------------------------------------------------------------- sequence / gather */
+
+__global__ void sequenceKernel(uint32_t start, size_t n, uint32_t* out)
+{
+    size_t i = size_t(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i < n) { out[i] = start + uint32_t(i); }
+}
+
+template<class E>
+__global__ void gatherKernel(const uint32_t* __restrict__ ord, size_t n, const E* __restrict__ src, E* __restrict__ dst)
+{
+    size_t i = size_t(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i < n) { dst[i] = src[ord[i]]; }
+}
+
+template<class E>
+struct Ptr4
+{
+    const E* src[4];
+    E* dst[4];
+};
+
+template<class E>
+__global__ void gather4Kernel(const uint32_t* __restrict__ ord, size_t n, Ptr4<E> p)
+{
+    size_t i = size_t(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i < n)
+    {
+        uint32_t o = ord[i];
+        E a = p.src[0][o], b = p.src[1][o], c = p.src[2][o], d = p.src[3][o];
+        p.dst[0][i] = a;
+        p.dst[1][i] = b;
+        p.dst[2][i] = c;
+        p.dst[3][i] = d;
+    }
+}
+
+} // namespace
+
+int sortByKeyU64(uint64_t* keys, uint32_t* values, size_t n, uint64_t* keyBuf, uint32_t* valueBuf, void* tmp,
+                 size_t tmpBytes, cudaStream_t stream)
+{
+    return sortByKey<uint64_t>(keys, values, n, keyBuf, valueBuf, tmp, tmpBytes, stream);
+}
+
+int sortByKeyU32(uint32_t* keys, uint32_t* values, size_t n, uint32_t* keyBuf, uint32_t* valueBuf, void* tmp,
+                 size_t tmpBytes, cudaStream_t stream)
+{
+    return sortByKey<uint32_t>(keys, values, n, keyBuf, valueBuf, tmp, tmpBytes, stream);
+}
+
+size_t sortTempBytesU64(size_t n) { return sortTempBytes<uint64_t>(n); }
+size_t sortTempBytesU32(size_t n) { return sortTempBytes<uint32_t>(n); }
+
+} // namespace csb
+
+extern "C"
+{
+
+size_t cs_sort_by_key_temp_bytes_u32(size_t n) { return csb::sortTempBytesU32(n); }
+size_t cs_sort_by_key_temp_bytes_u64(size_t n) { return csb::sortTempBytesU64(n); }
+
+int cs_sort_by_key_u32(uint32_t* keys, uint32_t* values, size_t n, uint32_t* keyBuf, uint32_t* valueBuf, void* tmp,
+                       size_t tmpBytes, void* stream)
+{
+    return csb::sortByKeyU32(keys, values, n, keyBuf, valueBuf, tmp, tmpBytes, cudaStream_t(stream));
+}
+
+int cs_sort_by_key_u64(uint64_t* keys, uint32_t* values, size_t n, uint64_t* keyBuf, uint32_t* valueBuf, void* tmp,
+                       size_t tmpBytes, void* stream)
+{
+    return csb::sortByKeyU64(keys, values, n, keyBuf, valueBuf, tmp, tmpBytes, cudaStream_t(stream));
+}
+
+int cs_sequence_u32(uint32_t start, size_t n, uint32_t* out, void* stream)
+{
+    if (n == 0) { return 0; }
+    csb::sequenceKernel<<<csb::iceil(n, 256), 256, 0, cudaStream_t(stream)>>>(start, n, out);
+    CSB_LAUNCH_CHECK();
+    return 0;
+}
+
+int cs_gather(const uint32_t* ordering, size_t n, const void* src, void* dst, int elemBytes, void* stream)
+{
+    CSB_REQUIRE(elemBytes == 4 || elemBytes == 8, "gather supports 4- and 8-byte elements");
+    if (n == 0) { return 0; }
+    if (elemBytes == 4)
+    {
+        csb::gatherKernel<uint32_t><<<csb::iceil(n, 256), 256, 0, cudaStream_t(stream)>>>(
+            ordering, n, static_cast<const uint32_t*>(src), static_cast<uint32_t*>(dst));
+    }
+    else
+    {
+        csb::gatherKernel<uint64_t><<<csb::iceil(n, 256), 256, 0, cudaStream_t(stream)>>>(
+            ordering, n, static_cast<const uint64_t*>(src), static_cast<uint64_t*>(dst));
+    }
+    CSB_LAUNCH_CHECK();
+    return 0;
+}
+
+int cs_gather4(const uint32_t* ordering, size_t n, const void* const* src4, void* const* dst4, int elemBytes,
+               void* stream)
+{
+    CSB_REQUIRE(elemBytes == 4 || elemBytes == 8, "gather supports 4- and 8-byte elements");
+    if (n == 0) { return 0; }
+    if (elemBytes == 4)
+    {
+        csb::Ptr4<uint32_t> p;
+        for (int i = 0; i < 4; ++i)
+        {
+            p.src[i] = static_cast<const uint32_t*>(src4[i]);
+            p.dst[i] = static_cast<uint32_t*>(dst4[i]);
+        }
+        csb::gather4Kernel<uint32_t><<<csb::iceil(n, 256), 256, 0, cudaStream_t(stream)>>>(ordering, n, p);
+    }
+    else
+    {
+        csb::Ptr4<uint64_t> p;
+        for (int i = 0; i < 4; ++i)
+        {
+            p.src[i] = static_cast<const uint64_t*>(src4[i]);
+            p.dst[i] = static_cast<uint64_t*>(dst4[i]);
+        }
+        csb::gather4Kernel<uint64_t><<<csb::iceil(n, 256), 256, 0, cudaStream_t(stream)>>>(ordering, n, p);
+    }
+    CSB_LAUNCH_CHECK();
+    return 0;
+}
+
+} // extern "C"

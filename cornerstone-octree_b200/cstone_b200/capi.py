@@ -1,0 +1,273 @@
+"""ctypes binding of libcstone_b200.so (the C ABI declared in include/cstone_b200.h).
+
+PyTorch is used only as the owner of device memory and streams: tensors are passed to the C ABI as raw device
+pointers.  There is NO fallback: if the shared library is missing or a call fails, an exception is raised.
+"""
+import ctypes as C
+import os
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libcstone_b200.so")
+
+KEY_DTYPES = {"u32": torch.uint32, "u64": torch.uint64}
+REAL_DTYPES = {"f": torch.float32, "d": torch.float64}
+MAXLEVEL = {"u32": 10, "u64": 21}
+
+
+class CstoneError(RuntimeError):
+    pass
+
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise CstoneError(f"{LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; "
+                              "g.build()'` (there is no CPU fallback)")
+        _lib = C.CDLL(LIB_PATH)
+        _lib.cs_last_error.restype = C.c_char_p
+        _lib.cs_kernel_launch_count.restype = C.c_uint64
+        for name in ("cs_sort_by_key_temp_bytes_u32", "cs_sort_by_key_temp_bytes_u64", "cs_scan_temp_bytes",
+                     "cs_build_octree_temp_bytes_u32", "cs_build_octree_temp_bytes_u64", "cs_node_ops_temp_bytes"):
+            getattr(_lib, name).restype = C.c_size_t
+    return _lib
+
+
+def _check(status, what):
+    if status != 0:
+        raise CstoneError(f"{what} failed with status {status}: {lib().cs_last_error().decode()}")
+
+
+def _ptr(t):
+    if t is None:
+        return C.c_void_p(0)
+    assert t.is_cuda and t.is_contiguous(), "device-resident contiguous tensors only"
+    return C.c_void_p(t.data_ptr())
+
+
+def _stream():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _box(lim, bnd):
+    lim_a = (C.c_double * 6)(*[float(v) for v in lim])
+    bnd_a = (C.c_int * 3)(*[int(v) for v in bnd])
+    return lim_a, bnd_a
+
+
+def key_suffix(t):
+    return {torch.uint32: "u32", torch.int32: "u32", torch.uint64: "u64", torch.int64: "u64"}[t.dtype]
+
+
+def real_suffix(t):
+    return {torch.float32: "f", torch.float64: "d"}[t.dtype]
+
+
+def kernel_launch_count():
+    return int(lib().cs_kernel_launch_count())
+
+
+# ---------------------------------------------------------------- SFC keys
+def compute_sfc_keys(x, y, z, keys, lim, bnd, kind=0, n=None):
+    """keys[i] = sfc3D(x[i], y[i], z[i], box) in place (removeKey entries are preserved)"""
+    n = x.numel() if n is None else n
+    combo = key_suffix(keys) + real_suffix(x)
+    lim_a, bnd_a = _box(lim, bnd)
+    f = getattr(lib(), "cs_compute_sfc_keys_" + combo)
+    _check(f(C.c_int(kind), _ptr(x), _ptr(y), _ptr(z), _ptr(keys), C.c_size_t(n), lim_a, bnd_a, _stream()),
+           "cs_compute_sfc_keys_" + combo)
+    return keys
+
+
+# ---------------------------------------------------------------- sort / gather / scan
+def sort_by_key(keys, values=None):
+    """stable ascending sort of keys (and values) in place"""
+    n = keys.numel()
+    kt = key_suffix(keys)
+    tmp_bytes = getattr(lib(), "cs_sort_by_key_temp_bytes_" + kt)(C.c_size_t(n))
+    key_buf = torch.empty_like(keys)
+    val_buf = torch.empty_like(values) if values is not None else None
+    tmp = torch.empty(tmp_bytes, dtype=torch.uint8, device=keys.device)
+    f = getattr(lib(), "cs_sort_by_key_" + kt)
+    _check(f(_ptr(keys), _ptr(values), C.c_size_t(n), _ptr(key_buf), _ptr(val_buf), _ptr(tmp), C.c_size_t(tmp_bytes),
+             _stream()), "cs_sort_by_key_" + kt)
+    return keys, values
+
+
+def sequence(start, n, device):
+    out = torch.empty(n, dtype=torch.uint32, device=device)
+    _check(lib().cs_sequence_u32(C.c_uint32(start), C.c_size_t(n), _ptr(out), _stream()), "cs_sequence_u32")
+    return out
+
+
+def gather(ordering, src):
+    dst = torch.empty(ordering.numel(), dtype=src.dtype, device=src.device)
+    _check(lib().cs_gather(_ptr(ordering), C.c_size_t(ordering.numel()), _ptr(src), _ptr(dst),
+                           C.c_int(src.element_size()), _stream()), "cs_gather")
+    return dst
+
+
+def gather4(ordering, srcs):
+    n = ordering.numel()
+    dsts = [torch.empty(n, dtype=s.dtype, device=s.device) for s in srcs]
+    src_a = (C.c_void_p * 4)(*[s.data_ptr() for s in srcs])
+    dst_a = (C.c_void_p * 4)(*[d.data_ptr() for d in dsts])
+    _check(lib().cs_gather4(_ptr(ordering), C.c_size_t(n), src_a, dst_a, C.c_int(srcs[0].element_size()), _stream()),
+           "cs_gather4")
+    return dsts
+
+
+def exclusive_scan(values):
+    n = values.numel()
+    out = torch.empty_like(values)
+    tmp = torch.empty(lib().cs_scan_temp_bytes(C.c_size_t(n)), dtype=torch.uint8, device=values.device)
+    _check(lib().cs_exclusive_scan_u32(_ptr(values), _ptr(out), C.c_size_t(n), _ptr(tmp), _stream()),
+           "cs_exclusive_scan_u32")
+    return out
+
+
+# ---------------------------------------------------------------- csarray
+def compute_node_counts(leaves, keys, max_count=0xFFFFFFFF, n=None):
+    kt = key_suffix(leaves)
+    nl = leaves.numel() - 1
+    n = keys.numel() if n is None else n
+    counts = torch.empty(nl, dtype=torch.uint32, device=leaves.device)
+    f = getattr(lib(), "cs_compute_node_counts_" + kt)
+    _check(f(_ptr(leaves), _ptr(counts), C.c_int(nl), _ptr(keys), C.c_size_t(n), C.c_uint32(max_count), _stream()),
+           "cs_compute_node_counts_" + kt)
+    return counts
+
+
+def compute_node_ops(leaves, counts, bucket):
+    """returns (scanned nodeOps[numLeaves+1], newNumLeaves, converged)"""
+    kt = key_suffix(leaves)
+    nl = leaves.numel() - 1
+    ops = torch.empty(nl + 1, dtype=torch.int32, device=leaves.device)
+    tmp = torch.empty(lib().cs_node_ops_temp_bytes(C.c_int(nl)), dtype=torch.uint8, device=leaves.device)
+    new_n, conv = C.c_int(0), C.c_int(0)
+    f = getattr(lib(), "cs_compute_node_ops_" + kt)
+    _check(f(_ptr(leaves), C.c_int(nl), _ptr(counts), C.c_uint32(bucket), _ptr(ops), _ptr(tmp), C.byref(new_n),
+             C.byref(conv), _stream()), "cs_compute_node_ops_" + kt)
+    return ops, new_n.value, bool(conv.value)
+
+
+def rebalance_tree(leaves, ops, new_num_leaves):
+    kt = key_suffix(leaves)
+    nl = leaves.numel() - 1
+    new_leaves = torch.empty(new_num_leaves + 1, dtype=leaves.dtype, device=leaves.device)
+    f = getattr(lib(), "cs_rebalance_tree_" + kt)
+    _check(f(_ptr(leaves), C.c_int(nl), C.c_int(new_num_leaves), _ptr(ops), _ptr(new_leaves), _stream()),
+           "cs_rebalance_tree_" + kt)
+    return new_leaves
+
+
+def compute_octree(keys, bucket, capacity=None, n=None):
+    """converged cornerstone leaf array + counts for sorted keys"""
+    kt = key_suffix(keys)
+    n = keys.numel() if n is None else n
+    capacity = capacity or max(4096, 16 * (n // max(1, bucket)) + 4096)
+    while True:
+        leaves = torch.empty(capacity + 1, dtype=keys.dtype, device=keys.device)
+        counts = torch.empty(capacity, dtype=torch.uint32, device=keys.device)
+        nl = C.c_int(0)
+        f = getattr(lib(), "cs_compute_octree_" + kt)
+        st = f(_ptr(keys), C.c_size_t(n), C.c_uint32(bucket), _ptr(leaves), _ptr(counts), C.c_int(capacity),
+               C.byref(nl), _stream())
+        if st == 3:
+            capacity = int(nl.value * 1.5) + 16
+            continue
+        _check(st, "cs_compute_octree_" + kt)
+        return leaves[:nl.value + 1].clone(), counts[:nl.value].clone()
+
+
+# ---------------------------------------------------------------- octree
+class Octree:
+    """device-resident OctreeData (tree/octree.hpp:285-360)"""
+
+    def __init__(self, leaves):
+        kt = key_suffix(leaves)
+        dev = leaves.device
+        nl = leaves.numel() - 1
+        self.num_leaves = nl
+        self.num_internal = (nl - 1) // 7
+        self.num_nodes = nl + self.num_internal
+        nn = self.num_nodes
+        self.leaves = leaves
+        self.prefixes = torch.empty(nn, dtype=leaves.dtype, device=dev)
+        self.child_offsets = torch.empty(nn + 1, dtype=torch.int32, device=dev)
+        self.parents = torch.empty(max(1, (nn - 1) // 8), dtype=torch.int32, device=dev)
+        self.level_range = torch.empty(MAXLEVEL[kt] + 2, dtype=torch.int32, device=dev)
+        self.internal_to_leaf = torch.empty(nn, dtype=torch.int32, device=dev)
+        self.leaf_to_internal = torch.empty(nn, dtype=torch.int32, device=dev)
+        tmp_bytes = getattr(lib(), "cs_build_octree_temp_bytes_" + kt)(C.c_int(nl))
+        tmp = torch.empty(tmp_bytes, dtype=torch.uint8, device=dev)
+        f = getattr(lib(), "cs_build_octree_" + kt)
+        _check(f(_ptr(leaves), C.c_int(nl), _ptr(self.prefixes), _ptr(self.child_offsets), _ptr(self.parents),
+                 _ptr(self.level_range), _ptr(self.internal_to_leaf), _ptr(self.leaf_to_internal), _ptr(tmp),
+                 C.c_size_t(tmp_bytes), _stream()), "cs_build_octree_" + kt)
+
+
+def compute_geo_centers(prefixes, real_dtype, lim, bnd, kind=0):
+    n = prefixes.numel()
+    combo = key_suffix(prefixes) + {torch.float32: "f", torch.float64: "d"}[real_dtype]
+    centers = torch.empty((n, 3), dtype=real_dtype, device=prefixes.device)
+    sizes = torch.empty((n, 3), dtype=real_dtype, device=prefixes.device)
+    lim_a, bnd_a = _box(lim, bnd)
+    f = getattr(lib(), "cs_compute_geo_centers_" + combo)
+    _check(f(C.c_int(kind), _ptr(prefixes), C.c_int(n), _ptr(centers), _ptr(sizes), lim_a, bnd_a, _stream()),
+           "cs_compute_geo_centers_" + combo)
+    return centers, sizes
+
+
+def upsweep_sum(kt, level_range_host, child_offsets, counts):
+    lr = (C.c_int * len(level_range_host))(*[int(v) for v in level_range_host])
+    _check(lib().cs_upsweep_sum(C.c_int(MAXLEVEL[kt]), lr, _ptr(child_offsets), _ptr(counts), _stream()),
+           "cs_upsweep_sum")
+    return counts
+
+
+# ---------------------------------------------------------------- halos
+def compute_bounding_boxes(x, y, z, h, layout, first, last, scale, search_centers):
+    """in: search_centers[leaf] = init point; out: (centers, sizes) of the per-leaf search boxes"""
+    sfx = real_suffix(x)
+    sc = search_centers.clone()
+    ss = torch.zeros_like(sc)
+    scale_arg = C.c_float(scale) if sfx == "f" else C.c_double(scale)
+    f = getattr(lib(), "cs_compute_bounding_boxes_" + sfx)
+    _check(f(_ptr(x), _ptr(y), _ptr(z), _ptr(h), _ptr(layout), C.c_int(first), C.c_int(last), scale_arg, _ptr(sc),
+             _ptr(ss), _stream()), "cs_compute_bounding_boxes_" + sfx)
+    return sc, ss
+
+
+def find_halos(tree, centers, sizes, sc, ss, lim, bnd, first, last, flags=None):
+    combo = key_suffix(tree.prefixes) + real_suffix(centers)
+    if flags is None:
+        flags = torch.zeros(tree.num_nodes, dtype=torch.uint8, device=centers.device)
+    lim_a, bnd_a = _box(lim, bnd)
+    f = getattr(lib(), "cs_find_halos_" + combo)
+    _check(f(_ptr(tree.prefixes), _ptr(tree.child_offsets), _ptr(tree.parents), _ptr(centers), _ptr(sizes),
+             _ptr(tree.leaves), _ptr(sc), _ptr(ss), lim_a, bnd_a, C.c_int(first), C.c_int(last), _ptr(flags),
+             _stream()), "cs_find_halos_" + combo)
+    return flags
+
+
+# ---------------------------------------------------------------- neighbours
+def find_neighbors(x, y, z, h, first, last, lim, bnd, tree, layout, centers, sizes, ngmax, neighbors=None,
+                   counts=None):
+    sfx = real_suffix(x)
+    nloc = last - first
+    if neighbors is None:
+        neighbors = torch.zeros(nloc * ngmax, dtype=torch.uint32, device=x.device)
+    if counts is None:
+        counts = torch.zeros(nloc, dtype=torch.uint32, device=x.device)
+    lim_a, bnd_a = _box(lim, bnd)
+    f = getattr(lib(), "cs_find_neighbors_" + sfx)
+    _check(f(_ptr(x), _ptr(y), _ptr(z), _ptr(h), C.c_uint32(first), C.c_uint32(last), lim_a, bnd_a,
+             _ptr(tree.child_offsets), _ptr(tree.parents), _ptr(tree.internal_to_leaf), _ptr(layout), _ptr(centers),
+             _ptr(sizes), C.c_uint32(ngmax), _ptr(neighbors), _ptr(counts), _stream()), "cs_find_neighbors_" + sfx)
+    return neighbors.view(nloc, ngmax), counts

@@ -1,0 +1,170 @@
+/* cornerstone-b200 C ABI — the drop-in boundary for the Cornerstone domain-sync hot path on B200 (sm_100a).
+ *
+ * Every entry point replaces one GPU entry point of the reference (sekelle/cornerstone-octree); the reference
+ * declaration it stands in for is cited as file:line relative to /root/reference/include/cstone.  INTEGRATION.md
+ * shows the forwarding stubs a maintainer adds on the reference side.
+ *
+ * Conventions
+ *  - plain C: pointers + sizes only. Unless stated otherwise all array pointers are DEVICE pointers, `stream` is a
+ *    cudaStream_t passed as void* (NULL = default stream) and work is enqueued asynchronously on it.
+ *  - functions whose results are needed on the host (sizes, convergence flags) synchronise the stream internally and
+ *    say so.
+ *  - suffixes: key type u32|u64, coordinate type f|d: *_u32f (uint32_t,float) *_u64f (uint64_t,float)
+ *    *_u64d (uint64_t,double).  `kind`: 0 = Hilbert, 1 = Morton.
+ *  - box: `lim` = host pointer to {xmin,xmax,ymin,ymax,zmin,zmax} (double, converted to the coordinate type exactly
+ *    like cstone::Box<T>'s constructor, sfc/box.hpp:100-122), `bnd` = host pointer to 3 ints, BoundaryType values
+ *    0 open, 1 periodic, 2 fixed, 3 cubic_open (sfc/box.hpp:78-84).
+ *  - return value: 0 on success; non-zero on failure with a message retrievable through cs_last_error().  The C++
+ *    forwarders turn CUDA failures into the reference's print+exit behaviour (cuda/errorcheck.cuh:15-27) and
+ *    contract violations into std::runtime_error (primitives_gpu.cu:338).
+ *  - no CPU fallback exists: without a CUDA device every compute call fails with a non-zero status.
+ */
+#ifndef CSTONE_B200_H
+#define CSTONE_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C"
+{
+#endif
+
+/* ---- library ---- */
+const char* cs_last_error(void);
+int cs_version(void);
+/* number of CUDA kernels launched by this library in the calling process since load (for bench.py's gpu_launches) */
+uint64_t cs_kernel_launch_count(void);
+
+/* ---- SFC keys: computeSfcKeys(Gpu, x,y,z, keys, n, box)  sfc/sfc_gpu.h:24-26, sfc/sfc_gpu.cu:23-62 ----
+ * keys[i] = sfc3D(x[i],y[i],z[i], box) unless keys[i] == removeKey = 2^(3*maxTreeLevel) (sfc/sfc.hpp:274). */
+int cs_compute_sfc_keys_u32f(int kind, const float* x, const float* y, const float* z, uint32_t* keys, size_t n,
+                             const double* lim, const int* bnd, void* stream);
+int cs_compute_sfc_keys_u64f(int kind, const float* x, const float* y, const float* z, uint64_t* keys, size_t n,
+                             const double* lim, const int* bnd, void* stream);
+int cs_compute_sfc_keys_u64d(int kind, const double* x, const double* y, const double* z, uint64_t* keys, size_t n,
+                             const double* lim, const int* bnd, void* stream);
+
+/* ---- key+index sort: sortByKey(Gpu, first,last, values, keyBuf, valueBuf, tmp, tmpBytes)
+ *      primitives/primitives_gpu.h:115-155, primitives_gpu.cu:310-356 ----
+ * Stable ascending LSD radix sort of (key, uint32 value) pairs over all key bits; the result is left in
+ * keys/values (values may be NULL for a keys-only sort).  keyBuf/valueBuf: n elements each; tmp: at least
+ * cs_sort_by_key_temp_bytes_*(n) bytes.  n < 2^30. */
+size_t cs_sort_by_key_temp_bytes_u32(size_t n);
+size_t cs_sort_by_key_temp_bytes_u64(size_t n);
+int cs_sort_by_key_u32(uint32_t* keys, uint32_t* values, size_t n, uint32_t* keyBuf, uint32_t* valueBuf, void* tmp,
+                       size_t tmpBytes, void* stream);
+int cs_sort_by_key_u64(uint64_t* keys, uint32_t* values, size_t n, uint64_t* keyBuf, uint32_t* valueBuf, void* tmp,
+                       size_t tmpBytes, void* stream);
+
+/* sequence(Gpu, start, n, out)  primitives_gpu.h:60-63 : out[i] = start + i */
+int cs_sequence_u32(uint32_t start, size_t n, uint32_t* out, void* stream);
+
+/* gather(Gpu, ordering, src, dst): dst[i] = src[ordering[i]]  primitives_gpu.h:30-42, primitives_gpu.cu:74-90.
+ * elemBytes in {4, 8}. */
+int cs_gather(const uint32_t* ordering, size_t n, const void* src, void* dst, int elemBytes, void* stream);
+/* fused form of gatherArrays(x,y,z,h) (domain/layout.hpp:230-261): one ordering read feeds four payload streams */
+int cs_gather4(const uint32_t* ordering, size_t n, const void* const* src4, void* const* dst4, int elemBytes,
+               void* stream);
+
+/* exclusiveScan(Gpu, in, in+n, out)  primitives_gpu.h:66-72 ; tmp >= cs_scan_temp_bytes(n) */
+size_t cs_scan_temp_bytes(size_t n);
+int cs_exclusive_scan_u32(const uint32_t* in, uint32_t* out, size_t n, void* tmp, void* stream);
+
+/* ---- cornerstone leaf array (tree/csarray_gpu.h:41-82, csarray_gpu.cu) ----
+ * computeNodeCountsGpu: counts[i] = min(#keys in [leaves[i], leaves[i+1]), maxCount); keys sorted ascending */
+int cs_compute_node_counts_u32(const uint32_t* leaves, uint32_t* counts, int numLeaves, const uint32_t* keys, size_t n,
+                               uint32_t maxCount, void* stream);
+int cs_compute_node_counts_u64(const uint64_t* leaves, uint32_t* counts, int numLeaves, const uint64_t* keys, size_t n,
+                               uint32_t maxCount, void* stream);
+/* computeNodeOpsGpu (csarray_gpu.cu:182-205): nodeOps[numLeaves+1] <- exclusive scan of the rebalance decisions
+ * (0 merge, 1 keep, 8/64/512/4096 split).  Synchronises; *newNumLeaves (host) = nodeOps[numLeaves],
+ * *converged (host) = 1 iff every decision was 1.  tmp >= cs_node_ops_temp_bytes(numLeaves). */
+size_t cs_node_ops_temp_bytes(int numLeaves);
+int cs_compute_node_ops_u32(const uint32_t* leaves, int numLeaves, const uint32_t* counts, uint32_t bucketSize,
+                            int* nodeOps, void* tmp, int* newNumLeaves, int* converged, void* stream);
+int cs_compute_node_ops_u64(const uint64_t* leaves, int numLeaves, const uint32_t* counts, uint32_t bucketSize,
+                            int* nodeOps, void* tmp, int* newNumLeaves, int* converged, void* stream);
+/* rebalanceTreeGpu (csarray_gpu.cu:212-231): newLeaves[newNumLeaves+1] from scanned nodeOps */
+int cs_rebalance_tree_u32(const uint32_t* leaves, int numLeaves, int newNumLeaves, const int* nodeOps,
+                          uint32_t* newLeaves, void* stream);
+int cs_rebalance_tree_u64(const uint64_t* leaves, int numLeaves, int newNumLeaves, const int* nodeOps,
+                          uint64_t* newLeaves, void* stream);
+/* computeOctree (csarray.hpp:429-440 / test/unit_cuda/tree/csarray.cu:164-185): converge a leaf array from the root
+ * for sorted keys.  leaves: capacity+1 keys, counts: capacity.  Synchronises; returns the leaf count in
+ * *numLeaves (host), status 3 if capacity is too small (then *numLeaves = required). */
+int cs_compute_octree_u32(const uint32_t* keys, size_t n, uint32_t bucketSize, uint32_t* leaves, uint32_t* counts,
+                          int capacity, int* numLeaves, void* stream);
+int cs_compute_octree_u64(const uint64_t* keys, size_t n, uint32_t bucketSize, uint64_t* leaves, uint32_t* counts,
+                          int capacity, int* numLeaves, void* stream);
+
+/* ---- internal octree: buildOctreeGpu(cstoneTree, OctreeView)  tree/octree_gpu.h:35-52, octree_gpu.cu:139-168 ----
+ * OctreeData layout (tree/octree.hpp:285-360): prefixes[numNodes], childOffsets[numNodes] (0 = leaf),
+ * parents[(numNodes-1)/8], levelRange[maxTreeLevel+2] (device), internalToLeaf[numNodes], leafToInternal[numNodes]
+ * with numInternal = (numLeaves-1)/7, numNodes = numLeaves+numInternal.  tmp >= cs_build_octree_temp_bytes_*. */
+size_t cs_build_octree_temp_bytes_u32(int numLeaves);
+size_t cs_build_octree_temp_bytes_u64(int numLeaves);
+int cs_build_octree_u32(const uint32_t* leaves, int numLeaves, uint32_t* prefixes, int* childOffsets, int* parents,
+                        int* levelRange, int* internalToLeaf, int* leafToInternal, void* tmp, size_t tmpBytes,
+                        void* stream);
+int cs_build_octree_u64(const uint64_t* leaves, int numLeaves, uint64_t* prefixes, int* childOffsets, int* parents,
+                        int* levelRange, int* internalToLeaf, int* leafToInternal, void* tmp, size_t tmpBytes,
+                        void* stream);
+/* upsweepSumGpu (octree_gpu.h:66-71, octree_gpu.cu:205-236): counts[node] = min(sum of 8 children, 2^32-1);
+ * levelRange is a HOST pointer here (as in the reference) */
+int cs_upsweep_sum(int maxLevel, const int* levelRangeHost, const int* childOffsets, uint32_t* counts, void* stream);
+
+/* computeGeoCentersGpu (focus/source_center_gpu.h:100-106, source_center_gpu.cu:212-237): centers/sizes are
+ * Vec3<T>[numNodes] (3 consecutive T).  kind selects the curve used to decode node boxes (the reference always uses
+ * Hilbert through SfcKind, sfc/sfc.hpp:39-40). */
+int cs_compute_geo_centers_u32f(int kind, const uint32_t* prefixes, int numNodes, float* centers, float* sizes,
+                                const double* lim, const int* bnd, void* stream);
+int cs_compute_geo_centers_u64f(int kind, const uint64_t* prefixes, int numNodes, float* centers, float* sizes,
+                                const double* lim, const int* bnd, void* stream);
+int cs_compute_geo_centers_u64d(int kind, const uint64_t* prefixes, int numNodes, double* centers, double* sizes,
+                                const double* lim, const int* bnd, void* stream);
+
+/* ---- halo discovery ----
+ * computeBoundingBoxGpu (source_center_gpu.h:40-52, source_center_gpu.cu:23-92): per leaf in [firstLeaf,lastLeaf)
+ * the AABB of particle spheres of radius h*scale, initialised with searchCenters[leaf] */
+int cs_compute_bounding_boxes_f(const float* x, const float* y, const float* z, const float* h, const uint32_t* layout,
+                                int firstLeaf, int lastLeaf, float scale, float* searchCenters, float* searchSizes,
+                                void* stream);
+int cs_compute_bounding_boxes_d(const double* x, const double* y, const double* z, const double* h,
+                                const uint32_t* layout, int firstLeaf, int lastLeaf, double scale,
+                                double* searchCenters, double* searchSizes, void* stream);
+/* findHalosGpu (traversal/collisions_gpu.h:46-58, collisions_gpu.cu:23-88): flags[numNodes] must be zeroed by the
+ * caller unless accumulating */
+int cs_find_halos_u32f(const uint32_t* prefixes, const int* childOffsets, const int* parents, const float* centers,
+                       const float* sizes, const uint32_t* leaves, const float* searchCenters,
+                       const float* searchSizes, const double* lim, const int* bnd, int firstLeaf, int lastLeaf,
+                       uint8_t* flags, void* stream);
+int cs_find_halos_u64f(const uint64_t* prefixes, const int* childOffsets, const int* parents, const float* centers,
+                       const float* sizes, const uint64_t* leaves, const float* searchCenters,
+                       const float* searchSizes, const double* lim, const int* bnd, int firstLeaf, int lastLeaf,
+                       uint8_t* flags, void* stream);
+int cs_find_halos_u64d(const uint64_t* prefixes, const int* childOffsets, const int* parents, const double* centers,
+                       const double* sizes, const uint64_t* leaves, const double* searchCenters,
+                       const double* searchSizes, const double* lim, const int* bnd, int firstLeaf, int lastLeaf,
+                       uint8_t* flags, void* stream);
+
+/* ---- neighbour search: findNeighbors(x,y,z,h, firstId,lastId, box, OctreeNsView, ngmax, neighbors, neighborsCount)
+ *      findneighbors.hpp:156-177 (the reference has no GPU function producing this layout) ----
+ * neighbors[(i-firstId)*ngmax + k] (ascending particle index, truncated at ngmax), neighborsCount[i-firstId]
+ * (not truncated).  Tree arrays as in OctreeNsView (tree/octree.hpp:259-283); layout[numLeaves+1]. */
+int cs_find_neighbors_f(const float* x, const float* y, const float* z, const float* h, uint32_t firstId,
+                        uint32_t lastId, const double* lim, const int* bnd, const int* childOffsets,
+                        const int* parents, const int* internalToLeaf, const uint32_t* layout, const float* centers,
+                        const float* sizes, uint32_t ngmax, uint32_t* neighbors, uint32_t* neighborsCount,
+                        void* stream);
+int cs_find_neighbors_d(const double* x, const double* y, const double* z, const double* h, uint32_t firstId,
+                        uint32_t lastId, const double* lim, const int* bnd, const int* childOffsets,
+                        const int* parents, const int* internalToLeaf, const uint32_t* layout, const double* centers,
+                        const double* sizes, uint32_t ngmax, uint32_t* neighbors, uint32_t* neighborsCount,
+                        void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+
+#endif /* CSTONE_B200_H */

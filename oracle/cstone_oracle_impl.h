@@ -734,7 +734,7 @@ typedef struct
 static int KT(orc_nb_continue)(int idx, void* vctx)
 {
     KT(OrcNbCtx)* c = (KT(OrcNbCtx)*)vctx;
-    REAL n2        = 0;
+    REAL sq[3];
     for (int d = 0; d < 3; ++d)
     {
         REAL dx;
@@ -747,9 +747,10 @@ static int KT(orc_nb_continue)(int idx, void* vctx)
         else { dx = RFABS(c->centers[3 * idx + d] - c->p[d]) - c->sizes[3 * idx + d]; }
         dx += RFABS(dx);
         dx *= (REAL)0.5;
-        /* util/array.hpp norm2: x*x + y*y + z*z, left to right */
-        n2 = d == 0 ? dx * dx : n2 + dx * dx;
+        sq[d] = dx * dx;
     }
+    /* util/array.hpp:236-240,316-320 norm2 = dot(a,a) = ((a[Is]*a[Is]) + ...), a unary RIGHT fold: x*x + (y*y + z*z) */
+    REAL n2 = sq[0] + (sq[1] + sq[2]);
     return n2 < c->cellRadiusSq;
 }
 

@@ -1,0 +1,337 @@
+"""GPU parity tests: every stage of the hot path, called through the C ABI (cstone_b200.capi -> libcstone_b200.so),
+compared bit-for-bit with the oracle (oracle/liboracle.so) and, when present, with the unmodified reference
+(oracle/_ref/libcstone_ref.so) on the same seeded inputs.  Run with `pytest -m gpu` on the B200 box."""
+import numpy as np
+import pytest
+import torch
+
+from _libs import COMBOS, KEYS, MAXLEVEL, key_of, oracle, real_of, ref
+from _util import const_h, gaussian_particles, plummer_particles, uniform_particles
+
+pytestmark = pytest.mark.gpu
+
+DEV = "cuda:0"
+
+
+def capi():
+    from cstone_b200 import capi as c
+    return c
+
+
+def dev(a):
+    return torch.from_numpy(np.ascontiguousarray(a)).to(DEV)
+
+
+def host(t):
+    return t.cpu().numpy()
+
+
+def checkers():
+    out = [("oracle", oracle())]
+    if ref() is not None:
+        out.append(("reference", ref()))
+    return out
+
+
+BOXES = [
+    ((0, 1, 0, 1, 0, 1), (0, 0, 0)),
+    ((0, 1, 0, 1, 0, 1), (1, 1, 1)),
+    ((-1.2, 1.3, -0.4, 2.2, -3.0, 1.0), (1, 0, 1)),
+]
+
+
+def particles(T, n, lim, seed=7):
+    rng = np.random.default_rng(seed)
+    out = []
+    for d in range(3):
+        lo, hi = lim[2 * d], lim[2 * d + 1]
+        a = (lo + (hi - lo) * rng.random(n)).astype(T)
+        np.clip(a, T(lo), np.nextafter(T(hi), T(lo)), out=a)
+        out.append(a)
+    return out
+
+
+# ------------------------------------------------------------------------------------------------ keys
+@pytest.mark.parametrize("combo", COMBOS)
+@pytest.mark.parametrize("kind", [0, 1])
+@pytest.mark.parametrize("lim,bnd", BOXES)
+def test_sfc_keys(combo, kind, lim, bnd):
+    T, K = real_of(combo), KEYS[key_of(combo)]
+    for n in (0, 1, 3, 1000, 100003):
+        x, y, z = particles(T, n + 1, lim)
+        # edge coordinates: box corners
+        if n >= 3:
+            x[0], y[0], z[0] = T(lim[0]), T(lim[2]), T(lim[4])
+            x[1], y[1], z[1] = (np.nextafter(T(lim[1]), T(lim[0])), np.nextafter(T(lim[3]), T(lim[2])),
+                                np.nextafter(T(lim[5]), T(lim[4])))
+        for off in (0, 1):  # off=1: pointers not 16-byte aligned -> scalar path
+            xs, ys, zs = x[off:off + n], y[off:off + n], z[off:off + n]
+            pre = np.zeros(n + 1, dtype=K)
+            remove = K(1) << K(3 * MAXLEVEL[key_of(combo)])
+            pre[::5] = remove
+            dk = dev(pre)
+            capi().compute_sfc_keys(dev(x)[off:off + n], dev(y)[off:off + n], dev(z)[off:off + n], dk[off:off + n],
+                                    lim, bnd, kind=kind, n=n)
+            got = host(dk)[off:off + n]
+            for name, chk in checkers():
+                want = chk.sfc_keys(combo, kind, xs.copy(), ys.copy(), zs.copy(), lim, bnd,
+                                    keys=pre[off:off + n].copy())
+                assert np.array_equal(got, want), (name, n, off)
+
+
+@pytest.mark.parametrize("combo", COMBOS)
+def test_hilbert_lut_exhaustive_low_levels(combo):
+    """all 2^15 cells of a 32^3 grid placed at several scales: exercises every state of the 3-level lookup tables"""
+    T = real_of(combo)
+    g = np.arange(32)
+    gx, gy, gz = [a.ravel() for a in np.meshgrid(g, g, g, indexing="ij")]
+    L = MAXLEVEL[key_of(combo)]
+    for shift in (0, 3, L - 5):
+        scale = float(1 << shift) / float(1 << L)
+        x, y, z = ((a + 0.5 if shift else a + 0.0) * scale for a in (gx, gy, gz))
+        x, y, z = x.astype(T), y.astype(T), z.astype(T)
+        lim, bnd = (0, 1, 0, 1, 0, 1), (0, 0, 0)
+        dk = torch.zeros(x.size, dtype=getattr(torch, "uint" + key_of(combo)[1:]), device=DEV)
+        capi().compute_sfc_keys(dev(x), dev(y), dev(z), dk, lim, bnd)
+        want = oracle().sfc_keys(combo, 0, x, y, z, lim, bnd)
+        assert np.array_equal(host(dk), want)
+
+
+# ------------------------------------------------------------------------------------------------ sort
+@pytest.mark.parametrize("kt", ["u32", "u64"])
+@pytest.mark.parametrize("n", [0, 1, 2, 31, 1000, 6143, 6144, 6145, 8192, 8193, 50000, 1 << 20])
+def test_sort_by_key(kt, n):
+    rng = np.random.default_rng(n + 1)
+    K = KEYS[kt]
+    hi = (1 << (3 * MAXLEVEL[kt])) + 1
+    for span in (hi, 50):  # span 50: heavy duplication => checks stability
+        keys = rng.integers(0, span, n, dtype=np.uint64).astype(K)
+        dk, dv = dev(keys), capi().sequence(0, n, DEV) if n else torch.zeros(0, dtype=torch.uint32, device=DEV)
+        capi().sort_by_key(dk, dv)
+        ko, vo = keys.copy(), np.arange(n, dtype=np.uint32)
+        oracle().sort_by_key(kt, ko, vo)
+        assert np.array_equal(host(dk), ko)
+        assert np.array_equal(host(dv), vo)
+    # keys only, with a non-zero sequence start
+    keys = rng.integers(0, hi, n, dtype=np.uint64).astype(K)
+    dk = dev(keys)
+    capi().sort_by_key(dk, None)
+    assert np.array_equal(host(dk), np.sort(keys, kind="stable"))
+    if n:
+        assert np.array_equal(host(capi().sequence(7, n, DEV)), np.arange(7, 7 + n, dtype=np.uint32))
+
+
+def test_sort_top_bit_and_extremes():
+    """removeKey (2^63) and all-ones keys sort to the end; already-sorted and reversed inputs"""
+    n = 20000
+    keys = np.arange(n, dtype=np.uint64)[::-1].copy()
+    keys[::97] = np.uint64(1) << np.uint64(63)
+    keys[5] = np.uint64(0xFFFFFFFFFFFFFFFF)
+    dk, dv = dev(keys), capi().sequence(0, n, DEV)
+    capi().sort_by_key(dk, dv)
+    order = np.argsort(keys, kind="stable")
+    assert np.array_equal(host(dk), keys[order])
+    assert np.array_equal(host(dv), order.astype(np.uint32))
+
+
+@pytest.mark.parametrize("T", [np.float32, np.float64])
+def test_gather_and_scan(T):
+    rng = np.random.default_rng(3)
+    n = 100001
+    order = rng.permutation(n).astype(np.uint32)
+    arrs = [rng.random(n).astype(T) for _ in range(4)]
+    do = dev(order)
+    got = capi().gather4(do, [dev(a) for a in arrs])
+    for g, a in zip(got, arrs):
+        assert np.array_equal(host(g), a[order])
+    assert np.array_equal(host(capi().gather(do, dev(arrs[0]))), arrs[0][order])
+    for m in (1, 2, 4095, 4096, 4097, 1 << 21):
+        v = rng.integers(0, 5000, m).astype(np.uint32)
+        want = np.zeros(m, dtype=np.uint32)
+        want[1:] = np.cumsum(v[:-1], dtype=np.uint64).astype(np.uint32)
+        assert np.array_equal(host(capi().exclusive_scan(dev(v))), want)
+
+
+# ------------------------------------------------------------------------------------------------ trees
+def sorted_keys(combo, n, dist, seed=11):
+    T = real_of(combo)
+    lim, bnd = (-1, 1, -1, 1, -1, 1), (0, 0, 0)
+    if dist == "gaussian":
+        x, y, z = gaussian_particles(n, T, seed)
+    elif dist == "plummer":
+        x, y, z = plummer_particles(n, T, seed)
+        m = max(np.abs(a).max() for a in (x, y, z)) * 1.001
+        lim = (-m, m, -m, m, -m, m)
+    else:
+        x, y, z = uniform_particles(n, T, seed, -1, 1)
+    keys = oracle().sfc_keys(combo, 0, x, y, z, lim, bnd)
+    order = np.arange(n, dtype=np.uint32)
+    oracle().sort_by_key(key_of(combo), keys, order)
+    return keys, (x[order], y[order], z[order]), lim, bnd
+
+
+@pytest.mark.parametrize("combo", COMBOS)
+@pytest.mark.parametrize("dist", ["uniform", "gaussian", "plummer"])
+@pytest.mark.parametrize("bucket", [1, 16, 64])
+def test_csarray_and_octree(combo, dist, bucket):
+    kt, T = key_of(combo), real_of(combo)
+    keys, _, lim, bnd = sorted_keys(combo, 40000, dist)
+    dk = dev(keys)
+    lo, co = oracle().compute_octree(kt, keys, bucket)
+    leaves, counts = capi().compute_octree(dk, bucket)
+    assert np.array_equal(host(leaves), lo) and np.array_equal(host(counts), co)
+
+    # stage functions one update step at a time from a coarse tree
+    lv = np.array([0, int(lo[-1])], dtype=KEYS[kt])
+    ct = np.array([keys.size], dtype=np.uint32)
+    for _ in range(3):
+        ops_o, conv_o = oracle().rebalance_decision(kt, lv, ct, bucket)
+        scan_o = np.zeros(lv.size, dtype=np.int64)
+        scan_o[1:] = np.cumsum(ops_o)
+        ops, new_n, conv = capi().compute_node_ops(dev(lv), dev(ct), bucket)
+        assert np.array_equal(host(ops).astype(np.int64), scan_o) and new_n == scan_o[-1] and conv == conv_o
+        new_leaves = capi().rebalance_tree(dev(lv), ops, new_n)
+        lv, ct, _ = oracle().update_octree(kt, keys, bucket, lv, ct)
+        assert np.array_equal(host(new_leaves), lv)
+        assert np.array_equal(host(capi().compute_node_counts(new_leaves, dk)), ct)
+    assert np.array_equal(host(capi().compute_node_counts(leaves, dev(keys[::3].copy()), 5)),
+                          oracle().compute_node_counts(kt, lo, keys[::3].copy(), 5))
+    # empty key set and keys beyond the last leaf
+    assert host(capi().compute_node_counts(leaves, dk, n=0)).sum() == 0
+
+    tree = capi().Octree(leaves)
+    to = oracle().build_octree(kt, lo)
+    nn = to["numNodes"]
+    assert np.array_equal(host(tree.prefixes), to["prefixes"])
+    assert np.array_equal(host(tree.child_offsets)[:nn], to["childOffsets"])
+    assert np.array_equal(host(tree.parents)[:(nn - 1) // 8], to["parents"])
+    assert np.array_equal(host(tree.level_range), to["levelRange"])
+    assert np.array_equal(host(tree.internal_to_leaf), to["internalToLeaf"])
+    assert np.array_equal(host(tree.leaf_to_internal), to["leafToInternal"])
+
+    tdtype = torch.float32 if T == np.float32 else torch.float64
+    for kind in (0, 1):
+        cen, siz = capi().compute_geo_centers(tree.prefixes, tdtype, lim, bnd, kind=kind)
+        cen_o, siz_o = oracle().node_fp_centers(combo, to["prefixes"], lim, bnd, kind=kind)
+        assert np.array_equal(host(cen), cen_o) and np.array_equal(host(siz), siz_o)
+
+    # count upsweep (octree_gpu.cu:205-236)
+    node_counts = np.zeros(nn, dtype=np.uint32)
+    node_counts[to["leafToInternal"][to["numInternal"]:]] = co
+    dn = dev(node_counts)
+    capi().upsweep_sum(kt, to["levelRange"], tree.child_offsets, dn)
+    got = host(dn)
+    assert got[0] == keys.size
+    internal = to["childOffsets"] > 0
+    kids = to["childOffsets"][internal][:, None] + np.arange(8)[None, :]
+    assert np.array_equal(got[internal], got[kids].sum(axis=1))
+
+
+def test_single_leaf_tree():
+    leaves = dev(np.array([0, 1 << 63], dtype=np.uint64))
+    tree = capi().Octree(leaves)
+    assert tree.num_nodes == 1 and host(tree.prefixes)[0] == 1
+    assert host(tree.child_offsets)[0] == 0
+    assert host(tree.level_range).tolist() == [0] + [1] * 22
+
+
+# ------------------------------------------------------------------------------------------------ neighbours
+@pytest.mark.parametrize("combo", COMBOS)
+@pytest.mark.parametrize("pbc", [0, 1])
+@pytest.mark.parametrize("dist", ["uniform", "gaussian"])
+def test_find_neighbors(combo, pbc, dist):
+    kt, T = key_of(combo), real_of(combo)
+    n = 20000
+    keys, (x, y, z), lim, _ = sorted_keys(combo, n, dist)
+    bnd = (pbc, pbc, pbc)
+    lo, co = oracle().compute_octree(kt, keys, 16)
+    to = oracle().build_octree(kt, lo)
+    cen_o, siz_o = oracle().node_fp_centers(combo, to["prefixes"], lim, bnd)
+    layout_o = np.zeros(lo.size, dtype=np.uint32)
+    layout_o[1:] = np.cumsum(co)
+    rng = np.random.default_rng(2)
+    h = (const_h(n, 40, T, 8.0) * (0.6 + 0.8 * rng.random(n))).astype(T)
+
+    tree = capi().Octree(dev(lo))
+    tdtype = torch.float32 if T == np.float32 else torch.float64
+    cen, siz = capi().compute_geo_centers(tree.prefixes, tdtype, lim, bnd)
+    dx, dy, dz, dh, dl = dev(x), dev(y), dev(z), dev(h), dev(layout_o)
+    for first, last, ngmax in [(0, n, 150), (0, n, 16), (37, n - 45, 64), (100, 101, 8)]:
+        nb, nc = capi().find_neighbors(dx, dy, dz, dh, first, last, lim, bnd, tree, dl, cen, siz, ngmax)
+        nb, nc = host(nb), host(nc)
+        for name, chk in checkers():
+            nb_o, nc_o = chk.find_neighbors(combo, x, y, z, h, first, last, lim, bnd, to, lo, layout_o, cen_o, siz_o,
+                                            ngmax)
+            assert np.array_equal(nc, nc_o), name
+            m = np.arange(ngmax)[None, :] < np.minimum(nc_o, ngmax)[:, None]
+            assert np.array_equal(nb[m], nb_o[m]), name
+    # sorted ascending (H3) and no self entries (H2)
+    nb, nc = capi().find_neighbors(dx, dy, dz, dh, 0, n, lim, bnd, tree, dl, cen, siz, 200)
+    nb, nc = host(nb).astype(np.int64), host(nc)
+    assert nc.max() <= 200
+    m = np.arange(200)[None, :] < nc[:, None]
+    assert not np.any((nb == np.arange(n)[:, None]) & m)
+    d = np.diff(nb, axis=1)
+    assert np.all((d > 0) | ~m[:, 1:])
+
+
+# ------------------------------------------------------------------------------------------------ halos
+@pytest.mark.parametrize("combo", COMBOS)
+@pytest.mark.parametrize("pbc", [0, 1])
+def test_halo_discovery(combo, pbc):
+    kt, T = key_of(combo), real_of(combo)
+    n = 30000
+    keys, (x, y, z), lim, _ = sorted_keys(combo, n, "gaussian")
+    bnd = (pbc, pbc, pbc)
+    lo, co = oracle().compute_octree(kt, keys, 8)
+    to = oracle().build_octree(kt, lo)
+    cen_o, siz_o = oracle().node_fp_centers(combo, to["prefixes"], lim, bnd)
+    layout_o = np.zeros(lo.size, dtype=np.uint32)
+    layout_o[1:] = np.cumsum(co)
+    h = const_h(n, 30, T, 8.0)
+    nl = lo.size - 1
+
+    tree = capi().Octree(dev(lo))
+    tdtype = torch.float32 if T == np.float32 else torch.float64
+    cen, siz = capi().compute_geo_centers(tree.prefixes, tdtype, lim, bnd)
+    init = cen_o[to["leafToInternal"][to["numInternal"]:]]
+    dx, dy, dz, dh, dl = dev(x), dev(y), dev(z), dev(h), dev(layout_o)
+    for first, last in [(0, nl // 4), (nl // 3, 2 * nl // 3), (nl - 5, nl), (0, nl)]:
+        sc, ss = capi().compute_bounding_boxes(dx, dy, dz, dh, dl, first, last, 2.0, dev(init))
+        sc_o, ss_o = oracle().bounding_boxes(combo, x, y, z, h, layout_o, first, last, 2.0, init)
+        assert np.array_equal(host(sc)[first:last], sc_o[first:last])
+        assert np.array_equal(host(ss)[first:last], ss_o[first:last])
+        flags = capi().find_halos(tree, cen, siz, sc, ss, lim, bnd, first, last)
+        for name, chk in checkers():
+            want = chk.find_halos(combo, to, cen_o, siz_o, lo, sc_o, ss_o, lim, bnd, first, last)
+            assert np.array_equal(host(flags), want), name
+
+
+# ------------------------------------------------------------------------------------------------ full size
+def test_full_size_keys_and_sort_properties():
+    """BASELINE config 2 size (64 Mi, u64/double): size-independent properties of keys + sort + gather"""
+    n = 64 * 1024 * 1024
+    g = torch.Generator(device=DEV)
+    g.manual_seed(42)
+    x, y, z = (torch.rand(n, dtype=torch.float64, device=DEV, generator=g) for _ in range(3))
+    lim, bnd = (0, 1, 0, 1, 0, 1), (0, 0, 0)
+    keys = torch.zeros(n, dtype=torch.uint64, device=DEV)
+    capi().compute_sfc_keys(x, y, z, keys, lim, bnd)
+    # sample check against the oracle
+    idx = torch.randint(0, n, (100000,), device=DEV, generator=g)
+    want = oracle().sfc_keys("u64d", 0, host(x[idx]), host(y[idx]), host(z[idx]), lim, bnd)
+    assert np.array_equal(host(keys.view(torch.int64)[idx]).view(np.uint64), want)
+
+    unsorted = keys.clone()
+    order = capi().sequence(0, n, DEV)
+    capi().sort_by_key(keys, order)
+    k64 = keys.view(torch.int64)  # keys < 2^63: signed comparison is order preserving
+    assert bool((k64[1:] >= k64[:-1]).all()), "keys not sorted"
+    o64 = order.view(torch.int32).to(torch.int64)  # n < 2^31
+    assert int(o64.sum()) == n * (n - 1) // 2, "values are not a permutation (checksum)"
+    assert bool((unsorted.view(torch.int64)[o64] == k64).all()), "values do not follow their keys"
+    # stability: among equal keys the original indices ascend
+    eq = k64[1:] == k64[:-1]
+    assert bool((o64[1:][eq] > o64[:-1][eq]).all())
+    xs = capi().gather(order, x)
+    assert bool((xs == x[o64]).all())
