@@ -147,56 +147,59 @@ def run_reference(args):
 
 
 # ------------------------------------------------------------------------------------------------ our arm
-class HotPath:
-    """the stage pipeline on one GPU; all buffers are allocated once and reused across steps"""
+def stage_rooflines(n, dev, x, y, z, h, reps=3):
+    """the HBM-bound stage kernels timed alone with CUDA events on the launching stream (same kernels the Domain
+    launches), against their algorithmic bytes (SURVEY.md 8d / DESIGN.md)"""
+    import torch
 
-    def __init__(self, n, device):
-        import torch
+    from cstone_b200 import capi
 
-        from cstone_b200 import capi
+    lim, bnd = (0, 1, 0, 1, 0, 1), (0, 0, 0)
+    res = {}
 
-        self.capi, self.torch, self.n, self.dev = capi, torch, n, device
-        self.lim, self.bnd = (0, 1, 0, 1, 0, 1), (0, 0, 0)
-        self.stage_ms = {}
-        self.leaves = None
+    def timeit(name, fn, setup=None):
+        ms = []
+        for _ in range(reps + 1):
+            if setup:
+                setup()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            fn()
+            e1.record()
+            torch.cuda.synchronize()
+            ms.append(e0.elapsed_time(e1))
+        res[name] = statistics.median(ms[1:])
 
-    def _timed(self, name, fn):
-        torch = self.torch
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        out = fn()
-        e1.record()
-        self._events.append((name, e0, e1))
-        return out
+    keys = torch.zeros(n, dtype=torch.uint64, device=dev)
+    timeit("keys", lambda: capi.compute_sfc_keys(x, y, z, keys, lim, bnd))
+    unsorted = keys.clone()
+    order = capi.sequence(0, n, dev)
+    kt = "u64"
+    tmp_bytes = capi.lib().cs_sort_by_key_temp_bytes_u64(n)
+    key_buf, val_buf = torch.empty_like(keys), torch.empty_like(order)
+    tmp = torch.empty(tmp_bytes, dtype=torch.uint8, device=dev)
+    import ctypes as C
 
-    def step(self, x, y, z, h, want_neighbors=True):
-        capi, torch, n = self.capi, self.torch, self.n
-        self._events = []
-        keys = torch.zeros(n, dtype=torch.uint64, device=self.dev)
-        self._timed("keys", lambda: capi.compute_sfc_keys(x, y, z, keys, self.lim, self.bnd))
-        order = self._timed("sequence", lambda: capi.sequence(0, n, self.dev))
-        self._timed("sort", lambda: capi.sort_by_key(keys, order))
-        sx, sy, sz, sh = self._timed("gather", lambda: capi.gather4(order, [x, y, z, h]))
-        leaves, counts = self._timed("csarray", lambda: capi.compute_octree(keys, BUCKET))
-        tree = self._timed("link", lambda: capi.Octree(leaves))
-        cen, siz = self._timed("centers", lambda: capi.compute_geo_centers(tree.prefixes, torch.float64, self.lim,
-                                                                            self.bnd))
-        layout = self._timed("layout", lambda: capi.exclusive_scan(
-            torch.cat([counts, torch.zeros(1, dtype=torch.uint32, device=self.dev)])))
-        nb = nc = None
-        if want_neighbors:
-            if not hasattr(self, "nb"):
-                self.nb = torch.empty(n * NGMAX, dtype=torch.uint32, device=self.dev)
-                self.nc = torch.empty(n, dtype=torch.uint32, device=self.dev)
-            nb, nc = self._timed("neighbors", lambda: capi.find_neighbors(sx, sy, sz, sh, 0, n, self.lim, self.bnd,
-                                                                          tree, layout, cen, siz, NGMAX, self.nb,
-                                                                          self.nc))
-        self.num_leaves = tree.num_leaves
-        return keys, (sx, sy, sz, sh), nc
+    def sort_setup():
+        keys.copy_(unsorted)
+        order.copy_(capi.sequence(0, n, dev))
 
-    def collect(self):
-        for name, e0, e1 in self._events:
-            self.stage_ms.setdefault(name, []).append(e0.elapsed_time(e1))
+    def sort_call():
+        capi._check(capi.lib().cs_sort_by_key_u64(capi._ptr(keys), capi._ptr(order), C.c_size_t(n), capi._ptr(key_buf),
+                                                  capi._ptr(val_buf), capi._ptr(tmp), C.c_size_t(tmp_bytes),
+                                                  capi._stream()), "sort")
+
+    timeit("sort", sort_call, sort_setup)
+    outs = [torch.empty_like(x) for _ in range(4)]
+    src_a = (C.c_void_p * 4)(*[t.data_ptr() for t in (x, y, z, h)])
+    dst_a = (C.c_void_p * 4)(*[t.data_ptr() for t in outs])
+    timeit("gather", lambda: capi._check(capi.lib().cs_gather4(capi._ptr(order), C.c_size_t(n), src_a, dst_a,
+                                                               C.c_int(8), capi._stream()), "gather4"))
+    leaves, counts = capi.compute_octree(keys, BUCKET)
+    timeit("counts", lambda: capi.compute_node_counts(leaves, keys))
+    res["num_leaves"] = leaves.numel() - 1
+    del keys, unsorted, order, key_buf, val_buf, tmp, outs
+    return res
 
 
 def run_ours(args):
@@ -221,12 +224,12 @@ def run_ours(args):
     g.manual_seed(42 + rank)
     x, y, z = (torch.rand(n, dtype=torch.float64, device=dev, generator=g) for _ in range(3))
     h = torch.full((n,), h_for(n, NG0), dtype=torch.float64, device=dev)
-    hx, hy, hz, hh = (t.cpu().pin_memory() for t in (x, y, z, h))
-    out_host = [torch.empty(n, dtype=torch.float64).pin_memory() for _ in range(4)]
-    keys_host = torch.empty(n, dtype=torch.uint64).pin_memory()
-    nc_host = torch.empty(n, dtype=torch.uint32).pin_memory()
+    lim, bnd = (0, 1, 0, 1, 0, 1), (0, 0, 0)
 
-    hp = HotPath(n, dev)
+    # Round 1: every rank synchronises its own shard as an independent single-rank Domain (no exchange yet)
+    dom = capi.Domain(0, 1, BUCKET, BUCKET, 0.5, lim, bnd, key="u64", real="d", device=str(dev))
+    nb = torch.empty(n * NGMAX, dtype=torch.uint32, device=dev)
+    nc = torch.empty(n, dtype=torch.uint32, device=dev)
 
     def barrier():
         if world > 1:
@@ -240,38 +243,65 @@ def run_ours(args):
             return float(t.item())
         return ms
 
-    # ---- device-resident timing
+    ev = lambda: torch.cuda.Event(enable_timing=True)  # noqa: E731
+    sync_ms, nb_ms = [], []
+
+    def step(record=False):
+        e0, e1, e2 = ev(), ev(), ev()
+        e0.record()
+        dom.reset()
+        dom.sync(x, y, z, h)
+        e1.record()
+        dom.find_neighbors(NGMAX, nb, nc)
+        e2.record()
+        if record:
+            sync_ms.append((e0, e1))
+            nb_ms.append((e1, e2))
+
+    # ---- device-resident timing: cold Domain::sync (fresh trees) + findNeighbors on unsorted input
     for _ in range(args.warmup):
-        hp.step(x, y, z, h)
+        step()
     barrier()
     sampler = ClockSampler(local_rank)
     sampler.start()
     launches0 = capi.kernel_launch_count()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0, e1 = ev(), ev()
     barrier()
     e0.record()
     for _ in range(args.steps):
-        hp.step(x, y, z, h)
-        hp_events = hp._events
-        hp.all_events = getattr(hp, "all_events", []) + [hp_events]
+        step(record=True)
     e1.record()
     barrier()
     clocks = sampler.stop()
     launches = capi.kernel_launch_count() - launches0
-    ms_total = max_over_ranks(e0.elapsed_time(e1))
-    for evs in hp.all_events:
-        hp._events = evs
-        hp.collect()
-    ms_per_step = ms_total / args.steps
+    ms_per_step = max_over_ranks(e0.elapsed_time(e1)) / args.steps
     value = world * n / (ms_per_step * 1e-3) / 1e6
+    cold_sync = statistics.median(a.elapsed_time(b) for a, b in sync_ms)
+    nb_time = statistics.median(a.elapsed_time(b) for a, b in nb_ms)
+    num_leaves = dom.num_focus_leaves
 
-    # ---- end to end: pinned host inputs -> device -> pipeline -> results back on the host
+    # ---- steady state: re-sync the (already SFC-ordered) domain arrays in place, one tree update per call
+    steady = []
+    for _ in range(4):
+        a, b = ev(), ev()
+        a.record()
+        dom.sync()
+        b.record()
+        torch.cuda.synchronize()
+        steady.append(a.elapsed_time(b))
+    steady_sync = statistics.median(steady[1:])
+
+    # ---- end to end: pinned host inputs -> C ABI (H2D inside) -> results back in pinned host memory
+    hx, hy, hz, hh = (t.cpu().pin_memory() for t in (x, y, z, h))
+    out_host = [torch.empty(n, dtype=torch.float64).pin_memory() for _ in range(4)]
+    keys_host = torch.empty(n, dtype=torch.uint64).pin_memory()
+    nc_host = torch.empty(n, dtype=torch.uint32).pin_memory()
+
     def e2e_step():
-        dx, dy, dz, dh = (t.to(dev, non_blocking=True) for t in (hx, hy, hz, hh))
-        keys, sorted_arrays, nc = hp.step(dx, dy, dz, dh)
-        keys_host.copy_(keys, non_blocking=True)
-        for o, s in zip(out_host, sorted_arrays):
-            o.copy_(s, non_blocking=True)
+        dom.reset()
+        dom.sync(hx, hy, hz, hh)
+        dom.find_neighbors(NGMAX, nb, nc)
+        dom.download(*out_host, keys_host)
         nc_host.copy_(nc, non_blocking=True)
 
     e2e_steps = max(1, min(args.steps, 3))
@@ -286,53 +316,50 @@ def run_ours(args):
     e2e_value = world * n / (e2e_ms * 1e-3) / 1e6
     h2d = 4 * 8 * n
     d2h = 4 * 8 * n + 8 * n + 4 * n
+    mean_nc = float(nc_host[: 1 << 20].to(torch.int64).sum()) / float(min(n, 1 << 20))
 
     if rank != 0:
         return None
 
-    # ---- per-stage rooflines (algorithmic bytes per particle: SURVEY.md §8d / DESIGN.md)
+    # ---- per-stage rooflines
     peak, peak_kind = hbm_peak()
-    nl = hp.num_leaves
-    alg_bytes = {
-        "keys": 40.0 * n,
-        "sort": 200.0 * n,
-        "gather": 68.0 * n,
-        "neighbors": None,
-    }
+    st = stage_rooflines(n, dev, x, y, z, h)
+    alg = {"keys": 40.0 * n, "sort": 200.0 * n, "gather": 68.0 * n, "counts": 8.0 * n + 12.0 * st["num_leaves"]}
     stages = {}
-    for name, ms in hp.stage_ms.items():
-        med = statistics.median(ms)
-        entry = {"ms": round(med, 4)}
-        if alg_bytes.get(name):
-            entry["achieved_gbs"] = round(alg_bytes[name] / (med * 1e-3) / 1e9, 1)
-            entry["frac"] = round(entry["achieved_gbs"] / peak, 4)
-        stages[name] = entry
-    mean_nc = float(nc_host[: 1 << 20].to(torch.int64).sum()) / float(1 << 20)
+    for name, nbytes in alg.items():
+        gbs = nbytes / (st[name] * 1e-3) / 1e9
+        stages[name] = {"ms": round(st[name], 4), "achieved_gbs": round(gbs, 1), "frac": round(gbs / peak, 4),
+                        "algorithmic_bytes": nbytes}
     nb_bytes = (4.0 * min(mean_nc, NGMAX) + 4 + 32) * n
-    stages["neighbors"]["achieved_gbs"] = round(nb_bytes / (stages["neighbors"]["ms"] * 1e-3) / 1e9, 1)
-    stages["neighbors"]["frac"] = round(stages["neighbors"]["achieved_gbs"] / peak, 4)
-    stages["neighbors"]["note"] = "traversal + FP64 distance tests; output-write floor used as algorithmic bytes"
+    stages["neighbors"] = {"ms": round(nb_time, 3), "achieved_gbs": round(nb_bytes / (nb_time * 1e-3) / 1e9, 1),
+                           "frac": round(nb_bytes / (nb_time * 1e-3) / 1e9 / peak, 4),
+                           "note": "traversal + FP64 distance tests (FP64-pipe bound, see profiles/); bytes = list "
+                                   "output + particle reads"}
+    stages["domain_sync_cold"] = {"ms": round(cold_sync, 3)}
+    stages["domain_sync_steady"] = {"ms": round(steady_sync, 3)}
 
-    dom = "sort"  # dominant HBM-bound kernel group of Domain::sync (histogram + 8 onesweep passes)
-    roofline = {"bound": "hbm", "kernel": "onesweepKernel<u64,values> x8 + radixHistogramKernel",
-                "achieved": stages[dom]["achieved_gbs"], "peak": peak, "unit": "GB/s", "frac": stages[dom]["frac"],
-                "traffic": None, "peak_source": peak_kind,
-                "algorithmic_bytes_per_particle": 200, "launch_ms": stages[dom]["ms"]}
+    roofline = {"bound": "hbm", "kernel": "onesweepKernel<u64,values> x8 (+ radixHistogramKernel)",
+                "achieved": stages["sort"]["achieved_gbs"], "peak": peak, "unit": "GB/s",
+                "frac": stages["sort"]["frac"], "traffic": None, "peak_source": peak_kind,
+                "algorithmic_bytes_per_particle": 200, "launch_group_ms": stages["sort"]["ms"],
+                "note": "dominant HBM-bound kernel group of Domain::sync; findNeighbors dominates the step by time but "
+                        "is FP64-bound, its numbers are under stages.neighbors"}
 
-    line = {
+    return {
         "metric": METRIC, "value": round(value, 2), "unit": UNIT, "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": round(ms_per_step, 3), "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "u64 keys / f64 coordinates", "data": "synthetic",
-        "config": {"workload": f"{n} uniform-random particles per GPU, 64-bit Hilbert, double, bucketSize={BUCKET}: "
-                               f"keys+sort+gather+tree build+link+findNeighbors(ng~{NG0}, ngmax={NGMAX})",
+        "config": {"workload": f"{n} uniform-random particles per GPU, 64-bit Hilbert, double, bucketSize="
+                               f"bucketSizeFocus={BUCKET}: first Domain::sync (cold trees, unsorted input) + "
+                               f"findNeighbors(ng~{NG0}, ngmax={NGMAX})",
                    "particles_per_gpu": n, "l2_policy": "inputs (>=512 MB per array) exceed the 126 MB L2",
-                   "parallelism": f"sfc-shards x{world}", "leaves": nl, "mean_neighbors": round(mean_nc, 2)},
+                   "parallelism": f"independent single-rank domains x{world}", "focus_leaves": num_leaves,
+                   "mean_neighbors": round(mean_nc, 2)},
         "e2e": {"value": round(e2e_value, 2), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "ms_per_step": round(e2e_ms, 3),
                 "note": "neighbour lists stay in HBM for the device-side consumer; keys, x,y,z,h and counts return"},
         "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "stages": stages,
     }
-    return line
 
 
 def main():

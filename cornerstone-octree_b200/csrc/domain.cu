@@ -1,0 +1,720 @@
+/* cs_domain_*: device-resident orchestration of the domain-sync hot path, the B200 counterpart of
+ * cstone::Domain<KeyType,T,Gpu>::sync (reference domain/domain.hpp:169-218) with its GlobalAssignment
+ * (domain/assignment.hpp:92-203) and FocusedOctree (focus/octree_focus_mpi.hpp:100-252,511-603,
+ * focus/octree_focus.hpp:65-212) collaborators.
+ *
+ * The update cadence of the reference is kept exactly (the trees lag the particles by design): one global-tree
+ * rebalance per sync (a loop only on the first call or after large count changes, assignment.hpp:115-123), a focus
+ * tree that is converged on the first call and then updated once per sync, node counts / layout recomputed after
+ * every tree update.  What changes is where things run: every array lives in HBM, each step is one of the kernels in
+ * this library, and the host only reads back the handful of scalars the control flow needs.
+ *
+ * Scope of this file in round 1: ONE rank (numRanks == 1).  With a single rank nothing is exchanged, every leaf is in
+ * focus (so MAC flags cannot change any rebalance decision, focus/rebalance.hpp:31-73) and no search box can leave
+ * the assigned SFC range (traversal/collisions.hpp:81-90), therefore halo flags are all zero; those two stages are
+ * skipped.  Multi-rank construction is rejected loudly ("what comes next").
+ */
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+#include <limits>
+#include <vector>
+
+#include "common.cuh"
+#include "cstone_b200.h"
+#include "focus.cuh"
+
+namespace csb
+{
+
+namespace
+{
+
+/* ---------------------------------------------------------------- small device buffer */
+template<class E>
+struct DevBuf
+{
+    E* p{nullptr};
+    size_t cap{0};
+    size_t n{0};
+
+    DevBuf() = default;
+    DevBuf(const DevBuf&)            = delete;
+    DevBuf& operator=(const DevBuf&) = delete;
+    ~DevBuf() { cudaFree(p); }
+
+    //! grow to m elements; keeps the first min(n, m) elements when keep is set; new elements are zeroed when zeroNew
+    int resize(size_t m, cudaStream_t s, bool keep = false, bool zeroNew = false, double growth = 1.05)
+    {
+        if (m > cap)
+        {
+            size_t newCap = std::max<size_t>(size_t(double(m) * growth), 64);
+            E* q          = nullptr;
+            CSB_CHECK(cudaMalloc(&q, newCap * sizeof(E)));
+            if (keep && n) { CSB_CHECK(cudaMemcpyAsync(q, p, n * sizeof(E), cudaMemcpyDeviceToDevice, s)); }
+            if (p)
+            {
+                CSB_CHECK(cudaStreamSynchronize(s));
+                CSB_CHECK(cudaFree(p));
+            }
+            p   = q;
+            cap = newCap;
+        }
+        if (zeroNew && m > n) { CSB_CHECK(cudaMemsetAsync(p + n, 0, (m - n) * sizeof(E), s)); }
+        n = m;
+        return 0;
+    }
+    void swap(DevBuf& o)
+    {
+        std::swap(p, o.p);
+        std::swap(cap, o.cap);
+        std::swap(n, o.n);
+    }
+};
+
+#define CSB_TRY(expr)                                                                                                  \
+    do                                                                                                                 \
+    {                                                                                                                  \
+        if (int e__ = (expr)) { return e__; }                                                                          \
+    } while (0)
+
+template<class K>
+struct OctreeBufs
+{
+    int numLeaves{0}, numInternal{0}, numNodes{0};
+    DevBuf<K> prefixes;
+    DevBuf<int> childOffsets, parents, levelRange, internalToLeaf, leafToInternal;
+    std::vector<int> levelRangeHost;
+
+    int resize(int nLeaves, cudaStream_t s)
+    {
+        numLeaves   = nLeaves;
+        numInternal = (nLeaves - 1) / 7;
+        numNodes    = numLeaves + numInternal;
+        CSB_TRY(prefixes.resize(numNodes, s));
+        CSB_TRY(childOffsets.resize(numNodes + 1, s));
+        CSB_TRY(parents.resize(std::max(1, (numNodes - 1) / 8), s));
+        CSB_TRY(levelRange.resize(KeyTraits<K>::maxLevel + 2, s));
+        CSB_TRY(internalToLeaf.resize(numNodes, s));
+        CSB_TRY(leafToInternal.resize(numNodes, s));
+        levelRangeHost.resize(KeyTraits<K>::maxLevel + 2);
+        return 0;
+    }
+    const int* leafToInternalLeaves() const { return leafToInternal.p + numInternal; }
+};
+
+inline int keysDispatch(int kind, const float* x, const float* y, const float* z, uint32_t* k, size_t n,
+                        const double* lim, const int* bnd, cudaStream_t s)
+{
+    return cs_compute_sfc_keys_u32f(kind, x, y, z, k, n, lim, bnd, s);
+}
+inline int keysDispatch(int kind, const float* x, const float* y, const float* z, uint64_t* k, size_t n,
+                        const double* lim, const int* bnd, cudaStream_t s)
+{
+    return cs_compute_sfc_keys_u64f(kind, x, y, z, k, n, lim, bnd, s);
+}
+inline int keysDispatch(int kind, const double* x, const double* y, const double* z, uint64_t* k, size_t n,
+                        const double* lim, const int* bnd, cudaStream_t s)
+{
+    return cs_compute_sfc_keys_u64d(kind, x, y, z, k, n, lim, bnd, s);
+}
+inline int sortDispatch(uint64_t* k, uint32_t* v, size_t n, uint64_t* kb, uint32_t* vb, void* t, size_t tb,
+                        cudaStream_t s)
+{
+    return sortByKeyU64(k, v, n, kb, vb, t, tb, s);
+}
+inline int sortDispatch(uint32_t* k, uint32_t* v, size_t n, uint32_t* kb, uint32_t* vb, void* t, size_t tb,
+                        cudaStream_t s)
+{
+    return sortByKeyU32(k, v, n, kb, vb, t, tb, s);
+}
+template<class K>
+size_t sortTempBytesT(size_t n)
+{
+    if constexpr (sizeof(K) == 8) { return sortTempBytesU64(n); }
+    else { return sortTempBytesU32(n); }
+}
+template<class K>
+size_t linkTempBytesT(int numLeaves)
+{
+    if constexpr (sizeof(K) == 8) { return buildOctreeTempBytesU64(numLeaves); }
+    else { return buildOctreeTempBytesU32(numLeaves); }
+}
+
+struct DomainBase
+{
+    virtual ~DomainBase()                                                                         = default;
+    virtual int sync(const void* x, const void* y, const void* z, const void* h, const void* keys, size_t n,
+                     bool hostInput, cudaStream_t s)                                               = 0;
+    virtual int info(uint64_t* out, double* box) const                                             = 0;
+    virtual void* ptr(int field)                                                                   = 0;
+    virtual int neighbors(uint32_t ngmax, uint32_t* nb, uint32_t* nc, cudaStream_t s)              = 0;
+    virtual int download(void* x, void* y, void* z, void* h, void* keys, cudaStream_t s)           = 0;
+    virtual int reset(cudaStream_t s)                                                              = 0;
+    int keyBytes{0}, realBytes{0};
+};
+
+template<class K, class T>
+class DomainImpl : public DomainBase
+{
+public:
+    DomainImpl(int rank, int numRanks, unsigned bucket, unsigned bucketFocus, float theta, const double* lim,
+               const int* bnd)
+        : rank_(rank)
+        , numRanks_(numRanks)
+        , bucket_(bucket)
+        , bucketFocus_(bucketFocus)
+        , theta_(theta)
+    {
+        std::copy(lim, lim + 6, lim_);
+        std::copy(lim, lim + 6, lim0_);
+        std::copy(bnd, bnd + 3, bnd_);
+        keyBytes  = sizeof(K);
+        realBytes = sizeof(T);
+    }
+
+    //! back to the freshly constructed state (next sync is a "first call"); device buffers are kept
+    int reset(cudaStream_t s) override
+    {
+        firstCall_ = true;
+        start_ = end_ = bufSize_ = 0;
+        std::copy(lim0_, lim0_ + 6, lim_);
+        return init(s);
+    }
+
+    int init(cudaStream_t s)
+    {
+        // GlobalAssignment ctor (assignment.hpp:53-74) for one rank: the spanning tree of {0, 2^(3L)} is the root
+        // node; its count starts at bucketSize - 1
+        K root[2]   = {0, nodeRange<K>(0)};
+        uint32_t c0 = bucket_ - 1;
+        CSB_TRY(gLeaves_.resize(2, s));
+        CSB_TRY(gCounts_.resize(1, s));
+        CSB_CHECK(cudaMemcpyAsync(gLeaves_.p, root, sizeof(root), cudaMemcpyHostToDevice, s));
+        CSB_CHECK(cudaMemcpyAsync(gCounts_.p, &c0, sizeof(c0), cudaMemcpyHostToDevice, s));
+        numGlobalLeaves_ = 1;
+
+        // FocusedOctree ctor (octree_focus_mpi.hpp:56-83): root leaf with count bucketSizeFocus + 1
+        uint32_t c1 = bucketFocus_ + 1;
+        CSB_TRY(fLeaves_.resize(2, s));
+        CSB_TRY(fLeafCounts_.resize(1, s));
+        CSB_TRY(fCounts_.resize(1, s));
+        CSB_TRY(macs_.resize(1, s, false, true));
+        CSB_CHECK(cudaMemcpyAsync(fLeaves_.p, root, sizeof(root), cudaMemcpyHostToDevice, s));
+        CSB_CHECK(cudaMemcpyAsync(fLeafCounts_.p, &c1, sizeof(c1), cudaMemcpyHostToDevice, s));
+        CSB_CHECK(cudaMemcpyAsync(fCounts_.p, &c1, sizeof(c1), cudaMemcpyHostToDevice, s));
+        CSB_TRY(scalars_.resize(64, s, false, true));
+        CSB_CHECK(cudaStreamSynchronize(s));
+        CSB_TRY(linkTree(fLeaves_, 1, fTree_, s));
+        CSB_TRY(linkTree(gLeaves_, 1, gTree_, s));
+        return 0;
+    }
+
+    /* ------------------------------------------------------------ sync */
+    int sync(const void* xin, const void* yin, const void* zin, const void* hin, const void* keysIn, size_t nIn,
+             bool hostInput, cudaStream_t s) override
+    {
+        auto kindOfCopy = hostInput ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToDevice;
+        if (xin)
+        {
+            CSB_REQUIRE(yin && zin && hin, "x, y, z, h must be given together");
+            if (!firstCall_)
+            {
+                CSB_REQUIRE(nIn == size_t(bufSize_), "Domain sync: input array sizes are inconsistent");
+            }
+            CSB_TRY(x_.resize(nIn, s));
+            CSB_TRY(y_.resize(nIn, s));
+            CSB_TRY(z_.resize(nIn, s));
+            CSB_TRY(h_.resize(nIn, s));
+            CSB_CHECK(cudaMemcpyAsync(x_.p, xin, nIn * sizeof(T), kindOfCopy, s));
+            CSB_CHECK(cudaMemcpyAsync(y_.p, yin, nIn * sizeof(T), kindOfCopy, s));
+            CSB_CHECK(cudaMemcpyAsync(z_.p, zin, nIn * sizeof(T), kindOfCopy, s));
+            CSB_CHECK(cudaMemcpyAsync(h_.p, hin, nIn * sizeof(T), kindOfCopy, s));
+            CSB_TRY(keys_.resize(nIn, s));
+            if (keysIn) { CSB_CHECK(cudaMemcpyAsync(keys_.p, keysIn, nIn * sizeof(K), kindOfCopy, s)); }
+            else { CSB_CHECK(cudaMemsetAsync(keys_.p, 0, nIn * sizeof(K), s)); }
+            if (firstCall_)
+            {
+                start_   = 0;
+                end_     = LocalIndex(nIn);
+                bufSize_ = LocalIndex(nIn);
+            }
+        }
+        else { CSB_REQUIRE(!firstCall_, "the first sync needs input arrays"); }
+        CSB_REQUIRE(size_t(bufSize_) < (size_t(1) << 30), "at most 2^30 - 1 particles per rank");
+
+        const size_t numPart = end_ - start_;
+
+        /* ---- GlobalAssignment::assign (assignment.hpp:92-144) */
+        CSB_TRY(updateBox(numPart, s));
+        CSB_TRY(keysDispatch(0, x_.p + start_, y_.p + start_, z_.p + start_, keys_.p + start_, numPart, lim_, bnd_, s));
+        CSB_TRY(ordering_.resize(numPart, s));
+        CSB_TRY(cs_sequence_u32(start_, numPart, ordering_.p, s));
+        CSB_TRY(sortPairs(keys_.p + start_, ordering_.p, numPart, s));
+
+        unsigned maxCount = 0;
+        CSB_TRY(updateGlobalTree(keys_.p + start_, numPart, &maxCount, s));
+        if (firstCall_ || maxCount >= 8 * bucket_)
+        {
+            do
+            {
+                CSB_TRY(updateGlobalTree(keys_.p + start_, numPart, &maxCount, s));
+            } while (maxCount > bucket_);
+        }
+        CSB_TRY(linkTree(gLeaves_, numGlobalLeaves_, gTree_, s));
+
+        // one rank: assignment = whole curve; particles with key >= 2^(3L) (removeKey) fall outside of it
+        K boundaries[2] = {0, nodeRange<K>(0)};
+        CSB_TRY(boundaryKeys_.resize(2, s));
+        CSB_CHECK(cudaMemcpyAsync(boundaryKeys_.p, boundaries, sizeof(boundaries), cudaMemcpyHostToDevice, s));
+        uint32_t* sendIdxDev = scalars_.p + 8;
+        CSB_TRY(lowerBounds<K>(keys_.p + start_, numPart, boundaryKeys_.p, 2, sendIdxDev, s));
+        uint32_t sendIdx[2];
+        CSB_CHECK(cudaMemcpyAsync(sendIdx, sendIdxDev, sizeof(sendIdx), cudaMemcpyDeviceToHost, s));
+        CSB_CHECK(cudaStreamSynchronize(s));
+        const LocalIndex numSendDown = sendIdx[0];
+        const LocalIndex numAssigned = sendIdx[1] - sendIdx[0];
+
+        /* ---- GlobalAssignment::distribute (assignment.hpp:167-203): nothing to exchange on one rank; the envelope
+         *      is already sorted, so the second sort of the reference is the identity and is skipped */
+        const K* keyView = keys_.p + start_ + numSendDown;
+
+        /* ---- gatherArrays(x,y,z,h) to offset 0 (domain.hpp:187) */
+        CSB_TRY(sx_.resize(std::max<size_t>(numAssigned, 1), s));
+        CSB_TRY(sy_.resize(std::max<size_t>(numAssigned, 1), s));
+        CSB_TRY(sz_.resize(std::max<size_t>(numAssigned, 1), s));
+        CSB_TRY(sh_.resize(std::max<size_t>(numAssigned, 1), s));
+        {
+            const void* src[4] = {x_.p, y_.p, z_.p, h_.p};
+            void* dst[4]       = {sx_.p, sy_.p, sz_.p, sh_.p};
+            CSB_TRY(cs_gather4(ordering_.p + numSendDown, numAssigned, src, dst, int(sizeof(T)), s));
+        }
+
+        /* ---- focus tree (domain.hpp:189-213) */
+        if (firstCall_)
+        {
+            int converged = 0;
+            while (!converged)
+            {
+                CSB_TRY(updateFocusTree(&converged, s));
+                CSB_TRY(updateFocusCounts(keyView, numAssigned, s));
+            }
+        }
+        {
+            int converged = 0;
+            CSB_TRY(updateFocusTree(&converged, s));
+            CSB_TRY(updateFocusCounts(keyView, numAssigned, s));
+            // discoverHalos + computeLayout (octree_focus_mpi.hpp:511-582): no foreign leaves on one rank
+            CSB_TRY(macs_.resize(fTree_.numNodes, s));
+            CSB_CHECK(cudaMemsetAsync(macs_.p, 0, size_t(fTree_.numNodes), s));
+            CSB_TRY(layout_.resize(fTree_.numLeaves + 1, s));
+            CSB_TRY(layoutCounts(fLeafCounts_.p, macs_.p, fTree_.leafToInternalLeaves(), fTree_.numLeaves, 0,
+                                 fTree_.numLeaves, layout_.p, s));
+            CSB_TRY(scanTmp_.resize(scanTempBytes(size_t(fTree_.numLeaves) + 1), s));
+            CSB_TRY(exclusiveScanU32(layout_.p, layout_.p, size_t(fTree_.numLeaves) + 1, scanTmp_.p, s));
+        }
+
+        /* ---- updateLayout (domain.hpp:490-537): new buffer = [0, numAssigned) without halos; keys move to offset 0 */
+        CSB_TRY(keyBuf_.resize(std::max<size_t>(numAssigned, 1), s));
+        CSB_CHECK(cudaMemcpyAsync(keyBuf_.p, keyView, size_t(numAssigned) * sizeof(K), cudaMemcpyDeviceToDevice, s));
+        keys_.swap(keyBuf_);
+        keys_.n = numAssigned;
+        x_.swap(sx_);
+        y_.swap(sy_);
+        z_.swap(sz_);
+        h_.swap(sh_);
+        x_.n = y_.n = z_.n = h_.n = numAssigned;
+
+        start_     = 0;
+        end_       = numAssigned;
+        bufSize_   = numAssigned;
+        firstCall_ = false;
+        return 0;
+    }
+
+    int info(uint64_t* out, double* box) const override
+    {
+        out[0] = start_;
+        out[1] = end_;
+        out[2] = bufSize_;
+        out[3] = uint64_t(fTree_.numLeaves);
+        out[4] = uint64_t(fTree_.numNodes);
+        out[5] = uint64_t(numGlobalLeaves_);
+        out[6] = uint64_t(gTree_.numNodes);
+        out[7] = uint64_t(KeyTraits<K>::maxLevel);
+        std::copy(lim_, lim_ + 6, box);
+        return 0;
+    }
+
+    void* ptr(int field) override
+    {
+        switch (field)
+        {
+            case CS_FIELD_X: return x_.p;
+            case CS_FIELD_Y: return y_.p;
+            case CS_FIELD_Z: return z_.p;
+            case CS_FIELD_H: return h_.p;
+            case CS_FIELD_KEYS: return keys_.p;
+            case CS_FIELD_FOCUS_LEAVES: return fLeaves_.p;
+            case CS_FIELD_FOCUS_LEAF_COUNTS: return fLeafCounts_.p;
+            case CS_FIELD_FOCUS_NODE_COUNTS: return fCounts_.p;
+            case CS_FIELD_LAYOUT: return layout_.p;
+            case CS_FIELD_PREFIXES: return fTree_.prefixes.p;
+            case CS_FIELD_CHILD_OFFSETS: return fTree_.childOffsets.p;
+            case CS_FIELD_PARENTS: return fTree_.parents.p;
+            case CS_FIELD_LEVEL_RANGE: return fTree_.levelRange.p;
+            case CS_FIELD_INTERNAL_TO_LEAF: return fTree_.internalToLeaf.p;
+            case CS_FIELD_LEAF_TO_INTERNAL: return fTree_.leafToInternal.p;
+            case CS_FIELD_GEO_CENTERS: return geoCenters_.p;
+            case CS_FIELD_GEO_SIZES: return geoSizes_.p;
+            case CS_FIELD_HALO_FLAGS: return macs_.p;
+            case CS_FIELD_GLOBAL_LEAVES: return gLeaves_.p;
+            case CS_FIELD_GLOBAL_COUNTS: return gCounts_.p;
+            case CS_FIELD_GLOBAL_PREFIXES: return gTree_.prefixes.p;
+            case CS_FIELD_GLOBAL_CHILD_OFFSETS: return gTree_.childOffsets.p;
+            default: return nullptr;
+        }
+    }
+
+    int neighbors(uint32_t ngmax, uint32_t* nb, uint32_t* nc, cudaStream_t s) override
+    {
+        CSB_REQUIRE(!firstCall_, "findNeighbors needs a synchronised domain");
+        return findNeighbors<T>(x_.p, y_.p, z_.p, h_.p, start_, end_, lim_, bnd_, fTree_.childOffsets.p,
+                                fTree_.parents.p, fTree_.internalToLeaf.p, layout_.p, geoCenters_.p, geoSizes_.p,
+                                ngmax, nb, nc, s);
+    }
+
+    int download(void* x, void* y, void* z, void* h, void* keys, cudaStream_t s) override
+    {
+        size_t n = bufSize_;
+        if (x) { CSB_CHECK(cudaMemcpyAsync(x, x_.p, n * sizeof(T), cudaMemcpyDeviceToHost, s)); }
+        if (y) { CSB_CHECK(cudaMemcpyAsync(y, y_.p, n * sizeof(T), cudaMemcpyDeviceToHost, s)); }
+        if (z) { CSB_CHECK(cudaMemcpyAsync(z, z_.p, n * sizeof(T), cudaMemcpyDeviceToHost, s)); }
+        if (h) { CSB_CHECK(cudaMemcpyAsync(h, h_.p, n * sizeof(T), cudaMemcpyDeviceToHost, s)); }
+        if (keys) { CSB_CHECK(cudaMemcpyAsync(keys, keys_.p, n * sizeof(K), cudaMemcpyDeviceToHost, s)); }
+        return 0;
+    }
+
+private:
+    /* ------------------------------------------------------------ box: makeGlobalBox (sfc/box_mpi.hpp:51-105) +
+     *                                                              limitBoxShrinking (sfc/box.hpp:398-415) */
+    int updateBox(size_t numPart, cudaStream_t s)
+    {
+        bool keep[3];
+        bool anyOpen = false;
+        for (int d = 0; d < 3; ++d)
+        {
+            keep[d] = bnd_[d] == 1 || bnd_[d] == 2;
+            anyOpen = anyOpen || !keep[d];
+        }
+        T prev[6];
+        for (int i = 0; i < 6; ++i)
+            prev[i] = T(lim_[i]);
+        T ext[6];
+        std::copy(prev, prev + 6, ext);
+        if (numPart && anyOpen)
+        {
+            constexpr int blocks = 592;
+            CSB_TRY(partials_.resize(size_t(3) * 2 * blocks, s));
+            const T* arrays[3] = {x_.p + start_, y_.p + start_, z_.p + start_};
+            for (int d = 0; d < 3; ++d)
+                if (!keep[d]) { CSB_TRY(minMaxPartials<T>(arrays[d], numPart, partials_.p + d * 2 * blocks, blocks, s)); }
+            std::vector<T> hostPartials(size_t(3) * 2 * blocks);
+            CSB_CHECK(cudaMemcpyAsync(hostPartials.data(), partials_.p, hostPartials.size() * sizeof(T),
+                                      cudaMemcpyDeviceToHost, s));
+            CSB_CHECK(cudaStreamSynchronize(s));
+            for (int d = 0; d < 3; ++d)
+            {
+                if (keep[d]) { continue; }
+                T mn = hostPartials[d * 2 * blocks], mx = hostPartials[d * 2 * blocks + 1];
+                for (int b = 1; b < blocks; ++b)
+                {
+                    mn = std::min(mn, hostPartials[d * 2 * blocks + 2 * b]);
+                    mx = std::max(mx, hostPartials[d * 2 * blocks + 2 * b + 1]);
+                }
+                ext[2 * d]     = mn;
+                ext[2 * d + 1] = mx;
+            }
+        }
+        const T maxSide = std::max({ext[1] - ext[0], ext[3] - ext[2], ext[5] - ext[4]});
+        for (int d = 0; d < 3; ++d)
+            if (bnd_[d] == 3) { ext[2 * d + 1] = std::max(ext[2 * d + 1], ext[2 * d] + maxSide); }
+
+        if (!firstCall_)
+        {
+            const T shrink = T(0.05);
+            for (int d = 0; d < 3; ++d)
+            {
+                T len          = prev[2 * d + 1] - prev[2 * d];
+                ext[2 * d]     = std::min(ext[2 * d], prev[2 * d] + shrink * len);
+                ext[2 * d + 1] = std::max(ext[2 * d + 1], prev[2 * d + 1] - shrink * len);
+            }
+        }
+        for (int i = 0; i < 6; ++i)
+            lim_[i] = double(ext[i]);
+        return 0;
+    }
+
+    int sortPairs(K* keys, uint32_t* values, size_t n, cudaStream_t s)
+    {
+        CSB_TRY(keyBuf_.resize(std::max<size_t>(n, 1), s));
+        CSB_TRY(valueBuf_.resize(std::max<size_t>(n, 1), s));
+        size_t tb = sortTempBytesT<K>(n);
+        CSB_TRY(sortTmp_.resize(tb, s));
+        return sortDispatch(keys, values, n, keyBuf_.p, valueBuf_.p, sortTmp_.p, tb, s);
+    }
+
+    int linkTree(DevBuf<K>& leaves, int numLeaves, OctreeBufs<K>& tree, cudaStream_t s)
+    {
+        CSB_TRY(tree.resize(numLeaves, s));
+        size_t tb = linkTempBytesT<K>(numLeaves);
+        CSB_TRY(linkTmp_.resize(tb, s));
+        CSB_TRY(buildOctree<K>(leaves.p, numLeaves, tree.prefixes.p, tree.childOffsets.p, tree.parents.p,
+                               tree.levelRange.p, tree.internalToLeaf.p, tree.leafToInternal.p, linkTmp_.p, tb, s));
+        CSB_CHECK(cudaMemcpyAsync(tree.levelRangeHost.data(), tree.levelRange.p,
+                                  tree.levelRangeHost.size() * sizeof(int), cudaMemcpyDeviceToHost, s));
+        CSB_CHECK(cudaStreamSynchronize(s));
+        return 0;
+    }
+
+    /* ------------------------------------------------------------ updateOctreeGlobal (tree/update_mpi.hpp:64-97) */
+    int updateGlobalTree(const K* keys, size_t n, unsigned* maxCountOut, cudaStream_t s)
+    {
+        int newNumLeaves = 0, converged = 0;
+        CSB_TRY(nodeOps_.resize(size_t(numGlobalLeaves_) + 1, s));
+        CSB_TRY(opsTmp_.resize(nodeOpsTempBytes(numGlobalLeaves_), s));
+        CSB_TRY(computeNodeOps<K>(gLeaves_.p, numGlobalLeaves_, gCounts_.p, bucket_, nodeOps_.p, opsTmp_.p,
+                                  &newNumLeaves, &converged, s));
+        CSB_TRY(gLeavesAlt_.resize(size_t(newNumLeaves) + 1, s));
+        CSB_TRY(rebalanceTree<K>(gLeaves_.p, numGlobalLeaves_, newNumLeaves, nodeOps_.p, gLeavesAlt_.p, s));
+        gLeaves_.swap(gLeavesAlt_);
+        numGlobalLeaves_ = newNumLeaves;
+        CSB_TRY(gCounts_.resize(newNumLeaves, s));
+        CSB_TRY(computeNodeCounts<K>(gLeaves_.p, gCounts_.p, newNumLeaves, keys, n,
+                                     std::numeric_limits<unsigned>::max(), s));
+        // (multi-rank: ncclAllReduce(sum) of the counts followed by max(local, reduced) goes here)
+        if (converged)
+        {
+            *maxCountOut = 0;
+            return 0;
+        }
+        CSB_TRY(maxU32(gCounts_.p, newNumLeaves, scalars_.p, s));
+        CSB_CHECK(cudaMemcpyAsync(maxCountOut, scalars_.p, sizeof(unsigned), cudaMemcpyDeviceToHost, s));
+        CSB_CHECK(cudaStreamSynchronize(s));
+        return 0;
+    }
+
+    /* ------------------------------------------------------------ FocusedOctree::updateTree
+     *  = CombinedUpdate::updateFocus (focus/octree_focus.hpp:65-127) + updateGeoCenters */
+    int updateFocusTree(int* convergedOut, cudaStream_t s)
+    {
+        const int numNodes  = fTree_.numNodes;
+        const int numLeaves = fTree_.numLeaves;
+        const K focusStart = 0, focusEnd = nodeRange<K>(0);
+
+        CSB_TRY(macs_.resize(numNodes, s));
+        CSB_CHECK(cudaMemsetAsync(macs_.p, 0, size_t(numNodes), s)); // irrelevant when every node is in focus
+        CSB_TRY(nodeOpsAll_.resize(numNodes, s));
+        int* statusDev  = reinterpret_cast<int*>(scalars_.p + 16);
+        int* changesDev = statusDev + 1;
+        int* notOneDev  = statusDev + 2;
+        CSB_CHECK(cudaMemsetAsync(statusDev, 0, 3 * sizeof(int), s));
+
+        CSB_TRY(essentialOps<K>(fTree_.prefixes.p, fTree_.childOffsets.p, fTree_.parents.p, fCounts_.p, macs_.p,
+                                focusStart, focusEnd, bucketFocus_, nodeOpsAll_.p, numNodes, s));
+        // mandatory keys: focus boundaries (trivial here) + the global leaves of the own assignment
+        CSB_TRY(enforceKeys<K>(gLeaves_.p, numGlobalLeaves_ + 1, fTree_.prefixes.p, fTree_.childOffsets.p,
+                               fTree_.parents.p, nodeOpsAll_.p, statusDev, s));
+        CSB_TRY(protectAncestors<K>(fTree_.prefixes.p, fTree_.parents.p, nodeOpsAll_.p, numNodes, changesDev, s));
+
+        CSB_TRY(nodeOps_.resize(size_t(numLeaves) + 1, s));
+        CSB_TRY(gatherLeafOps(fTree_.leafToInternalLeaves(), numLeaves, nodeOpsAll_.p, nodeOps_.p, notOneDev, s));
+        CSB_TRY(scanTmp_.resize(scanTempBytes(size_t(numLeaves) + 1), s));
+        CSB_TRY(exclusiveScanU32(reinterpret_cast<uint32_t*>(nodeOps_.p), reinterpret_cast<uint32_t*>(nodeOps_.p),
+                                 size_t(numLeaves) + 1, scanTmp_.p, s));
+
+        int flags[3];
+        int newNumLeaves = 0;
+        CSB_CHECK(cudaMemcpyAsync(flags, statusDev, sizeof(flags), cudaMemcpyDeviceToHost, s));
+        CSB_CHECK(cudaMemcpyAsync(&newNumLeaves, nodeOps_.p + numLeaves, sizeof(int), cudaMemcpyDeviceToHost, s));
+        CSB_CHECK(cudaStreamSynchronize(s));
+        const int status = flags[0];
+        bool converged   = flags[1] == 0;
+        if (status == ENFORCE_CANCEL_MERGE) { converged = flags[2] == 0; }
+        else if (status == ENFORCE_REBALANCE) { converged = false; }
+
+        CSB_TRY(fLeavesAlt_.resize(size_t(newNumLeaves) + 1, s));
+        CSB_TRY(rebalanceTree<K>(fLeaves_.p, numLeaves, newNumLeaves, nodeOps_.p, fLeavesAlt_.p, s));
+        fLeaves_.swap(fLeavesAlt_);
+        int numFocusLeaves = newNumLeaves;
+
+        if (status == ENFORCE_FAILED)
+        {
+            converged = false;
+            CSB_TRY(injectKeys(gLeaves_.p, numGlobalLeaves_ + 1, &numFocusLeaves, s));
+        }
+
+        CSB_TRY(linkTree(fLeaves_, numFocusLeaves, fTree_, s));
+        CSB_TRY(geoCenters_.resize(size_t(3) * fTree_.numNodes, s));
+        CSB_TRY(geoSizes_.resize(size_t(3) * fTree_.numNodes, s));
+        CSB_TRY((computeGeoCenters<K, T>(0, fTree_.prefixes.p, fTree_.numNodes, geoCenters_.p, geoSizes_.p, lim_, bnd_,
+                                         s)));
+        *convergedOut = converged ? 1 : 0;
+        return 0;
+    }
+
+    //! focus/inject.hpp:50-84: leaves <- span(sort(leaves U keys))
+    int injectKeys(const K* keys, int numKeys, int* numLeavesInOut, cudaStream_t s)
+    {
+        size_t total = size_t(*numLeavesInOut) + 1 + numKeys;
+        CSB_TRY(fLeavesAlt_.resize(total, s));
+        CSB_CHECK(cudaMemcpyAsync(fLeavesAlt_.p, fLeaves_.p, (size_t(*numLeavesInOut) + 1) * sizeof(K),
+                                  cudaMemcpyDeviceToDevice, s));
+        CSB_CHECK(cudaMemcpyAsync(fLeavesAlt_.p + *numLeavesInOut + 1, keys, size_t(numKeys) * sizeof(K),
+                                  cudaMemcpyDeviceToDevice, s));
+        CSB_TRY(keyBuf_.resize(total, s));
+        size_t tb = sortTempBytesT<K>(total);
+        CSB_TRY(sortTmp_.resize(tb, s));
+        CSB_TRY(sortDispatch(fLeavesAlt_.p, nullptr, total, keyBuf_.p, nullptr, sortTmp_.p, tb, s));
+
+        int numGaps = int(total) - 1;
+        CSB_TRY(gapCounts_.resize(total, s));
+        CSB_TRY(countGaps<K>(fLeavesAlt_.p, numGaps, gapCounts_.p, s));
+        CSB_TRY(scanTmp_.resize(scanTempBytes(total), s));
+        CSB_TRY(exclusiveScanU32(gapCounts_.p, gapCounts_.p, total, scanTmp_.p, s));
+        uint32_t numNodesGap = 0;
+        CSB_CHECK(cudaMemcpyAsync(&numNodesGap, gapCounts_.p + numGaps, sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
+        CSB_CHECK(cudaStreamSynchronize(s));
+        CSB_TRY(fLeaves_.resize(size_t(numNodesGap) + 1, s));
+        CSB_TRY(fillGaps<K>(fLeavesAlt_.p, numGaps, gapCounts_.p, fLeaves_.p, s));
+        *numLeavesInOut = int(numNodesGap);
+        return 0;
+    }
+
+    /* ------------------------------------------------------------ FocusedOctree::updateCounts
+     *  (octree_focus_mpi.hpp:193-252): leaf counts, scatter to nodes, upsweep (no peers on one rank) */
+    int updateFocusCounts(const K* keyView, size_t numKeys, cudaStream_t s)
+    {
+        CSB_TRY(fLeafCounts_.resize(fTree_.numLeaves, s));
+        CSB_TRY(computeNodeCounts<K>(fLeaves_.p, fLeafCounts_.p, fTree_.numLeaves, keyView, numKeys,
+                                     std::numeric_limits<unsigned>::max(), s));
+        CSB_TRY(fCounts_.resize(fTree_.numNodes, s));
+        CSB_TRY(scatterCounts(fTree_.leafToInternalLeaves(), fTree_.numLeaves, fLeafCounts_.p, fCounts_.p, s));
+        CSB_TRY(upsweepSum(KeyTraits<K>::maxLevel, fTree_.levelRangeHost.data(), fTree_.childOffsets.p, fCounts_.p, s));
+        return 0;
+    }
+
+    int rank_, numRanks_;
+    unsigned bucket_, bucketFocus_;
+    float theta_;
+    double lim_[6];
+    double lim0_[6];
+    int bnd_[3];
+    bool firstCall_{true};
+    LocalIndex start_{0}, end_{0}, bufSize_{0};
+
+    DevBuf<T> x_, y_, z_, h_, sx_, sy_, sz_, sh_, partials_, geoCenters_, geoSizes_;
+    DevBuf<K> keys_, keyBuf_, boundaryKeys_;
+    DevBuf<uint32_t> ordering_, valueBuf_, scalars_, gapCounts_, layout_;
+    DevBuf<unsigned char> sortTmp_, linkTmp_, opsTmp_, scanTmp_;
+    DevBuf<int> nodeOps_, nodeOpsAll_;
+
+    // global tree
+    DevBuf<K> gLeaves_, gLeavesAlt_;
+    DevBuf<uint32_t> gCounts_;
+    OctreeBufs<K> gTree_;
+    int numGlobalLeaves_{0};
+
+    // focus tree
+    DevBuf<K> fLeaves_, fLeavesAlt_;
+    DevBuf<uint32_t> fLeafCounts_, fCounts_;
+    DevBuf<uint8_t> macs_;
+    OctreeBufs<K> fTree_;
+};
+
+template<class K, class T>
+cs_domain_t* createDomain(int rank, int numRanks, unsigned bucket, unsigned bucketFocus, float theta,
+                          const double* lim, const int* bnd)
+{
+    if (numRanks != 1 || rank != 0)
+    {
+        setLastError("cs_domain_create: round 1 supports numRanks == 1 only (multi-rank sync is not implemented yet)");
+        return nullptr;
+    }
+    if (bucket < bucketFocus)
+    {
+        // domain.hpp:81-85
+        setLastError("The bucket size of the global tree must not be smaller than the bucket size of the focused tree");
+        return nullptr;
+    }
+    auto* d = new DomainImpl<K, T>(rank, numRanks, bucket, bucketFocus, theta, lim, bnd);
+    if (d->init(nullptr) != 0)
+    {
+        delete d;
+        return nullptr;
+    }
+    return reinterpret_cast<cs_domain_t*>(static_cast<DomainBase*>(d));
+}
+
+inline DomainBase* impl(cs_domain_t* d) { return reinterpret_cast<DomainBase*>(d); }
+
+} // namespace
+
+} // namespace csb
+
+extern "C"
+{
+
+cs_domain_t* cs_domain_create_u32f(int rank, int numRanks, unsigned bucketSize, unsigned bucketSizeFocus, float theta,
+                                   const double* lim, const int* bnd)
+{
+    return csb::createDomain<uint32_t, float>(rank, numRanks, bucketSize, bucketSizeFocus, theta, lim, bnd);
+}
+cs_domain_t* cs_domain_create_u64f(int rank, int numRanks, unsigned bucketSize, unsigned bucketSizeFocus, float theta,
+                                   const double* lim, const int* bnd)
+{
+    return csb::createDomain<uint64_t, float>(rank, numRanks, bucketSize, bucketSizeFocus, theta, lim, bnd);
+}
+cs_domain_t* cs_domain_create_u64d(int rank, int numRanks, unsigned bucketSize, unsigned bucketSizeFocus, float theta,
+                                   const double* lim, const int* bnd)
+{
+    return csb::createDomain<uint64_t, double>(rank, numRanks, bucketSize, bucketSizeFocus, theta, lim, bnd);
+}
+
+void cs_domain_destroy(cs_domain_t* d) { delete csb::impl(d); }
+
+int cs_domain_sync(cs_domain_t* d, const void* x, const void* y, const void* z, const void* h, const void* keys,
+                   size_t n, int hostInput, void* stream)
+{
+    CSB_REQUIRE(d != nullptr, "null domain");
+    return csb::impl(d)->sync(x, y, z, h, keys, n, hostInput != 0, cudaStream_t(stream));
+}
+
+int cs_domain_info(const cs_domain_t* d, uint64_t* out8, double* box6)
+{
+    CSB_REQUIRE(d != nullptr, "null domain");
+    return csb::impl(const_cast<cs_domain_t*>(d))->info(out8, box6);
+}
+
+void* cs_domain_ptr(cs_domain_t* d, int field) { return d ? csb::impl(d)->ptr(field) : nullptr; }
+
+int cs_domain_find_neighbors(cs_domain_t* d, uint32_t ngmax, uint32_t* neighbors, uint32_t* neighborsCount,
+                             void* stream)
+{
+    CSB_REQUIRE(d != nullptr, "null domain");
+    return csb::impl(d)->neighbors(ngmax, neighbors, neighborsCount, cudaStream_t(stream));
+}
+
+int cs_domain_reset(cs_domain_t* d, void* stream)
+{
+    CSB_REQUIRE(d != nullptr, "null domain");
+    return csb::impl(d)->reset(cudaStream_t(stream));
+}
+
+int cs_domain_download(cs_domain_t* d, void* x, void* y, void* z, void* h, void* keys, void* stream)
+{
+    CSB_REQUIRE(d != nullptr, "null domain");
+    return csb::impl(d)->download(x, y, z, h, keys, cudaStream_t(stream));
+}
+
+} // extern "C"

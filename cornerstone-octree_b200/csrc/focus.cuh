@@ -1,0 +1,90 @@
+/* declarations shared between focus.cu, csarray.cu, octree.cu, ... and the Domain driver (domain.cu) */
+#pragma once
+
+#include "common.cuh"
+
+namespace csb
+{
+
+enum EnforceStatus : int
+{
+    ENFORCE_CONVERGED    = 0,
+    ENFORCE_CANCEL_MERGE = 1,
+    ENFORCE_REBALANCE    = 2,
+    ENFORCE_FAILED       = 3
+};
+
+/* focus.cu */
+template<class K>
+int essentialOps(const K* prefixes, const int* childOffsets, const int* parents, const uint32_t* counts,
+                 const uint8_t* macs, K focusStart, K focusEnd, uint32_t bucketSize, int* nodeOps, int numNodes,
+                 cudaStream_t s);
+template<class K>
+int enforceKeys(const K* keys, int numKeys, const K* prefixes, const int* childOffsets, const int* parents,
+                int* nodeOps, int* statusDev, cudaStream_t s);
+template<class K>
+int protectAncestors(const K* prefixes, const int* parents, int* nodeOps, int numNodes, int* changesDev,
+                     cudaStream_t s);
+int gatherLeafOps(const int* leafToInternalLeaves, int numLeaves, const int* nodeOpsAll, int* leafOps,
+                  int* notAllOneDev, cudaStream_t s);
+template<class K>
+int countGaps(const K* keys, int numGaps, uint32_t* gapCounts, cudaStream_t s);
+template<class K>
+int fillGaps(const K* keys, int numGaps, const uint32_t* offsets, K* out, cudaStream_t s);
+int scatterCounts(const int* leafToInternalLeaves, int numLeaves, const uint32_t* leafCounts, uint32_t* nodeCounts,
+                  cudaStream_t s);
+template<class T>
+int gatherVec3(const int* map, int n, const T* src, T* dst, cudaStream_t s);
+int layoutCounts(const uint32_t* leafCounts, const uint8_t* flags, const int* leafToInternalLeaves, int numLeaves,
+                 int ownStart, int ownEnd, uint32_t* layout, cudaStream_t s);
+template<class T>
+int minMaxPartials(const T* a, size_t n, T* partial, int numBlocks, cudaStream_t s);
+int maxU32(const uint32_t* a, size_t n, uint32_t* resultDev, cudaStream_t s);
+template<class K>
+int lowerBounds(const K* keys, size_t n, const K* targets, int numTargets, uint32_t* out, cudaStream_t s);
+template<class K>
+int spanSfcRangeHost(K a, K b, K* output);
+
+/* csarray.cu */
+template<class K>
+int computeNodeCounts(const K* leaves, uint32_t* counts, int numLeaves, const K* keys, size_t n, uint32_t maxCount,
+                      cudaStream_t s);
+template<class K>
+int computeNodeOps(const K* leaves, int numLeaves, const uint32_t* counts, uint32_t bucketSize, int* nodeOps, void* tmp,
+                   int* newNumLeaves, int* converged, cudaStream_t s);
+template<class K>
+int rebalanceTree(const K* leaves, int numLeaves, int newNumLeaves, const int* nodeOps, K* newLeaves, cudaStream_t s);
+size_t nodeOpsTempBytes(size_t numLeaves);
+
+/* octree.cu */
+template<class K>
+int buildOctree(const K* leaves, int numLeaves, K* prefixes, int* childOffsets, int* parents, int* levelRange,
+                int* internalToLeaf, int* leafToInternal, void* tmp, size_t tmpBytes, cudaStream_t s);
+template<class K, class T>
+int computeGeoCenters(int kind, const K* prefixes, int numNodes, T* centers, T* sizes, const double* lim,
+                      const int* bnd, cudaStream_t s);
+int upsweepSum(int maxLevel, const int* levelRangeHost, const int* childOffsets, uint32_t* counts, cudaStream_t s);
+size_t buildOctreeTempBytesU32(int numLeaves);
+size_t buildOctreeTempBytesU64(int numLeaves);
+
+/* sort.cu */
+int sortByKeyU64(uint64_t*, uint32_t*, size_t, uint64_t*, uint32_t*, void*, size_t, cudaStream_t);
+int sortByKeyU32(uint32_t*, uint32_t*, size_t, uint32_t*, uint32_t*, void*, size_t, cudaStream_t);
+size_t sortTempBytesU64(size_t n);
+size_t sortTempBytesU32(size_t n);
+
+/* halos.cu / neighbors.cu */
+template<class T>
+int computeBoundingBoxes(const T* x, const T* y, const T* z, const T* h, const uint32_t* layout, int firstLeaf,
+                         int lastLeaf, T scale, T* sc, T* ss, cudaStream_t s);
+template<class K, class T>
+int findHalos(const K* prefixes, const int* childOffsets, const int* parents, const T* centers, const T* sizes,
+              const K* leaves, const T* searchCenters, const T* searchSizes, const double* lim, const int* bnd,
+              int firstLeaf, int lastLeaf, uint8_t* flags, cudaStream_t s);
+template<class T>
+int findNeighbors(const T* x, const T* y, const T* z, const T* h, uint32_t first, uint32_t last, const double* lim,
+                  const int* bnd, const int* childOffsets, const int* parents, const int* internalToLeaf,
+                  const uint32_t* layout, const T* centers, const T* sizes, uint32_t ngmax, uint32_t* neighbors,
+                  uint32_t* neighborsCount, cudaStream_t s);
+
+} // namespace csb

@@ -35,6 +35,13 @@ const char* cs_last_error(void)
 
 int cs_version(void) { return 100; }
 
+/* experiment hook: L2 fetch granularity hint (bytes: 32, 64 or 128) for the current device */
+int cs_set_l2_fetch_granularity(int bytes)
+{
+    CSB_CHECK(cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, size_t(bytes)));
+    return 0;
+}
+
 uint64_t cs_kernel_launch_count(void) { return csb::g_launches.load(); }
 
 } // extern "C"

@@ -271,3 +271,113 @@ def find_neighbors(x, y, z, h, first, last, lim, bnd, tree, layout, centers, siz
              _ptr(tree.child_offsets), _ptr(tree.parents), _ptr(tree.internal_to_leaf), _ptr(layout), _ptr(centers),
              _ptr(sizes), C.c_uint32(ngmax), _ptr(neighbors), _ptr(counts), _stream()), "cs_find_neighbors_" + sfx)
     return neighbors.view(nloc, ngmax), counts
+
+
+# ---------------------------------------------------------------- Domain
+FIELDS = ["x", "y", "z", "h", "keys", "focus_leaves", "focus_leaf_counts", "focus_node_counts", "layout", "prefixes",
+          "child_offsets", "parents", "level_range", "internal_to_leaf", "leaf_to_internal", "geo_centers",
+          "geo_sizes", "halo_flags", "global_leaves", "global_counts", "global_prefixes", "global_child_offsets"]
+
+
+class _View:
+    """zero-copy torch view of a device array owned by the C library"""
+
+    def __init__(self, ptr, shape, dtype, device):
+        self.ptr, self.shape, self.dtype, self.device = ptr, shape, dtype, device
+
+    @property
+    def __cuda_array_interface__(self):
+        # exported as a signed integer type of the same width and re-viewed by the caller: the unsigned 32/64-bit
+        # dtypes are not accepted by every torch version on this path
+        typestr = {1: "|u1", 4: "<i4", 8: "<i8"}[torch.empty(0, dtype=self.dtype).element_size()]
+        return {"shape": self.shape, "typestr": typestr, "data": (self.ptr, False), "version": 2}
+
+
+class Domain:
+    """host-side mirror of cstone::Domain<KeyType, T, Gpu> (domain/domain.hpp:38-664) over the cs_domain_* C ABI"""
+
+    def __init__(self, rank, num_ranks, bucket_size, bucket_size_focus, theta, lim, bnd, key="u64", real="d",
+                 device="cuda:0"):
+        self.combo = key + real
+        self.kt, self.real = key, real
+        self.device = torch.device(device)
+        lim_a, bnd_a = _box(lim, bnd)
+        f = getattr(lib(), "cs_domain_create_" + self.combo)
+        f.restype = C.c_void_p
+        with torch.cuda.device(self.device):
+            self.handle = f(C.c_int(rank), C.c_int(num_ranks), C.c_uint(bucket_size), C.c_uint(bucket_size_focus),
+                            C.c_float(theta), lim_a, bnd_a)
+        if not self.handle:
+            # the reference throws std::runtime_error from the constructor (domain.hpp:81-85)
+            raise CstoneError(lib().cs_last_error().decode())
+        lib().cs_domain_ptr.restype = C.c_void_p
+
+    def __del__(self):
+        if getattr(self, "handle", None):
+            lib().cs_domain_destroy(C.c_void_p(self.handle))
+            self.handle = None
+
+    def sync(self, x=None, y=None, z=None, h=None, keys=None):
+        """x,y,z,h: torch tensors on the domain's device or in (pinned) host memory, or None to re-sync in place"""
+        if x is None:
+            args = [C.c_void_p(0)] * 5 + [C.c_size_t(0), C.c_int(0)]
+        else:
+            host = not x.is_cuda
+            ptrs = [C.c_void_p(t.data_ptr()) for t in (x, y, z, h)]
+            ptrs.append(C.c_void_p(keys.data_ptr()) if keys is not None else C.c_void_p(0))
+            args = ptrs + [C.c_size_t(x.numel()), C.c_int(1 if host else 0)]
+        with torch.cuda.device(self.device):
+            _check(lib().cs_domain_sync(C.c_void_p(self.handle), *args, _stream()), "cs_domain_sync")
+        self._info()
+
+    def reset(self):
+        with torch.cuda.device(self.device):
+            _check(lib().cs_domain_reset(C.c_void_p(self.handle), _stream()), "cs_domain_reset")
+
+    def _info(self):
+        out = (C.c_uint64 * 8)()
+        box = (C.c_double * 6)()
+        _check(lib().cs_domain_info(C.c_void_p(self.handle), out, box), "cs_domain_info")
+        (self.start_index, self.end_index, self.n_particles_with_halos, self.num_focus_leaves, self.num_focus_nodes,
+         self.num_global_leaves, self.num_global_nodes, self.max_level) = [int(v) for v in out]
+        self.box = tuple(box)
+
+    def field(self, name):
+        """torch view (no copy) of one of the arrays listed in FIELDS"""
+        real_t = REAL_DTYPES[self.real]
+        key_t = KEY_DTYPES[self.kt]
+        n, nl, nn = self.n_particles_with_halos, self.num_focus_leaves, self.num_focus_nodes
+        gl, gn = self.num_global_leaves, self.num_global_nodes
+        spec = {
+            "x": ((n,), real_t), "y": ((n,), real_t), "z": ((n,), real_t), "h": ((n,), real_t), "keys": ((n,), key_t),
+            "focus_leaves": ((nl + 1,), key_t), "focus_leaf_counts": ((nl,), torch.uint32),
+            "focus_node_counts": ((nn,), torch.uint32), "layout": ((nl + 1,), torch.uint32),
+            "prefixes": ((nn,), key_t), "child_offsets": ((nn,), torch.int32),
+            "parents": ((max(1, (nn - 1) // 8),), torch.int32), "level_range": ((self.max_level + 2,), torch.int32),
+            "internal_to_leaf": ((nn,), torch.int32), "leaf_to_internal": ((nn,), torch.int32),
+            "geo_centers": ((nn, 3), real_t), "geo_sizes": ((nn, 3), real_t), "halo_flags": ((nn,), torch.uint8),
+            "global_leaves": ((gl + 1,), key_t), "global_counts": ((gl,), torch.uint32),
+            "global_prefixes": ((gn,), key_t), "global_child_offsets": ((gn,), torch.int32),
+        }[name]
+        ptr = lib().cs_domain_ptr(C.c_void_p(self.handle), C.c_int(FIELDS.index(name)))
+        shape, dtype = spec
+        if 0 in shape or not ptr:
+            return torch.empty(shape, dtype=dtype, device=self.device)
+        return torch.as_tensor(_View(ptr, shape, dtype, self.device), device=self.device).view(dtype)
+
+    def find_neighbors(self, ngmax, neighbors=None, counts=None):
+        nloc = self.end_index - self.start_index
+        if neighbors is None:
+            neighbors = torch.zeros(nloc * ngmax, dtype=torch.uint32, device=self.device)
+        if counts is None:
+            counts = torch.zeros(nloc, dtype=torch.uint32, device=self.device)
+        with torch.cuda.device(self.device):
+            _check(lib().cs_domain_find_neighbors(C.c_void_p(self.handle), C.c_uint32(ngmax), _ptr(neighbors),
+                                                  _ptr(counts), _stream()), "cs_domain_find_neighbors")
+        return neighbors.view(nloc, ngmax), counts
+
+    def download(self, x, y, z, h, keys):
+        """asynchronous device -> (pinned) host copy of the synchronised arrays"""
+        ptrs = [C.c_void_p(t.data_ptr()) if t is not None else C.c_void_p(0) for t in (x, y, z, h, keys)]
+        with torch.cuda.device(self.device):
+            _check(lib().cs_domain_download(C.c_void_p(self.handle), *ptrs, _stream()), "cs_domain_download")

@@ -163,6 +163,72 @@ int cs_find_neighbors_d(const double* x, const double* y, const double* z, const
                         const double* sizes, uint32_t ngmax, uint32_t* neighbors, uint32_t* neighborsCount,
                         void* stream);
 
+/* ---- Domain: cstone::Domain<KeyType,T,Gpu> (domain/domain.hpp:38-664) ----
+ * cs_domain_create_*  <-> Domain(exec, rank, nRanks, bucketSize, bucketSizeFocus, theta, comm, box)  domain.hpp:63-86
+ *                         (returns NULL + cs_last_error() where the reference throws std::runtime_error)
+ * cs_domain_sync      <-> sync(keys, x, y, z, h, {}, scratch)                                       domain.hpp:169-218
+ * cs_domain_info      <-> startIndex/endIndex/nParticlesWithHalos/box()                             domain.hpp:339-361
+ * cs_domain_ptr       <-> the arrays sync() leaves behind + focusTree()/globalTree()/layout()/octreeProperties()
+ * cs_domain_find_neighbors <-> findNeighbors(x,y,z,h, startIndex, endIndex, box, octreeProperties(), ...)
+ *
+ * The domain owns the particle arrays in HBM (a C ABI cannot resize the caller's vectors).  cs_domain_sync takes
+ * x,y,z,h (and optionally keys, for removeKey marking) of n particles from device (hostInput = 0) or host
+ * (hostInput = 1) memory; passing x == NULL re-synchronises the domain-owned arrays in place after the caller has
+ * updated them through cs_domain_ptr.  After the call the arrays hold nParticlesWithHalos elements, SFC-sorted
+ * assigned particles in [startIndex, endIndex).  Synchronises the stream.
+ * Round 1: numRanks must be 1. */
+typedef struct cs_domain cs_domain_t;
+
+enum cs_domain_field
+{
+    CS_FIELD_X = 0,
+    CS_FIELD_Y,
+    CS_FIELD_Z,
+    CS_FIELD_H,
+    CS_FIELD_KEYS,
+    CS_FIELD_FOCUS_LEAVES,      /* KeyType[numFocusLeaves + 1]      focusTree().treeLeavesAcc() */
+    CS_FIELD_FOCUS_LEAF_COUNTS, /* unsigned[numFocusLeaves]         focusTree().leafCountsAcc() */
+    CS_FIELD_FOCUS_NODE_COUNTS, /* unsigned[numFocusNodes]          focusTree().countsAcc()     */
+    CS_FIELD_LAYOUT,            /* LocalIndex[numFocusLeaves + 1]   layout()                    */
+    CS_FIELD_PREFIXES,          /* OctreeView of the focus tree: tree/octree.hpp:234-256 */
+    CS_FIELD_CHILD_OFFSETS,
+    CS_FIELD_PARENTS,
+    CS_FIELD_LEVEL_RANGE,
+    CS_FIELD_INTERNAL_TO_LEAF,
+    CS_FIELD_LEAF_TO_INTERNAL,
+    CS_FIELD_GEO_CENTERS, /* Vec3<T>[numFocusNodes] */
+    CS_FIELD_GEO_SIZES,
+    CS_FIELD_HALO_FLAGS,    /* uint8_t[numFocusNodes]            focusTree().flags() */
+    CS_FIELD_GLOBAL_LEAVES, /* KeyType[numGlobalLeaves + 1]      globalTree().leaves */
+    CS_FIELD_GLOBAL_COUNTS,
+    CS_FIELD_GLOBAL_PREFIXES,
+    CS_FIELD_GLOBAL_CHILD_OFFSETS
+};
+
+cs_domain_t* cs_domain_create_u32f(int rank, int numRanks, unsigned bucketSize, unsigned bucketSizeFocus, float theta,
+                                   const double* lim, const int* bnd);
+cs_domain_t* cs_domain_create_u64f(int rank, int numRanks, unsigned bucketSize, unsigned bucketSizeFocus, float theta,
+                                   const double* lim, const int* bnd);
+cs_domain_t* cs_domain_create_u64d(int rank, int numRanks, unsigned bucketSize, unsigned bucketSizeFocus, float theta,
+                                   const double* lim, const int* bnd);
+void cs_domain_destroy(cs_domain_t* d);
+int cs_domain_sync(cs_domain_t* d, const void* x, const void* y, const void* z, const void* h, const void* keys,
+                   size_t n, int hostInput, void* stream);
+/* out8 = {startIndex, endIndex, nParticlesWithHalos, numFocusLeaves, numFocusNodes, numGlobalLeaves,
+ *         numGlobalNodes, maxTreeLevel}; box6 = current global box limits */
+int cs_domain_info(const cs_domain_t* d, uint64_t* out8, double* box6);
+void* cs_domain_ptr(cs_domain_t* d, int field);
+int cs_domain_find_neighbors(cs_domain_t* d, uint32_t ngmax, uint32_t* neighbors, uint32_t* neighborsCount,
+                             void* stream);
+/* forget all tree state so that the next cs_domain_sync behaves like the first call on a new Domain (device buffers
+ * are kept; used by bench.py to time cold syncs without re-allocating) */
+int cs_domain_reset(cs_domain_t* d, void* stream);
+/* device -> host copy of the synchronised arrays (NULL pointers are skipped); asynchronous on the stream */
+int cs_domain_download(cs_domain_t* d, void* x, void* y, void* z, void* h, void* keys, void* stream);
+
+/* tuning hook: L2 fetch granularity hint in bytes (32, 64, 128) for the current device */
+int cs_set_l2_fetch_granularity(int bytes);
+
 #ifdef __cplusplus
 }
 #endif
