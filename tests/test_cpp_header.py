@@ -1,0 +1,46 @@
+"""the C++ forwarder header compiles against stand-ins for the reference's vocabulary types and links to the C ABI"""
+import os
+import subprocess
+import tempfile
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+PKG = os.path.join(ROOT, "cornerstone-octree_b200")
+
+SRC = r'''
+#include <cstdio>
+#include "cstone_b200.hpp"
+// stand-ins with the interface of cstone::Box<T> (sfc/box.hpp:86-174) and execution::Gpu (execution.hpp:37-56)
+enum class BoundaryType : uint8_t { open = 0, periodic = 1 };
+struct Box { double xmin() const {return 0;} double xmax() const {return 1;} double ymin() const {return 0;}
+             double ymax() const {return 1;} double zmin() const {return 0;} double zmax() const {return 1;}
+             BoundaryType boundaryX() const {return BoundaryType::open;} BoundaryType boundaryY() const {return BoundaryType::open;}
+             BoundaryType boundaryZ() const {return BoundaryType::periodic;} };
+struct Gpu { void* stream() const { return nullptr; } };
+int main()
+{
+    if (cs_version() < 100) return 1;
+    double x[4] = {0}; uint64_t keys[4] = {0};
+    // no GPU here: the forwarder must fail loudly, not fall back (CUDA failure => print + exit(EXIT_FAILURE))
+    try { cstone_b200::computeSfcKeys(Gpu{}, x, x, x, keys, 4, Box{}); }
+    catch (std::exception& e) { std::printf("threw: %s\n", e.what()); return 3; }
+    std::printf("computed\n");
+    return 0;
+}
+'''
+
+
+def test_header_compiles_and_links():
+    lib_dir = os.path.join(PKG, "cstone_b200")
+    with tempfile.TemporaryDirectory() as tmp:
+        src = os.path.join(tmp, "t.cpp")
+        exe = os.path.join(tmp, "t")
+        open(src, "w").write(SRC)
+        subprocess.check_call(["/usr/bin/g++" if os.path.exists("/usr/bin/g++") else "g++", "-std=c++20", "-I" + os.path.join(ROOT, "include"),
+                               "-I" + os.path.join(PKG, "include"), src, "-o", exe, "-L" + lib_dir,
+                               "-l:libcstone_b200.so", "-Wl,-rpath," + lib_dir])
+        import torch
+        r = subprocess.run([exe], capture_output=True, text=True)
+        if torch.cuda.is_available():
+            assert r.returncode == 0, r.stdout + r.stderr
+        else:
+            assert r.returncode != 0 and "CUDA error" in r.stderr, (r.returncode, r.stdout, r.stderr)
