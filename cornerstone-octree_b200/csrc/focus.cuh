@@ -83,8 +83,9 @@ int findHalos(const K* prefixes, const int* childOffsets, const int* parents, co
               int firstLeaf, int lastLeaf, uint8_t* flags, cudaStream_t s);
 template<class T>
 int findNeighbors(const T* x, const T* y, const T* z, const T* h, uint32_t first, uint32_t last, const double* lim,
-                  const int* bnd, const int* childOffsets, const int* parents, const int* internalToLeaf,
-                  const uint32_t* layout, const T* centers, const T* sizes, uint32_t ngmax, uint32_t* neighbors,
+                  const int* bnd, int numLeaves, const int* childOffsets, const int* parents,
+                  const int* internalToLeaf, const uint32_t* layout, const T* centers, const T* sizes, uint32_t ngmax,
+                  uint32_t* neighbors,
                   uint32_t* neighborsCount, cudaStream_t s);
 
 } // namespace csb

@@ -5,13 +5,14 @@
  * sequence (:56-63) and the gather kernels (:74-90).  Results are fully specified (stable ascending order), so
  * parity is bit-exact against the CPU std::stable_sort path (primitives/gather.hpp:42-67).
  *
- * Per digit pass, a 512-thread CTA owns one tile of keys (dynamic tile ids, so predecessors are always resident):
- *   warp-striped load -> per-warp digit ranks with match.any (stable: rank order == input order)
+ * Per digit pass, a 384-thread CTA owns one tile of keys (dynamic tile ids, so predecessors are always resident):
+ *   warp-striped load -> per-warp digit ranks from 8 ballots (stable: rank order == input order)
  *   -> CTA digit histogram -> publish AGGREGATE -> decoupled look-back over predecessor tiles -> publish INCLUSIVE
  *   -> keys/values staged in shared memory in locally sorted order -> run-coalesced stores.
  * Algorithmic traffic: K (histogram read) + passes * 2 * (K + 4) bytes per element (200 B for u64 keys + u32 index).
  */
 #include <algorithm>
+#include <type_traits>
 
 #include "common.cuh"
 #include "cstone_b200.h"
@@ -24,8 +25,7 @@ namespace
 
 constexpr int RADIX_BITS   = 8;
 constexpr int RADIX        = 1 << RADIX_BITS;
-constexpr int SORT_THREADS = 512;
-constexpr int SORT_WARPS   = SORT_THREADS / 32;
+constexpr int MIN_TILE = 2048; // smallest tile of any kernel variant (sizes the look-back state)
 
 constexpr uint32_t FLAG_AGG   = 1u << 30;
 constexpr uint32_t FLAG_INCL  = 2u << 30;
@@ -35,12 +35,20 @@ constexpr uint32_t VALUE_MASK = ~FLAG_MASK;
 template<class K>
 struct SortCfg
 {
-    static constexpr int passes = sizeof(K);                   // 8-bit digits over all key bits
-    static constexpr int ipt    = sizeof(K) == 8 ? 12 : 16;    // items per thread
-    static constexpr int tile   = SORT_THREADS * ipt;
-    static constexpr size_t smemBytes =
-        size_t(tile) * sizeof(K) + size_t(tile) * 4 + size_t(SORT_WARPS) * RADIX * 4 + RADIX * 4 + 64 * 4;
+    static constexpr int passes = sizeof(K); // 8-bit digits over all key bits
 };
+
+template<class K>
+constexpr size_t sortSmemBytes(int threads, int ipt)
+{
+    return size_t(threads) * ipt * sizeof(K) + size_t(threads) * ipt * 4 + size_t(threads / 32) * RADIX * 4 +
+           RADIX * 4 + 64 * 4;
+}
+
+//! kernel variant used by sortByKey: 0 = 512x12, 1 = 256x12, 2 = 256x15, 3 = 384x12 (default, fastest in
+//! tools/exp_sort.py), 4 = 256x9 (threads x keys/thread for 64-bit keys; 32-bit keys take 4/3 as many)
+int g_sortVariant = 3;
+int g_sortDebugNoLookback = 0; // experiments only: wrong results, isolates the cost of the look-back chain
 
 /* ---------------------------------------------------------------- histogram of all digit places */
 
@@ -96,8 +104,8 @@ __global__ void __launch_bounds__(RADIX) scanHistogramKernel(uint32_t* globalHis
 
 /* ---------------------------------------------------------------- one digit pass */
 
-template<class K, bool HAS_VALUES>
-__global__ void __launch_bounds__(SORT_THREADS, 2) onesweepKernel(const K* __restrict__ keysIn,
+template<class K, bool HAS_VALUES, int THREADS, int IPT, int MINB>
+__global__ void __launch_bounds__(THREADS, MINB) onesweepKernel(const K* __restrict__ keysIn,
                                                                   K* __restrict__ keysOut,
                                                                   const uint32_t* __restrict__ valsIn,
                                                                   uint32_t* __restrict__ valsOut,
@@ -105,11 +113,13 @@ __global__ void __launch_bounds__(SORT_THREADS, 2) onesweepKernel(const K* __res
                                                                   int shift,
                                                                   const uint32_t* __restrict__ digitBase,
                                                                   volatile uint32_t* tileStates,
-                                                                  uint32_t* tileCounter)
+                                                                  uint32_t* tileCounter,
+                                                                  int debugNoLookback)
 {
-    using Cfg          = SortCfg<K>;
-    constexpr int IPT  = Cfg::ipt;
-    constexpr int TILE = Cfg::tile;
+    constexpr int TILE         = THREADS * IPT;
+    constexpr int SORT_THREADS = THREADS;
+    constexpr int SORT_WARPS   = THREADS / 32;
+    static_assert(THREADS >= RADIX, "one thread per digit bin in the scan phases");
 
     extern __shared__ __align__(16) unsigned char smemRaw[];
     K* keysS           = reinterpret_cast<K*>(smemRaw);
@@ -128,14 +138,24 @@ __global__ void __launch_bounds__(SORT_THREADS, 2) onesweepKernel(const K* __res
     const size_t tileBase  = size_t(tileIdx) * TILE;
     const uint32_t tileCount = uint32_t(min(size_t(TILE), n - tileBase));
 
-    /* ---- load (warp-striped: element order == (warp, item, lane) order) */
+    /* ---- load (warp-striped: element order == (warp, item, lane) order); 32-bit offsets inside the tile */
     K key[IPT];
-    const size_t warpBase = tileBase + size_t(warp) * 32 * IPT + lane;
-#pragma unroll
-    for (int i = 0; i < IPT; ++i)
+    const uint32_t warpOff = warp * 32 * IPT + lane;
+    const K* tileKeys      = keysIn + tileBase;
+    if (tileCount == TILE)
     {
-        size_t idx = warpBase + size_t(i) * 32;
-        key[i]     = idx < n ? keysIn[idx] : K(~K(0));
+#pragma unroll
+        for (int i = 0; i < IPT; ++i)
+            key[i] = tileKeys[warpOff + i * 32];
+    }
+    else
+    {
+#pragma unroll
+        for (int i = 0; i < IPT; ++i)
+        {
+            uint32_t off = warpOff + i * 32;
+            key[i]       = off < tileCount ? tileKeys[off] : K(~K(0));
+        }
     }
 
     /* ---- stable ranks within the warp per digit */
@@ -145,7 +165,16 @@ __global__ void __launch_bounds__(SORT_THREADS, 2) onesweepKernel(const K* __res
     for (int i = 0; i < IPT; ++i)
     {
         unsigned d      = unsigned((key[i] >> shift) & (RADIX - 1));
-        unsigned peers  = __match_any_sync(0xffffffffu, d);
+        // lanes holding the same digit, from 8 ballots: MATCH.ANY runs on the ADU pipe at ~1 warp instruction per
+        // 64 cycles per SM on sm_100 and was the limiter of this kernel (profiles/r1_first_path_summary.txt)
+        unsigned peers = 0xffffffffu;
+#pragma unroll
+        for (int b = 0; b < RADIX_BITS; ++b)
+        {
+            const unsigned bit  = (d >> b) & 1u;
+            const unsigned vote = __ballot_sync(0xffffffffu, bit);
+            peers &= vote ^ (bit - 1u); // bit set: keep voters; bit clear: keep non-voters
+        }
         unsigned leader = __ffs(peers) - 1;
         unsigned below  = __popc(peers & ((1u << lane) - 1u));
         uint32_t pre    = 0;
@@ -197,7 +226,7 @@ __global__ void __launch_bounds__(SORT_THREADS, 2) onesweepKernel(const K* __res
         else
         {
             *myState = FLAG_AGG | binCount;
-            for (long long t = (long long)tileIdx - 1; t >= 0; --t)
+            for (long long t = (long long)tileIdx - 1; t >= 0 && !debugNoLookback; --t)
             {
                 volatile uint32_t* p = tileStates + size_t(t) * RADIX + tid;
                 uint32_t s;
@@ -237,11 +266,21 @@ __global__ void __launch_bounds__(SORT_THREADS, 2) onesweepKernel(const K* __res
 
     if constexpr (HAS_VALUES)
     {
-#pragma unroll
-        for (int i = 0; i < IPT; ++i)
+        const uint32_t* tileVals = valsIn + tileBase;
+        if (tileCount == TILE)
         {
-            size_t idx = warpBase + size_t(i) * 32;
-            if (idx < n) { valsS[rank[i]] = valsIn[idx]; }
+#pragma unroll
+            for (int i = 0; i < IPT; ++i)
+                valsS[rank[i]] = tileVals[warpOff + i * 32];
+        }
+        else
+        {
+#pragma unroll
+            for (int i = 0; i < IPT; ++i)
+            {
+                uint32_t off = warpOff + i * 32;
+                if (off < tileCount) { valsS[rank[i]] = tileVals[off]; }
+            }
         }
         __syncthreads();
         for (uint32_t j = tid; j < tileCount; j += SORT_THREADS)
@@ -256,7 +295,7 @@ template<class K>
 size_t sortTempBytes(size_t n)
 {
     using Cfg       = SortCfg<K>;
-    size_t numTiles = (n + Cfg::tile - 1) / Cfg::tile;
+    size_t numTiles = (n + MIN_TILE - 1) / MIN_TILE;
     size_t words    = size_t(Cfg::passes) * RADIX      // digit histograms
                    + 64                                // tile counters (one per pass)
                    + size_t(Cfg::passes) * numTiles * RADIX; // look-back states
@@ -273,56 +312,78 @@ int sortByKey(K* keys, uint32_t* values, size_t n, K* keyBuf, uint32_t* valueBuf
     CSB_REQUIRE(tmpBytes >= sortTempBytes<K>(n), "sort_by_key temp storage too small");
     CSB_REQUIRE(keyBuf != nullptr && (values == nullptr || valueBuf != nullptr), "sort_by_key needs double buffers");
 
-    static bool attrSet[64][2] = {};
-    int dev                    = 0;
+    int dev = 0, numSm = 0;
     CSB_CHECK(cudaGetDevice(&dev));
-    CSB_REQUIRE(dev < 64, "device ordinal too large");
-    if (!attrSet[dev][0])
-    {
-        CSB_CHECK(cudaFuncSetAttribute(onesweepKernel<K, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       int(Cfg::smemBytes)));
-        CSB_CHECK(cudaFuncSetAttribute(onesweepKernel<K, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       int(Cfg::smemBytes)));
-        attrSet[dev][0] = true;
-    }
-    int numSm = 0;
     CSB_CHECK(cudaDeviceGetAttribute(&numSm, cudaDevAttrMultiProcessorCount, dev));
 
-    size_t numTiles      = (n + Cfg::tile - 1) / Cfg::tile;
-    uint32_t* hist       = reinterpret_cast<uint32_t*>((reinterpret_cast<uintptr_t>(tmp) + 255) & ~uintptr_t(255));
-    uint32_t* counters   = hist + Cfg::passes * RADIX;
-    uint32_t* tileStates = counters + 64;
-    size_t zeroBytes     = (size_t(Cfg::passes) * RADIX + 64 + size_t(Cfg::passes) * numTiles * RADIX) * 4;
-    CSB_CHECK(cudaMemsetAsync(hist, 0, zeroBytes, stream));
+    uint32_t* hist     = reinterpret_cast<uint32_t*>((reinterpret_cast<uintptr_t>(tmp) + 255) & ~uintptr_t(255));
+    uint32_t* counters = hist + Cfg::passes * RADIX;
+    uint32_t* states   = counters + 64;
 
     unsigned histGrid = unsigned(std::min<size_t>(size_t(numSm) * 4, (n + 511) / 512));
-    radixHistogramKernel<K><<<histGrid, 512, 0, stream>>>(keys, n, hist);
-    CSB_LAUNCH_CHECK();
-    scanHistogramKernel<<<Cfg::passes, RADIX, 0, stream>>>(hist);
-    CSB_LAUNCH_CHECK();
-
-    K* kin         = keys;
-    K* kout        = keyBuf;
-    uint32_t* vin  = values;
-    uint32_t* vout = valueBuf;
-    for (int p = 0; p < Cfg::passes; ++p)
+    int status        = 0;
+    auto run = [&](auto threadsC, auto iptC, auto minbC)
     {
-        if (values)
+        constexpr int THREADS = decltype(threadsC)::value;
+        constexpr int IPT     = decltype(iptC)::value * (sizeof(K) == 8 ? 3 : 4) / 3; // u32 keys: 4/3 more per thread
+        constexpr int MINB    = decltype(minbC)::value;
+        constexpr int TILE    = THREADS * IPT;
+        constexpr size_t smem = sortSmemBytes<K>(THREADS, IPT);
+        auto kv               = onesweepKernel<K, true, THREADS, IPT, MINB>;
+        auto ko               = onesweepKernel<K, false, THREADS, IPT, MINB>;
+        if (cudaFuncSetAttribute(kv, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)) != cudaSuccess ||
+            cudaFuncSetAttribute(ko, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)) != cudaSuccess)
         {
-            onesweepKernel<K, true><<<unsigned(numTiles), SORT_THREADS, Cfg::smemBytes, stream>>>(
-                kin, kout, vin, vout, n, p * RADIX_BITS, hist + p * RADIX, tileStates + size_t(p) * numTiles * RADIX,
-                counters + p);
+            setLastError("sort_by_key: cannot configure shared memory");
+            status = 1;
+            return;
         }
-        else
+        size_t numTiles  = (n + TILE - 1) / TILE;
+        size_t zeroBytes = (size_t(Cfg::passes) * RADIX + 64 + size_t(Cfg::passes) * numTiles * RADIX) * 4;
+        if (cudaMemsetAsync(hist, 0, zeroBytes, stream) != cudaSuccess)
         {
-            onesweepKernel<K, false><<<unsigned(numTiles), SORT_THREADS, Cfg::smemBytes, stream>>>(
-                kin, kout, nullptr, nullptr, n, p * RADIX_BITS, hist + p * RADIX,
-                tileStates + size_t(p) * numTiles * RADIX, counters + p);
+            setLastError("sort_by_key: memset failed");
+            status = 1;
+            return;
         }
-        CSB_LAUNCH_CHECK();
-        std::swap(kin, kout);
-        std::swap(vin, vout);
+        radixHistogramKernel<K><<<histGrid, 512, 0, stream>>>(keys, n, hist);
+        countLaunch();
+        scanHistogramKernel<<<Cfg::passes, RADIX, 0, stream>>>(hist);
+        countLaunch();
+
+        K* kin         = keys;
+        K* kout        = keyBuf;
+        uint32_t* vin  = values;
+        uint32_t* vout = valueBuf;
+        for (int p = 0; p < Cfg::passes; ++p)
+        {
+            uint32_t* st = states + size_t(p) * numTiles * RADIX;
+            if (values)
+            {
+                kv<<<unsigned(numTiles), THREADS, smem, stream>>>(kin, kout, vin, vout, n, p * RADIX_BITS,
+                                                                  hist + p * RADIX, st, counters + p, g_sortDebugNoLookback);
+            }
+            else
+            {
+                ko<<<unsigned(numTiles), THREADS, smem, stream>>>(kin, kout, nullptr, nullptr, n, p * RADIX_BITS,
+                                                                  hist + p * RADIX, st, counters + p, g_sortDebugNoLookback);
+            }
+            countLaunch();
+            std::swap(kin, kout);
+            std::swap(vin, vout);
+        }
+    };
+    using std::integral_constant;
+    switch (g_sortVariant)
+    {
+        case 1: run(integral_constant<int, 256>{}, integral_constant<int, 12>{}, integral_constant<int, 4>{}); break;
+        case 2: run(integral_constant<int, 256>{}, integral_constant<int, 15>{}, integral_constant<int, 3>{}); break;
+        case 3: run(integral_constant<int, 384>{}, integral_constant<int, 12>{}, integral_constant<int, 3>{}); break;
+        case 4: run(integral_constant<int, 256>{}, integral_constant<int, 9>{}, integral_constant<int, 5>{}); break;
+        default: run(integral_constant<int, 512>{}, integral_constant<int, 12>{}, integral_constant<int, 2>{}); break;
     }
+    if (status) { return status; }
+    CSB_CHECK(cudaGetLastError());
     // passes is even for both key widths, so the sorted data is back in keys/values
     static_assert(Cfg::passes % 2 == 0);
     return 0;
@@ -379,6 +440,11 @@ int sortByKeyU32(uint32_t* keys, uint32_t* values, size_t n, uint32_t* keyBuf, u
     return sortByKey<uint32_t>(keys, values, n, keyBuf, valueBuf, tmp, tmpBytes, stream);
 }
 
+void setSortVariant(int v)
+{
+    g_sortVariant          = v % 100;
+    g_sortDebugNoLookback = v >= 100;
+}
 size_t sortTempBytesU64(size_t n) { return sortTempBytes<uint64_t>(n); }
 size_t sortTempBytesU32(size_t n) { return sortTempBytes<uint32_t>(n); }
 
@@ -386,6 +452,13 @@ size_t sortTempBytesU32(size_t n) { return sortTempBytes<uint32_t>(n); }
 
 extern "C"
 {
+
+/* tuning hook (not part of the drop-in surface): select the onesweep kernel variant */
+int cs_sort_set_variant(int variant)
+{
+    csb::setSortVariant(variant);
+    return 0;
+}
 
 size_t cs_sort_by_key_temp_bytes_u32(size_t n) { return csb::sortTempBytesU32(n); }
 size_t cs_sort_by_key_temp_bytes_u64(size_t n) { return csb::sortTempBytesU64(n); }

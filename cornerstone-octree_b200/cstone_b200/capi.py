@@ -268,7 +268,7 @@ def find_neighbors(x, y, z, h, first, last, lim, bnd, tree, layout, centers, siz
     lim_a, bnd_a = _box(lim, bnd)
     f = getattr(lib(), "cs_find_neighbors_" + sfx)
     _check(f(_ptr(x), _ptr(y), _ptr(z), _ptr(h), C.c_uint32(first), C.c_uint32(last), lim_a, bnd_a,
-             _ptr(tree.child_offsets), _ptr(tree.parents), _ptr(tree.internal_to_leaf), _ptr(layout), _ptr(centers),
+             C.c_int(tree.num_leaves), _ptr(tree.child_offsets), _ptr(tree.parents), _ptr(tree.internal_to_leaf), _ptr(layout), _ptr(centers),
              _ptr(sizes), C.c_uint32(ngmax), _ptr(neighbors), _ptr(counts), _stream()), "cs_find_neighbors_" + sfx)
     return neighbors.view(nloc, ngmax), counts
 

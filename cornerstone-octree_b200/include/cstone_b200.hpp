@@ -198,15 +198,15 @@ void findNeighborsGpu(const Exec& exec,
     auto* sizes   = reinterpret_cast<const T*>(tree.sizes);
     if constexpr (std::is_same_v<T, double>)
     {
-        csCheck(cs_find_neighbors_d(x, y, z, h, firstId, lastId, b.lim, b.bnd, tree.childOffsets, tree.parents,
-                                    tree.internalToLeaf, tree.layout, centers, sizes, ngmax, neighbors, neighborsCount,
-                                    streamOf(exec)),
+        csCheck(cs_find_neighbors_d(x, y, z, h, firstId, lastId, b.lim, b.bnd, tree.numLeafNodes, tree.childOffsets,
+                                    tree.parents, tree.internalToLeaf, tree.layout, centers, sizes, ngmax, neighbors,
+                                    neighborsCount, streamOf(exec)),
                 "findNeighbors");
     }
     else
     {
-        csCheck(cs_find_neighbors_f(x, y, z, h, firstId, lastId, b.lim, b.bnd, tree.childOffsets, tree.parents,
-                                    tree.internalToLeaf, tree.layout, centers, sizes, ngmax, neighbors, neighborsCount,
+        csCheck(cs_find_neighbors_f(x, y, z, h, firstId, lastId, b.lim, b.bnd, tree.numLeafNodes, tree.childOffsets,
+                                    tree.parents, tree.internalToLeaf, tree.layout, centers, sizes, ngmax, neighbors, neighborsCount,
                                     streamOf(exec)),
                 "findNeighbors");
     }

@@ -153,12 +153,12 @@ int cs_find_halos_u64d(const uint64_t* prefixes, const int* childOffsets, const 
  * neighbors[(i-firstId)*ngmax + k] (ascending particle index, truncated at ngmax), neighborsCount[i-firstId]
  * (not truncated).  Tree arrays as in OctreeNsView (tree/octree.hpp:259-283); layout[numLeaves+1]. */
 int cs_find_neighbors_f(const float* x, const float* y, const float* z, const float* h, uint32_t firstId,
-                        uint32_t lastId, const double* lim, const int* bnd, const int* childOffsets,
+                        uint32_t lastId, const double* lim, const int* bnd, int numLeaves, const int* childOffsets,
                         const int* parents, const int* internalToLeaf, const uint32_t* layout, const float* centers,
                         const float* sizes, uint32_t ngmax, uint32_t* neighbors, uint32_t* neighborsCount,
                         void* stream);
 int cs_find_neighbors_d(const double* x, const double* y, const double* z, const double* h, uint32_t firstId,
-                        uint32_t lastId, const double* lim, const int* bnd, const int* childOffsets,
+                        uint32_t lastId, const double* lim, const int* bnd, int numLeaves, const int* childOffsets,
                         const int* parents, const int* internalToLeaf, const uint32_t* layout, const double* centers,
                         const double* sizes, uint32_t ngmax, uint32_t* neighbors, uint32_t* neighborsCount,
                         void* stream);
