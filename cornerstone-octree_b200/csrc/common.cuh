@@ -55,6 +55,19 @@ void countLaunch();
         CSB_CHECK(cudaGetLastError());                                                                                 \
     } while (0)
 
+//! library-owned scratch, one growing buffer per (device, stream, slot); nullptr (+ last error) on failure (lib.cu)
+void* scratch(cudaStream_t s, int slot, size_t bytes);
+enum ScratchSlot : int
+{
+    SCRATCH_A = 0,
+    SCRATCH_B = 1,
+    SCRATCH_C = 2,
+    SCRATCH_D = 3
+};
+#define CSB_SCRATCH(ptr, type, stream, slot, bytes)                                                                    \
+    type ptr = static_cast<type>(::csb::scratch(stream, slot, bytes));                                                 \
+    if (!ptr) { return 1; }
+
 inline unsigned iceil(size_t a, size_t b) { return unsigned((a + b - 1) / b); }
 
 /* ------------------------------------------------------------------------------------------------ key traits */

@@ -192,12 +192,9 @@ int computeOctree(const K* keys, size_t n, uint32_t bucketSize, K* leaves, uint3
                   int* numLeavesOut, cudaStream_t s)
 {
     CSB_REQUIRE(capacity >= 1, "leaf capacity must be positive");
-    K* alt       = nullptr;
-    int* nodeOps = nullptr;
-    void* tmp    = nullptr;
-    CSB_CHECK(cudaMallocAsync(&alt, (size_t(capacity) + 1) * sizeof(K), s));
-    CSB_CHECK(cudaMallocAsync(&nodeOps, (size_t(capacity) + 1) * sizeof(int), s));
-    CSB_CHECK(cudaMallocAsync(&tmp, nodeOpsTempBytes(capacity), s));
+    CSB_SCRATCH(alt, K*, s, SCRATCH_A, (size_t(capacity) + 1) * sizeof(K));
+    CSB_SCRATCH(nodeOps, int*, s, SCRATCH_B, (size_t(capacity) + 1) * sizeof(int));
+    CSB_SCRATCH(tmp, void*, s, SCRATCH_C, nodeOpsTempBytes(capacity));
 
     K root[2]      = {0, nodeRange<K>(0)};
     uint32_t cnt0  = uint32_t(std::min<size_t>(n, 0xFFFFFFFFu));
@@ -236,9 +233,6 @@ int computeOctree(const K* keys, size_t n, uint32_t bucketSize, K* leaves, uint3
         }
         *numLeavesOut = numLeaves;
     }
-    cudaFreeAsync(alt, s);
-    cudaFreeAsync(nodeOps, s);
-    cudaFreeAsync(tmp, s);
     CSB_CHECK(cudaStreamSynchronize(s));
     return status;
 }

@@ -1,5 +1,7 @@
 /* library-level state: last error string, launch counter, version */
+#include <algorithm>
 #include <atomic>
+#include <map>
 #include <mutex>
 
 #include "common.cuh"
@@ -19,6 +21,83 @@ void setLastError(const std::string& msg)
 }
 
 void countLaunch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
+
+/* Library-owned scratch for entry points that need internal temporaries.  The reference takes these from the
+ * stream-ordered allocator on every call (primitives_gpu.cu:289,302, octree_gpu.cu:190-199); with the default pool's
+ * release threshold of zero that returns the memory to the driver at every synchronisation, which on a GPU holding
+ * >100 GB of allocations costs up to hundreds of ms per call (measured: profiles/r1_notes.md).  Instead each
+ * (device, stream, slot) owns one buffer that only ever grows.  State is keyed per device AND stream, so two streams
+ * (or two devices) never share scratch ("Threading / stream semantics"). */
+namespace
+{
+struct ScratchKey
+{
+    int device;
+    cudaStream_t stream;
+    int slot;
+    bool operator<(const ScratchKey& o) const
+    {
+        if (device != o.device) { return device < o.device; }
+        if (stream != o.stream) { return stream < o.stream; }
+        return slot < o.slot;
+    }
+};
+struct ScratchBuf
+{
+    void* p{nullptr};
+    size_t cap{0};
+};
+std::mutex g_scratchMutex;
+std::map<ScratchKey, ScratchBuf> g_scratch;
+} // namespace
+
+void* scratch(cudaStream_t s, int slot, size_t bytes)
+{
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess)
+    {
+        setLastError("scratch: no CUDA device");
+        return nullptr;
+    }
+    std::lock_guard<std::mutex> lk(g_scratchMutex);
+    ScratchBuf& b = g_scratch[ScratchKey{dev, s, slot}];
+    if (bytes > b.cap)
+    {
+        if (b.p)
+        {
+            cudaStreamSynchronize(s);
+            cudaFree(b.p);
+            b.p   = nullptr;
+            b.cap = 0;
+        }
+        size_t newCap = std::max<size_t>(bytes + bytes / 8, 4096);
+        if (cudaMalloc(&b.p, newCap) != cudaSuccess)
+        {
+            cudaGetLastError();
+            b.p = nullptr;
+            setLastError("scratch: cudaMalloc of " + std::to_string(newCap) + " bytes failed");
+            return nullptr;
+        }
+        b.cap = newCap;
+    }
+    return b.p;
+}
+
+int releaseScratch()
+{
+    std::lock_guard<std::mutex> lk(g_scratchMutex);
+    int cur = 0;
+    cudaGetDevice(&cur);
+    for (auto& kv : g_scratch)
+    {
+        cudaSetDevice(kv.first.device);
+        cudaDeviceSynchronize();
+        cudaFree(kv.second.p);
+    }
+    g_scratch.clear();
+    cudaSetDevice(cur);
+    return 0;
+}
 
 } // namespace csb
 
@@ -41,6 +120,8 @@ int cs_set_l2_fetch_granularity(int bytes)
     CSB_CHECK(cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, size_t(bytes)));
     return 0;
 }
+
+int cs_release_scratch(void) { return csb::releaseScratch(); }
 
 uint64_t cs_kernel_launch_count(void) { return csb::g_launches.load(); }
 

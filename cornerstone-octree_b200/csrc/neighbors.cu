@@ -79,14 +79,7 @@ struct Target
     bool usePbc;
 };
 
-//! one staged candidate; 4 x T so that (x,y) and (z,pad) are each one vector LDS
-template<class T>
-struct alignas(4 * sizeof(T)) Staged
-{
-    T x, y, z, pad;
-};
-
-//! continuation test of findneighbors.hpp:108-112
+//! continuation test of findneighbors.hpp:108-112 in the reference's precision and operation order
 template<bool PBC, class T>
 __device__ inline bool cellOverlap(const Target<T>& t, const T* __restrict__ centers, const T* __restrict__ sizes,
                                    int node, const Box<T>& box)
@@ -116,10 +109,65 @@ __device__ inline bool cellOverlap(const Target<T>& t, const T* __restrict__ cen
     return n2 < t.radiusSq; // cellRadiusSq == radiusSq for searchExtFactor == 1
 }
 
+__device__ inline float warpMax(float v)
+{
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1)
+        v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+
+/* ---- certified single-precision pre-filter for double-precision searches ----
+ * B200 issues FP64 at a quarter of the FP32 rate and the search is instruction-issue bound, so for T = double every
+ * distance test is first evaluated in float on coordinates taken RELATIVE to the first target of the warp (that
+ * removes the magnitude of the box from the rounding error).  With every float coordinate difference within
+ * e = k * 2^-24 * D of the true one (D: largest relative coordinate involved; k = 4 for particle pairs, 8 for the
+ * point-cell distance which has two more roundings), the float sum of squares s satisfies
+ *      |s - d2| <= delta * s + 3 e^2 (1 + 1/delta)         (AM-GM on the cross term) + 4 * 2^-24 * s (float rounding)
+ * so with delta = 2^-12:   s < A := (r2(1-2^-22) - E)(1-2^-11)  =>  d2 < r2   in the reference's double arithmetic
+ *                          s > B := (r2(1+2^-22) + E)(1+2^-11)  =>  d2 >= r2
+ * where E = 2^-29 D^2 (pairs) or 2^-27 D^2 (cells) over-covers 3 e^2 (1 + 2^12).  Only candidates inside the band
+ * [A, B] (a shell of relative width 2^-10 around the search sphere, < 1 % of the neighbours) are re-evaluated with the
+ * reference's double expression, so the accepted set — and therefore list order, counts and truncation — is identical
+ * to the CPU result bit for bit.  Degenerate magnitudes (radius^2 below 1e-30 in float, overflow, NaN) make the band
+ * cover everything, i.e. fall back to the double expression. */
+struct Band
+{
+    float a, b;
+};
+
+__device__ inline Band makeBand(float r2f, float D, float eScale, bool active)
+{
+    Band t;
+    float E = D * D * eScale;
+    t.a     = (r2f * (1.0f - 0x1p-22f) - E) * (1.0f - 0x1p-11f);
+    t.b     = (r2f * (1.0f + 0x1p-22f) + E) * (1.0f + 0x1p-11f);
+    if (!(r2f > 1e-30f) || !(E < 3e38f))
+    {
+        t.a = -1.0f;
+        t.b = __int_as_float(0x7f800000);
+    }
+    if (!active)
+    {
+        t.a = -1.0f; // never surely inside
+        t.b = -1.0f; // always surely outside (sum of squares >= 0)
+    }
+    return t;
+}
+
+constexpr int NB_MAX_DEPTH = 23; // >= maxTreeLevel<uint64_t> + 2
+
+struct WarpShared
+{
+    float4 cand[32];                 // staged candidates (relative floats for T = double, absolute for T = float)
+    float4 geoC[8], geoS[8];         // relative centres / sizes of the 8 children of the node being expanded
+    uint8_t mask[NB_MAX_DEPTH][32];  // per tree depth, per lane: which of the 8 siblings this lane's own walk enters
+};
+
 /*! PBC = false: the box has no periodic dimension, the fold code is not even compiled in.  PBC = true: whether the
- *  fold is needed is decided per warp (any lane whose search sphere leaves the box), so interior warps run the plain
- *  loop; lanes that do not need the fold select the unfolded difference, exactly as the reference picks per particle
- *  (findneighbors.hpp:104-106,150-151). */
+ *  fold is needed is decided per warp (any lane whose search sphere leaves the box); such warps run the reference
+ *  expressions directly, lanes that do not need the fold select the unfolded difference exactly as the reference
+ *  picks per particle (findneighbors.hpp:104-106,150-151).  Interior warps take the filtered path. */
 template<class T, bool PBC>
 __global__ void __launch_bounds__(NB_THREADS) findNeighborsKernel(const T* __restrict__ x,
                                                                   const T* __restrict__ y,
@@ -139,12 +187,13 @@ __global__ void __launch_bounds__(NB_THREADS) findNeighborsKernel(const T* __res
                                                                   uint32_t* __restrict__ neighbors,
                                                                   uint32_t* __restrict__ neighborsCount)
 {
-    __shared__ Staged<T> stageAll[NB_THREADS / 32][32];
+    constexpr bool Filt = sizeof(T) == 8;
+    __shared__ WarpShared shAll[NB_THREADS / 32];
 
     const unsigned lane = threadIdx.x & 31;
     const size_t warpId = (size_t(blockIdx.x) * NB_THREADS + threadIdx.x) >> 5;
     if (warpId >= size_t(*numGroupsPtr)) { return; }
-    Staged<T>* stage = stageAll[threadIdx.x >> 5];
+    WarpShared& sh = shAll[threadIdx.x >> 5];
 
     const uint2 grp  = groups[warpId];
     const bool valid = grp.x + lane < grp.y;
@@ -164,36 +213,117 @@ __global__ void __launch_bounds__(NB_THREADS) findNeighborsKernel(const T* __res
         t.usePbc    = PBC && anyPbc && !inside;
     }
     const bool warpPbc = PBC && __any_sync(0xffffffffu, t.usePbc);
+    const bool filter  = Filt && !warpPbc;
 
-    uint32_t* row     = neighbors + size_t(i - first) * size_t(ngmax);
+    // origin of the relative single-precision frame: the first target of the group
+    const T ox = __shfl_sync(0xffffffffu, t.x, 0);
+    const T oy = __shfl_sync(0xffffffffu, t.y, 0);
+    const T oz = __shfl_sync(0xffffffffu, t.z, 0);
+    const float txf = Filt ? float(t.x - ox) : float(t.x);
+    const float tyf = Filt ? float(t.y - oy) : float(t.y);
+    const float tzf = Filt ? float(t.z - oz) : float(t.z);
+    const float r2f = float(t.radiusSq);
+    const float DwT = Filt ? warpMax(fmaxf(fabsf(txf), fmaxf(fabsf(tyf), fabsf(tzf)))) : 0.0f;
+
+    // out == row + numFound at all times; entries beyond ngmax are counted but not stored (findneighbors.hpp:139-146)
+    uint32_t* out     = neighbors + size_t(i - first) * size_t(ngmax);
     uint32_t numFound = 0;
+
+    auto append = [&](uint32_t j)
+    {
+        if (numFound < ngmax) { *out = j; }
+        ++out;
+        ++numFound;
+    };
 
     auto scanLeaf = [&](int node, bool mine)
     {
         int leafIdx = internalToLeaf[node];
         uint32_t jb = layout[leafIdx];
         uint32_t je = layout[leafIdx + 1];
+        if (Filt && !filter)
+        {
+            // periodic-boundary warps of a double-precision search: the reference expressions on broadcast loads
+            for (uint32_t j = jb; j < je; ++j)
+            {
+                T dx = x[j] - t.x;
+                T dy = y[j] - t.y;
+                T dz = z[j] - t.z;
+                T fx = pbcFold(dx, 0, box);
+                T fy = pbcFold(dy, 1, box);
+                T fz = pbcFold(dz, 2, box);
+                dx   = t.usePbc ? fx : dx;
+                dy   = t.usePbc ? fy : dy;
+                dz   = t.usePbc ? fz : dz;
+                T d2 = dx * dx + dy * dy + dz * dz;
+                if (mine && j != i && d2 < t.radiusSq) { append(j); }
+            }
+            return;
+        }
         // candidates are staged 32 at a time in shared memory with coalesced loads, then broadcast to all lanes
-        // (2 LDS per candidate instead of 3 uniform global loads: the loop was LSU-issue bound, profiles/)
         for (uint32_t base = jb; base < je; base += 32)
         {
             const uint32_t cnt = min(32u, je - base);
+            float m            = 0.0f;
             __syncwarp();
             if (lane < cnt)
             {
-                stage[lane].x = x[base + lane];
-                stage[lane].y = y[base + lane];
-                stage[lane].z = z[base + lane];
+                float4 c;
+                if (Filt)
+                {
+                    c.x = float(x[base + lane] - ox);
+                    c.y = float(y[base + lane] - oy);
+                    c.z = float(z[base + lane] - oz);
+                    m   = fmaxf(fabsf(c.x), fmaxf(fabsf(c.y), fabsf(c.z)));
+                }
+                else
+                {
+                    c.x = float(x[base + lane]);
+                    c.y = float(y[base + lane]);
+                    c.z = float(z[base + lane]);
+                }
+                c.w          = 0.0f;
+                sh.cand[lane] = c;
             }
             __syncwarp();
-            if (warpPbc)
+            if (Filt)
+            {
+                const Band band = makeBand(r2f, fmaxf(warpMax(m), DwT), 0x1p-29f, mine);
+#pragma unroll 4
+                for (uint32_t k = 0; k < cnt; ++k)
+                {
+                    const float4 c = sh.cand[k];
+                    float dx       = c.x - txf;
+                    float dy       = c.y - tyf;
+                    float dz       = c.z - tzf;
+                    float s2       = fmaf(dx, dx, fmaf(dy, dy, dz * dz));
+                    if (!(s2 > band.b))
+                    {
+                        const uint32_t j = base + k;
+                        if (s2 < band.a)
+                        {
+                            if (j != i) { append(j); }
+                        }
+                        else if (mine)
+                        {
+                            // inside the uncertainty band: the reference's own expression decides
+                            T ex = x[j] - t.x;
+                            T ey = y[j] - t.y;
+                            T ez = z[j] - t.z;
+                            if (ex * ex + ey * ey + ez * ez < t.radiusSq && j != i) { append(j); }
+                        }
+                    }
+                }
+            }
+            else if (warpPbc)
             {
                 for (uint32_t k = 0; k < cnt; ++k)
                 {
                     const uint32_t j = base + k;
-                    T dx = stage[k].x - t.x;
-                    T dy = stage[k].y - t.y;
-                    T dz = stage[k].z - t.z;
+                    const float4 c   = sh.cand[k];
+                    T dx = T(c.x) - t.x;
+                    T dy = T(c.y) - t.y;
+                    T dz = T(c.z) - t.z;
                     T fx = pbcFold(dx, 0, box);
                     T fy = pbcFold(dy, 1, box);
                     T fz = pbcFold(dz, 2, box);
@@ -201,11 +331,7 @@ __global__ void __launch_bounds__(NB_THREADS) findNeighborsKernel(const T* __res
                     dy   = t.usePbc ? fy : dy;
                     dz   = t.usePbc ? fz : dz;
                     T d2 = dx * dx + dy * dy + dz * dz;
-                    if (mine && j != i && d2 < t.radiusSq)
-                    {
-                        if (numFound < ngmax) { row[numFound] = j; }
-                        ++numFound;
-                    }
+                    if (mine && j != i && d2 < t.radiusSq) { append(j); }
                 }
             }
             else
@@ -214,62 +340,103 @@ __global__ void __launch_bounds__(NB_THREADS) findNeighborsKernel(const T* __res
                 for (uint32_t k = 0; k < cnt; ++k)
                 {
                     const uint32_t j = base + k;
-                    T dx = stage[k].x - t.x;
-                    T dy = stage[k].y - t.y;
-                    T dz = stage[k].z - t.z;
+                    const float4 c   = sh.cand[k];
+                    T dx = T(c.x) - t.x;
+                    T dy = T(c.y) - t.y;
+                    T dz = T(c.z) - t.z;
                     T d2 = dx * dx + dy * dy + dz * dz;
-                    if (mine && j != i && d2 < t.radiusSq)
-                    {
-                        if (numFound < ngmax) { row[numFound] = j; }
-                        ++numFound;
-                    }
+                    if (mine && j != i && d2 < t.radiusSq) { append(j); }
                 }
             }
         }
     };
 
-    // bit l of `path` : this lane's own walk reached (passed the test at) the current ancestor of depth l
-    uint32_t path = (valid && cellOverlap<PBC>(t, centers, sizes, 0, box)) ? 1u : 0u;
-    if (__any_sync(0xffffffffu, path))
+    //! this lane's continuation decisions for the 8 children of an internal node its own walk has entered
+    auto testChildren = [&](int child0, bool mine) -> uint32_t
+    {
+        uint32_t bits = 0;
+        if (!filter)
+        {
+            if (mine)
+            {
+#pragma unroll
+                for (int c = 0; c < 8; ++c)
+                    bits |= uint32_t(cellOverlap<PBC>(t, centers, sizes, child0 + c, box)) << c;
+            }
+            return bits;
+        }
+        float m = 0.0f;
+        __syncwarp();
+        if (lane < 8)
+        {
+            int node = child0 + int(lane);
+            float4 gc, gs;
+            gc.x = float(centers[3 * node] - ox);
+            gc.y = float(centers[3 * node + 1] - oy);
+            gc.z = float(centers[3 * node + 2] - oz);
+            gc.w = 0.0f;
+            gs.x = float(sizes[3 * node]);
+            gs.y = float(sizes[3 * node + 1]);
+            gs.z = float(sizes[3 * node + 2]);
+            gs.w = 0.0f;
+            m    = fmaxf(fmaxf(fabsf(gc.x), fmaxf(fabsf(gc.y), fabsf(gc.z))), fmaxf(gs.x, fmaxf(gs.y, gs.z)));
+            sh.geoC[lane] = gc;
+            sh.geoS[lane] = gs;
+        }
+        __syncwarp();
+        const Band band = makeBand(r2f, fmaxf(warpMax(m), DwT), 0x1p-27f, mine);
+        if (mine)
+        {
+#pragma unroll
+            for (int c = 0; c < 8; ++c)
+            {
+                const float4 gc = sh.geoC[c];
+                const float4 gs = sh.geoS[c];
+                float dx        = fmaxf(fabsf(gc.x - txf) - gs.x, 0.0f);
+                float dy        = fmaxf(fabsf(gc.y - tyf) - gs.y, 0.0f);
+                float dz        = fmaxf(fabsf(gc.z - tzf) - gs.z, 0.0f);
+                float s2        = fmaf(dx, dx, fmaf(dy, dy, dz * dz));
+                bool pass       = s2 < band.a;
+                if (!pass && !(s2 > band.b)) { pass = cellOverlap<false>(t, centers, sizes, child0 + c, box); }
+                bits |= uint32_t(pass) << c;
+            }
+        }
+        return bits;
+    };
+
+    const bool rootMine = valid && cellOverlap<PBC>(t, centers, sizes, 0, box);
+    if (__any_sync(0xffffffffu, rootMine))
     {
         int rootChild = childOffsets[0];
-        if (rootChild == 0) { scanLeaf(0, path & 1u); }
+        if (rootChild == 0) { scanLeaf(0, rootMine); }
         else
         {
-            int node       = rootChild;
-            int depth      = 1;
-            bool backtrack = false;
-            while (node != 0)
+            int depth           = 1;
+            int node            = rootChild;
+            sh.mask[1][lane]    = uint8_t(testChildren(rootChild, rootMine));
+            while (true)
             {
-                int child    = childOffsets[node];
-                bool isLeaf  = child == 0;
-                bool mine    = false;
-                bool descend = false;
-                if (!backtrack)
+                const bool mine = (sh.mask[depth][lane] >> ((node - 1) & 7)) & 1u;
+                if (__any_sync(0xffffffffu, mine))
                 {
-                    mine = ((path >> (depth - 1)) & 1u) && cellOverlap<PBC>(t, centers, sizes, node, box);
-                    path = (path & ~(1u << depth)) | (uint32_t(mine) << depth);
-                    descend = __any_sync(0xffffffffu, mine);
+                    const int child = childOffsets[node];
+                    if (child == 0) { scanLeaf(node, mine); }
+                    else
+                    {
+                        ++depth;
+                        sh.mask[depth][lane] = uint8_t(testChildren(child, mine));
+                        node                 = child;
+                        continue;
+                    }
                 }
-                if (isLeaf && descend) { scanLeaf(node, mine); }
-
-                if (!isLeaf && descend)
-                {
-                    node = child;
-                    ++depth;
-                    backtrack = false;
-                }
-                else if (((node - 1) & 7) < 7)
-                {
-                    ++node;
-                    backtrack = false;
-                }
-                else
+                while (((node - 1) & 7) == 7)
                 {
                     node = parents[(node - 1) >> 3];
                     --depth;
-                    backtrack = true;
+                    if (node == 0) { break; }
                 }
+                if (node == 0) { break; }
+                ++node;
             }
         }
     }
@@ -293,12 +460,9 @@ int findNeighbors(const T* x, const T* y, const T* z, const T* h, uint32_t first
     // leaf-aligned groups: counts -> exclusive scan -> fill.  Upper bound on the number of groups is known on the host,
     // the exact number stays on the device (no synchronisation)
     size_t maxGroups = size_t(numLeaves) + (size_t(last) - first) / 32 + 1;
-    uint32_t* groupOffsets = nullptr;
-    uint2* groups          = nullptr;
-    void* scanTmp          = nullptr;
-    CSB_CHECK(cudaMallocAsync(&groupOffsets, (size_t(numLeaves) + 1) * sizeof(uint32_t), s));
-    CSB_CHECK(cudaMallocAsync(&groups, maxGroups * sizeof(uint2), s));
-    CSB_CHECK(cudaMallocAsync(&scanTmp, scanTempBytes(size_t(numLeaves) + 1), s));
+    CSB_SCRATCH(groupOffsets, uint32_t*, s, SCRATCH_A, (size_t(numLeaves) + 1) * sizeof(uint32_t));
+    CSB_SCRATCH(groups, uint2*, s, SCRATCH_B, maxGroups * sizeof(uint2));
+    CSB_SCRATCH(scanTmp, void*, s, SCRATCH_C, scanTempBytes(size_t(numLeaves) + 1));
 
     groupCountKernel<<<iceil(numLeaves + 1, 256), 256, 0, s>>>(layout, numLeaves, first, last, groupOffsets);
     CSB_LAUNCH_CHECK();
@@ -320,9 +484,6 @@ int findNeighbors(const T* x, const T* y, const T* z, const T* h, uint32_t first
                                                                   centers, sizes, ngmax, neighbors, neighborsCount);
     }
     CSB_LAUNCH_CHECK();
-    CSB_CHECK(cudaFreeAsync(groupOffsets, s));
-    CSB_CHECK(cudaFreeAsync(groups, s));
-    CSB_CHECK(cudaFreeAsync(scanTmp, s));
     return 0;
 }
 

@@ -312,10 +312,16 @@ class Domain:
             raise CstoneError(lib().cs_last_error().decode())
         lib().cs_domain_ptr.restype = C.c_void_p
 
-    def __del__(self):
+    def close(self):
         if getattr(self, "handle", None):
             lib().cs_domain_destroy(C.c_void_p(self.handle))
             self.handle = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:  # interpreter shutdown: module globals may already be gone
+            pass
 
     def sync(self, x=None, y=None, z=None, h=None, keys=None):
         """x,y,z,h: torch tensors on the domain's device or in (pinned) host memory, or None to re-sync in place"""

@@ -35,6 +35,10 @@ const char* cs_last_error(void);
 int cs_version(void);
 /* number of CUDA kernels launched by this library in the calling process since load (for bench.py's gpu_launches) */
 uint64_t cs_kernel_launch_count(void);
+/* Entry points that need internal temporaries (the reference takes them from cudaMallocAsync, e.g.
+ * primitives_gpu.cu:289,302) use library-owned scratch that is keyed per (device, stream) and only grows;
+ * cs_release_scratch() synchronises the devices involved and frees all of it. */
+int cs_release_scratch(void);
 
 /* ---- SFC keys: computeSfcKeys(Gpu, x,y,z, keys, n, box)  sfc/sfc_gpu.h:24-26, sfc/sfc_gpu.cu:23-62 ----
  * keys[i] = sfc3D(x[i],y[i],z[i], box) unless keys[i] == removeKey = 2^(3*maxTreeLevel) (sfc/sfc.hpp:274). */

@@ -274,6 +274,73 @@ def test_find_neighbors(combo, pbc, dist):
     assert np.all((d > 0) | ~m[:, 1:])
 
 
+def _neighbors_vs_oracle(combo, x, y, z, h, lim, bnd, bucket, ngmax):
+    """sort the particles along the curve, build the tree with the oracle, compare GPU lists with the checkers"""
+    kt, T = key_of(combo), real_of(combo)
+    n = x.size
+    keys = oracle().sfc_keys(combo, 0, x, y, z, lim, bnd)
+    order = np.arange(n, dtype=np.uint32)
+    oracle().sort_by_key(kt, keys, order)
+    x, y, z, h = x[order], y[order], z[order], h[order]
+    lo, co = oracle().compute_octree(kt, keys, bucket)
+    to = oracle().build_octree(kt, lo)
+    cen_o, siz_o = oracle().node_fp_centers(combo, to["prefixes"], lim, bnd)
+    layout_o = np.zeros(lo.size, dtype=np.uint32)
+    layout_o[1:] = np.cumsum(co)
+    tree = capi().Octree(dev(lo))
+    tdtype = torch.float32 if T == np.float32 else torch.float64
+    cen, siz = capi().compute_geo_centers(tree.prefixes, tdtype, lim, bnd)
+    nb, nc = capi().find_neighbors(dev(x), dev(y), dev(z), dev(h), 0, n, lim, bnd, tree, dev(layout_o), cen, siz, ngmax)
+    nb, nc = host(nb), host(nc)
+    for name, chk in checkers():
+        nb_o, nc_o = chk.find_neighbors(combo, x, y, z, h, 0, n, lim, bnd, to, lo, layout_o, cen_o, siz_o, ngmax)
+        assert np.array_equal(nc, nc_o), name
+        m = np.arange(ngmax)[None, :] < np.minimum(nc_o, ngmax)[:, None]
+        assert np.array_equal(nb[m], nb_o[m]), name
+    return nc
+
+
+@pytest.mark.parametrize("combo", COMBOS)
+@pytest.mark.parametrize("pbc", [0, 1])
+def test_find_neighbors_lattice_exact_radius(combo, pbc):
+    """adversarial for the certified float pre-filter: lattice particles whose distances are exactly 2h (and exactly
+    representable), so d2 == r2 and the strict `<` of findneighbors.hpp:134 must exclude them; plus duplicates"""
+    T = real_of(combo)
+    g = 24
+    c = (np.arange(g, dtype=np.float64) + 0.5) / 32.0
+    x, y, z = (a.ravel().astype(T) for a in np.meshgrid(c, c, c, indexing="ij"))
+    x, y, z = (np.concatenate([a, a[:50]]) for a in (x, y, z))  # 50 coincident pairs (d2 == 0, kept: H2)
+    lim, bnd = (0, 1, 0, 1, 0, 1), (pbc, pbc, pbc)
+    for mult in (1.0, 2.0, np.sqrt(2.0), np.sqrt(3.0)):
+        h = np.full(x.size, T(0.5 * mult / 32.0), dtype=T)
+        nc = _neighbors_vs_oracle(combo, x, y, z, h, lim, bnd, 8, 64)
+        assert nc.max() > 0 or mult == 1.0
+
+
+@pytest.mark.parametrize("combo", COMBOS)
+def test_find_neighbors_offset_box_and_clustered(combo):
+    """large coordinate magnitudes relative to h (box far from the origin) and a Plummer sphere with per-particle h
+    spanning orders of magnitude: the float pre-filter's error bound must hold or defer to the exact expression"""
+    T = real_of(combo)
+    n = 30000
+    rng = np.random.default_rng(5)
+    off = 1000.0 if T == np.float32 else 1.0e6
+    x, y, z = ((off + rng.random(n)).astype(T) for _ in range(3))
+    lim = (off, off + 1, off, off + 1, off, off + 1)
+    for a in (x, y, z):
+        np.clip(a, T(off), np.nextafter(T(off + 1), T(off)), out=a)
+    h = (const_h(n, 50, T) * (0.5 + rng.random(n))).astype(T)
+    _neighbors_vs_oracle(combo, x, y, z, h, lim, (0, 0, 0), 16, 100)
+
+    x, y, z = plummer_particles(n, T, 9)
+    m = float(max(np.abs(a).max() for a in (x, y, z))) * 1.001
+    lim = (-m, m, -m, m, -m, m)
+    r = np.sqrt(x.astype(np.float64) ** 2 + y.astype(np.float64) ** 2 + z.astype(np.float64) ** 2)
+    h = (0.02 * (0.05 + r) * (0.5 + rng.random(n))).astype(T)
+    _neighbors_vs_oracle(combo, x, y, z, h, lim, (0, 0, 0), 8, 128)
+    _neighbors_vs_oracle(combo, x, y, z, h, lim, (1, 1, 1), 64, 32)
+
+
 # ------------------------------------------------------------------------------------------------ halos
 @pytest.mark.parametrize("combo", COMBOS)
 @pytest.mark.parametrize("pbc", [0, 1])
