@@ -124,8 +124,12 @@ __global__ void enforceKeysKernel(const K* __restrict__ keys,
     K nodeKeyHave     = prefixes[nodeIdx];
     int nodeLevelHave = int(decodePrefixLength(nodeKeyHave) / 3);
 
-    bool trySplit   = nodeKeyHave != nodeKeyWant && nodeLevelHave < maxLevel;
-    bool undoMerges = atomicAdd(&nodeOps[nodeIdx], 0) == 0 || trySplit;
+    // nodeOps only ever move 0 -> 1 (cancelled merge) or up (atomicMax), so a plain read that already shows the wanted
+    // state is final; the atomics are only issued when the read says work is left.  With millions of mandatory keys
+    // (the global leaves) mapping to a few coarse focus nodes this removes nearly all of the contended atomics.
+    volatile int* ops = nodeOps;
+    bool trySplit     = nodeKeyHave != nodeKeyWant && nodeLevelHave < maxLevel;
+    bool undoMerges   = ops[nodeIdx] == 0 || trySplit;
     if (undoMerges && nodeIdx > 0)
     {
         st         = ENFORCE_CANCEL_MERGE;
@@ -135,7 +139,7 @@ __global__ void enforceKeysKernel(const K* __restrict__ keys,
             parent           = parents[(parent - 1) / 8];
             int firstSibling = childOffsets[parent];
             for (int i = firstSibling; i < firstSibling + 8; ++i)
-                atomicCAS(&nodeOps[i], 0, 1);
+                if (ops[i] == 0) { atomicCAS(&nodeOps[i], 0, 1); }
         } while (parent != 0);
     }
     if (trySplit)
@@ -144,9 +148,10 @@ __global__ void enforceKeysKernel(const K* __restrict__ keys,
         int levelDiff = keyPos - nodeLevelHave;
         st            = levelDiff > 1 ? ENFORCE_FAILED : ENFORCE_REBALANCE;
         levelDiff     = levelDiff < 1 ? levelDiff : 1;
-        atomicMax(&nodeOps[nodeIdx], 1 << (3 * levelDiff));
+        int want      = 1 << (3 * levelDiff);
+        if (ops[nodeIdx] < want) { atomicMax(&nodeOps[nodeIdx], want); }
     }
-    if (st != ENFORCE_CONVERGED) { atomicMax(status, st); }
+    if (st != ENFORCE_CONVERGED && *(volatile int*)status < st) { atomicMax(status, st); }
 }
 
 //! focus/rebalance.hpp:91-116,156-169; in-place with the reference's benign race

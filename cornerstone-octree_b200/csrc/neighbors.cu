@@ -109,65 +109,53 @@ __device__ inline bool cellOverlap(const Target<T>& t, const T* __restrict__ cen
     return n2 < t.radiusSq; // cellRadiusSq == radiusSq for searchExtFactor == 1
 }
 
-__device__ inline float warpMax(float v)
-{
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1)
-        v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
-    return v;
-}
-
 /* ---- certified single-precision pre-filter for double-precision searches ----
- * B200 issues FP64 at a quarter of the FP32 rate and the search is instruction-issue bound, so for T = double every
- * distance test is first evaluated in float on coordinates taken RELATIVE to the first target of the warp (that
- * removes the magnitude of the box from the rounding error).  With every float coordinate difference within
- * e = k * 2^-24 * D of the true one (D: largest relative coordinate involved; k = 4 for particle pairs, 8 for the
- * point-cell distance which has two more roundings), the float sum of squares s satisfies
+ * B200 issues FP64 at half the FP32 rate and the search is instruction-issue bound, so for T = double every distance
+ * test is first evaluated in float on coordinates taken RELATIVE to the first target of the warp (that removes the
+ * magnitude of the box from the rounding error).  With every float coordinate difference within
+ * e = k * 2^-24 * D of the true one (D: largest relative coordinate involved; k = 4 for particle pairs, 8 for
+ * point-box distances which have more roundings), the float sum of squares s satisfies
  *      |s - d2| <= delta * s + 3 e^2 (1 + 1/delta)         (AM-GM on the cross term) + 4 * 2^-24 * s (float rounding)
  * so with delta = 2^-12:   s < A := (r2(1-2^-22) - E)(1-2^-11)  =>  d2 < r2   in the reference's double arithmetic
  *                          s > B := (r2(1+2^-22) + E)(1+2^-11)  =>  d2 >= r2
- * where E = 2^-29 D^2 (pairs) or 2^-27 D^2 (cells) over-covers 3 e^2 (1 + 2^12).  Only candidates inside the band
+ * where E = 2^-29 D^2 (pairs) or 2^-27 D^2 (boxes) over-covers 3 e^2 (1 + 2^12).  Only candidates inside the band
  * [A, B] (a shell of relative width 2^-10 around the search sphere, < 1 % of the neighbours) are re-evaluated with the
  * reference's double expression, so the accepted set — and therefore list order, counts and truncation — is identical
  * to the CPU result bit for bit.  Degenerate magnitudes (radius^2 below 1e-30 in float, overflow, NaN) make the band
- * cover everything, i.e. fall back to the double expression. */
-struct Band
-{
-    float a, b;
-};
+ * cover everything, i.e. fall back to the double expression.
+ *
+ * The same bound gives a warp-level cull: a candidate whose distance to the bounding box of the warp's targets is
+ * certainly larger than the largest search radius of the warp cannot be a neighbour of any lane and is dropped while
+ * staging (about 40 % of the particles of the 27 cells around a leaf), for float searches as well. */
+constexpr float BAND_KA = (1.0f - 0x1p-22f) * (1.0f - 0x1p-11f);
+constexpr float BAND_KB = (1.0f + 0x1p-22f) * (1.0f + 0x1p-11f);
+constexpr float BAND_SA = 1.0f - 0x1p-11f;
+constexpr float BAND_SB = 1.0f + 0x1p-11f;
 
-__device__ inline Band makeBand(float r2f, float D, float eScale, bool active)
+//! order-preserving map float -> int (for REDUX min/max); NaNs map above +inf / below -inf by sign
+__device__ inline int floatKey(float f)
 {
-    Band t;
-    float E = D * D * eScale;
-    t.a     = (r2f * (1.0f - 0x1p-22f) - E) * (1.0f - 0x1p-11f);
-    t.b     = (r2f * (1.0f + 0x1p-22f) + E) * (1.0f + 0x1p-11f);
-    if (!(r2f > 1e-30f) || !(E < 3e38f))
-    {
-        t.a = -1.0f;
-        t.b = __int_as_float(0x7f800000);
-    }
-    if (!active)
-    {
-        t.a = -1.0f; // never surely inside
-        t.b = -1.0f; // always surely outside (sum of squares >= 0)
-    }
-    return t;
+    int b = __float_as_int(f);
+    return b ^ ((b >> 31) & 0x7fffffff);
 }
+__device__ inline float keyFloat(int k) { return __int_as_float(k ^ ((k >> 31) & 0x7fffffff)); }
+__device__ inline float warpMinF(float v) { return keyFloat(__reduce_min_sync(0xffffffffu, floatKey(v))); }
+__device__ inline float warpMaxF(float v) { return keyFloat(__reduce_max_sync(0xffffffffu, floatKey(v))); }
 
 constexpr int NB_MAX_DEPTH = 23; // >= maxTreeLevel<uint64_t> + 2
+constexpr int NB_STAGE     = 64; // staged candidates per round (two half-rounds of 32 loads)
 
 struct WarpShared
 {
-    float4 cand[32];                 // staged candidates (relative floats for T = double, absolute for T = float)
-    float4 geoC[8], geoS[8];         // relative centres / sizes of the 8 children of the node being expanded
-    uint8_t mask[NB_MAX_DEPTH][32];  // per tree depth, per lane: which of the 8 siblings this lane's own walk enters
+    float4 cand[NB_STAGE];          // x, y, z (relative floats for T = double, the values themselves for T = float), j
+    float4 geoC[8], geoS[8];        // centres / sizes of the 8 children being tested; geoS.w = error term E of the child
+    uint8_t mask[NB_MAX_DEPTH][32]; // per tree depth, per lane: which of the 8 siblings this lane's own walk enters
 };
 
 /*! PBC = false: the box has no periodic dimension, the fold code is not even compiled in.  PBC = true: whether the
  *  fold is needed is decided per warp (any lane whose search sphere leaves the box); such warps run the reference
- *  expressions directly, lanes that do not need the fold select the unfolded difference exactly as the reference
- *  picks per particle (findneighbors.hpp:104-106,150-151).  Interior warps take the filtered path. */
+ *  expressions directly on broadcast loads, lanes that do not need the fold select the unfolded difference exactly as
+ *  the reference picks per particle (findneighbors.hpp:104-106,150-151).  Interior warps take the staged path. */
 template<class T, bool PBC>
 __global__ void __launch_bounds__(NB_THREADS) findNeighborsKernel(const T* __restrict__ x,
                                                                   const T* __restrict__ y,
@@ -190,8 +178,9 @@ __global__ void __launch_bounds__(NB_THREADS) findNeighborsKernel(const T* __res
     constexpr bool Filt = sizeof(T) == 8;
     __shared__ WarpShared shAll[NB_THREADS / 32];
 
-    const unsigned lane = threadIdx.x & 31;
-    const size_t warpId = (size_t(blockIdx.x) * NB_THREADS + threadIdx.x) >> 5;
+    const unsigned lane   = threadIdx.x & 31;
+    const unsigned ltMask = (1u << lane) - 1u;
+    const size_t warpId   = (size_t(blockIdx.x) * NB_THREADS + threadIdx.x) >> 5;
     if (warpId >= size_t(*numGroupsPtr)) { return; }
     WarpShared& sh = shAll[threadIdx.x >> 5];
 
@@ -213,17 +202,36 @@ __global__ void __launch_bounds__(NB_THREADS) findNeighborsKernel(const T* __res
         t.usePbc    = PBC && anyPbc && !inside;
     }
     const bool warpPbc = PBC && __any_sync(0xffffffffu, t.usePbc);
-    const bool filter  = Filt && !warpPbc;
 
-    // origin of the relative single-precision frame: the first target of the group
-    const T ox = __shfl_sync(0xffffffffu, t.x, 0);
-    const T oy = __shfl_sync(0xffffffffu, t.y, 0);
-    const T oz = __shfl_sync(0xffffffffu, t.z, 0);
-    const float txf = Filt ? float(t.x - ox) : float(t.x);
-    const float tyf = Filt ? float(t.y - oy) : float(t.y);
-    const float tzf = Filt ? float(t.z - oz) : float(t.z);
+    // single-precision frame: relative to the first target of the group for double searches, absolute for float
+    const T ox = Filt ? __shfl_sync(0xffffffffu, t.x, 0) : T(0);
+    const T oy = Filt ? __shfl_sync(0xffffffffu, t.y, 0) : T(0);
+    const T oz = Filt ? __shfl_sync(0xffffffffu, t.z, 0) : T(0);
+    const float txf = float(t.x - ox);
+    const float tyf = float(t.y - oy);
+    const float tzf = float(t.z - oz);
     const float r2f = float(t.radiusSq);
-    const float DwT = Filt ? warpMax(fmaxf(fabsf(txf), fmaxf(fabsf(tyf), fabsf(tzf)))) : 0.0f;
+
+    // bounding box of the targets, largest radius, and the magnitude bounds of the error terms (group constants)
+    const float lox = warpMinF(txf), hix = warpMaxF(txf);
+    const float loy = warpMinF(tyf), hiy = warpMaxF(tyf);
+    const float loz = warpMinF(tzf), hiz = warpMaxF(tzf);
+    const float DwT = fmaxf(fmaxf(fmaxf(fabsf(lox), fabsf(hix)), fmaxf(fabsf(loy), fabsf(hiy))),
+                            fmaxf(fabsf(loz), fabsf(hiz)));
+    const float r2max = warpMaxF(r2f);
+    const float r2bMax = (r2max > 1e-30f) ? r2max * BAND_KB : __int_as_float(0x7f800000);
+
+    float r2a = r2f * BAND_KA, r2b = r2f * BAND_KB;
+    if (!(r2f > 1e-30f))
+    {
+        r2a = -1.0f;
+        r2b = __int_as_float(0x7f800000);
+    }
+    // every staged (un-culled) candidate has |coordinate| <= 1.01 (DwT + sqrt(r2max)), see the cull test
+    const float Dpair = 1.01f * (DwT + sqrtf(r2max));
+    const float Epair = Dpair * Dpair * 0x1p-29f;
+    const float pairA = fmaf(-Epair, BAND_SA, r2a);
+    const float pairB = fmaf(Epair, BAND_SB, r2b);
 
     // out == row + numFound at all times; entries beyond ngmax are counted but not stored (findneighbors.hpp:139-146)
     uint32_t* out     = neighbors + size_t(i - first) * size_t(ngmax);
@@ -241,9 +249,9 @@ __global__ void __launch_bounds__(NB_THREADS) findNeighborsKernel(const T* __res
         int leafIdx = internalToLeaf[node];
         uint32_t jb = layout[leafIdx];
         uint32_t je = layout[leafIdx + 1];
-        if (Filt && !filter)
+        if (warpPbc)
         {
-            // periodic-boundary warps of a double-precision search: the reference expressions on broadcast loads
+            // warps touching a periodic boundary: the reference expressions on broadcast loads
             for (uint32_t j = jb; j < je; ++j)
             {
                 T dx = x[j] - t.x;
@@ -260,35 +268,39 @@ __global__ void __launch_bounds__(NB_THREADS) findNeighborsKernel(const T* __res
             }
             return;
         }
-        // candidates are staged 32 at a time in shared memory with coalesced loads, then broadcast to all lanes
-        for (uint32_t base = jb; base < je; base += 32)
+        const float bandA = mine ? pairA : -1.0f; // not mine: never inside ...
+        const float bandB = mine ? pairB : -1.0f; // ... and always surely outside (sums of squares are >= 0)
+        for (uint32_t base = jb; base < je; base += NB_STAGE)
         {
-            const uint32_t cnt = min(32u, je - base);
-            float m            = 0.0f;
+            // stage up to 64 candidates with coalesced loads, dropping those no lane can reach
+            uint32_t cnt = 0;
             __syncwarp();
-            if (lane < cnt)
+#pragma unroll
+            for (int half = 0; half < NB_STAGE / 32; ++half)
             {
+                const uint32_t j = base + half * 32 + lane;
+                bool keep        = false;
                 float4 c;
-                if (Filt)
+                if (j < je)
                 {
-                    c.x = float(x[base + lane] - ox);
-                    c.y = float(y[base + lane] - oy);
-                    c.z = float(z[base + lane] - oz);
-                    m   = fmaxf(fabsf(c.x), fmaxf(fabsf(c.y), fabsf(c.z)));
+                    c.x = float(x[j] - ox);
+                    c.y = float(y[j] - oy);
+                    c.z = float(z[j] - oz);
+                    c.w = __uint_as_float(j);
+                    float D  = fmaxf(fmaxf(fabsf(c.x), fabsf(c.y)), fmaxf(fabsf(c.z), DwT));
+                    float bc = fmaf(D * D * 0x1p-27f, BAND_SB, r2bMax);
+                    float ex = fmaxf(fmaxf(lox - c.x, c.x - hix), 0.0f);
+                    float ey = fmaxf(fmaxf(loy - c.y, c.y - hiy), 0.0f);
+                    float ez = fmaxf(fmaxf(loz - c.z, c.z - hiz), 0.0f);
+                    keep     = !(fmaf(ex, ex, fmaf(ey, ey, ez * ez)) > bc);
                 }
-                else
-                {
-                    c.x = float(x[base + lane]);
-                    c.y = float(y[base + lane]);
-                    c.z = float(z[base + lane]);
-                }
-                c.w          = 0.0f;
-                sh.cand[lane] = c;
+                const unsigned km = __ballot_sync(0xffffffffu, keep);
+                if (keep) { sh.cand[cnt + __popc(km & ltMask)] = c; }
+                cnt += __popc(km);
             }
             __syncwarp();
             if (Filt)
             {
-                const Band band = makeBand(r2f, fmaxf(warpMax(m), DwT), 0x1p-29f, mine);
 #pragma unroll 4
                 for (uint32_t k = 0; k < cnt; ++k)
                 {
@@ -297,10 +309,10 @@ __global__ void __launch_bounds__(NB_THREADS) findNeighborsKernel(const T* __res
                     float dy       = c.y - tyf;
                     float dz       = c.z - tzf;
                     float s2       = fmaf(dx, dx, fmaf(dy, dy, dz * dz));
-                    if (!(s2 > band.b))
+                    if (!(s2 > bandB))
                     {
-                        const uint32_t j = base + k;
-                        if (s2 < band.a)
+                        const uint32_t j = __float_as_uint(c.w);
+                        if (s2 < bandA)
                         {
                             if (j != i) { append(j); }
                         }
@@ -315,32 +327,13 @@ __global__ void __launch_bounds__(NB_THREADS) findNeighborsKernel(const T* __res
                     }
                 }
             }
-            else if (warpPbc)
-            {
-                for (uint32_t k = 0; k < cnt; ++k)
-                {
-                    const uint32_t j = base + k;
-                    const float4 c   = sh.cand[k];
-                    T dx = T(c.x) - t.x;
-                    T dy = T(c.y) - t.y;
-                    T dz = T(c.z) - t.z;
-                    T fx = pbcFold(dx, 0, box);
-                    T fy = pbcFold(dy, 1, box);
-                    T fz = pbcFold(dz, 2, box);
-                    dx   = t.usePbc ? fx : dx;
-                    dy   = t.usePbc ? fy : dy;
-                    dz   = t.usePbc ? fz : dz;
-                    T d2 = dx * dx + dy * dy + dz * dz;
-                    if (mine && j != i && d2 < t.radiusSq) { append(j); }
-                }
-            }
             else
             {
 #pragma unroll 4
                 for (uint32_t k = 0; k < cnt; ++k)
                 {
-                    const uint32_t j = base + k;
                     const float4 c   = sh.cand[k];
+                    const uint32_t j = __float_as_uint(c.w);
                     T dx = T(c.x) - t.x;
                     T dy = T(c.y) - t.y;
                     T dz = T(c.z) - t.z;
@@ -355,7 +348,7 @@ __global__ void __launch_bounds__(NB_THREADS) findNeighborsKernel(const T* __res
     auto testChildren = [&](int child0, bool mine) -> uint32_t
     {
         uint32_t bits = 0;
-        if (!filter)
+        if (warpPbc)
         {
             if (mine)
             {
@@ -365,7 +358,6 @@ __global__ void __launch_bounds__(NB_THREADS) findNeighborsKernel(const T* __res
             }
             return bits;
         }
-        float m = 0.0f;
         __syncwarp();
         if (lane < 8)
         {
@@ -378,13 +370,13 @@ __global__ void __launch_bounds__(NB_THREADS) findNeighborsKernel(const T* __res
             gs.x = float(sizes[3 * node]);
             gs.y = float(sizes[3 * node + 1]);
             gs.z = float(sizes[3 * node + 2]);
-            gs.w = 0.0f;
-            m    = fmaxf(fmaxf(fabsf(gc.x), fmaxf(fabsf(gc.y), fabsf(gc.z))), fmaxf(gs.x, fmaxf(gs.y, gs.z)));
+            float D = fmaxf(fmaxf(fmaxf(fabsf(gc.x), fabsf(gc.y)), fmaxf(fabsf(gc.z), DwT)),
+                            fmaxf(gs.x, fmaxf(gs.y, gs.z)));
+            gs.w          = D * D * 0x1p-27f;
             sh.geoC[lane] = gc;
             sh.geoS[lane] = gs;
         }
         __syncwarp();
-        const Band band = makeBand(r2f, fmaxf(warpMax(m), DwT), 0x1p-27f, mine);
         if (mine)
         {
 #pragma unroll
@@ -392,12 +384,33 @@ __global__ void __launch_bounds__(NB_THREADS) findNeighborsKernel(const T* __res
             {
                 const float4 gc = sh.geoC[c];
                 const float4 gs = sh.geoS[c];
-                float dx        = fmaxf(fabsf(gc.x - txf) - gs.x, 0.0f);
-                float dy        = fmaxf(fabsf(gc.y - tyf) - gs.y, 0.0f);
-                float dz        = fmaxf(fabsf(gc.z - tzf) - gs.z, 0.0f);
-                float s2        = fmaf(dx, dx, fmaf(dy, dy, dz * dz));
-                bool pass       = s2 < band.a;
-                if (!pass && !(s2 > band.b)) { pass = cellOverlap<false>(t, centers, sizes, child0 + c, box); }
+                bool pass;
+                if (Filt)
+                {
+                    float dx = fmaxf(fabsf(gc.x - txf) - gs.x, 0.0f);
+                    float dy = fmaxf(fabsf(gc.y - tyf) - gs.y, 0.0f);
+                    float dz = fmaxf(fabsf(gc.z - tzf) - gs.z, 0.0f);
+                    float s2 = fmaf(dx, dx, fmaf(dy, dy, dz * dz));
+                    pass     = s2 < fmaf(-gs.w, BAND_SA, r2a);
+                    if (!pass && !(s2 > fmaf(gs.w, BAND_SB, r2b)))
+                    {
+                        pass = cellOverlap<false>(t, centers, sizes, child0 + c, box);
+                    }
+                }
+                else
+                {
+                    // float searches: the staged values are the reference's operands, evaluate its expression
+                    T dx = rabs(T(gc.x) - t.x) - T(gs.x);
+                    T dy = rabs(T(gc.y) - t.y) - T(gs.y);
+                    T dz = rabs(T(gc.z) - t.z) - T(gs.z);
+                    dx += rabs(dx);
+                    dy += rabs(dy);
+                    dz += rabs(dz);
+                    dx *= T(0.5);
+                    dy *= T(0.5);
+                    dz *= T(0.5);
+                    pass = dx * dx + (dy * dy + dz * dz) < t.radiusSq;
+                }
                 bits |= uint32_t(pass) << c;
             }
         }
@@ -411,9 +424,9 @@ __global__ void __launch_bounds__(NB_THREADS) findNeighborsKernel(const T* __res
         if (rootChild == 0) { scanLeaf(0, rootMine); }
         else
         {
-            int depth           = 1;
-            int node            = rootChild;
-            sh.mask[1][lane]    = uint8_t(testChildren(rootChild, rootMine));
+            int depth        = 1;
+            int node         = rootChild;
+            sh.mask[1][lane] = uint8_t(testChildren(rootChild, rootMine));
             while (true)
             {
                 const bool mine = (sh.mask[depth][lane] >> ((node - 1) & 7)) & 1u;
