@@ -142,6 +142,18 @@ __device__ inline float keyFloat(int k) { return __int_as_float(k ^ ((k >> 31) &
 __device__ inline float warpMinF(float v) { return keyFloat(__reduce_min_sync(0xffffffffu, floatKey(v))); }
 __device__ inline float warpMaxF(float v) { return keyFloat(__reduce_max_sync(0xffffffffu, floatKey(v))); }
 
+//! the reference's acceptance test (findneighbors.hpp:33-60,134); out of line so that the rare call does not get
+//! if-converted into the hot loop
+template<class T>
+__device__ __noinline__ bool exactInside(const T* __restrict__ x, const T* __restrict__ y, const T* __restrict__ z,
+                                         uint32_t j, T tx, T ty, T tz, T radiusSq)
+{
+    T ex = x[j] - tx;
+    T ey = y[j] - ty;
+    T ez = z[j] - tz;
+    return ex * ex + ey * ey + ez * ez < radiusSq;
+}
+
 constexpr int NB_MAX_DEPTH = 23; // >= maxTreeLevel<uint64_t> + 2
 constexpr int NB_STAGE     = 64; // staged candidates per round (two half-rounds of 32 loads)
 
@@ -278,6 +290,7 @@ __global__ void __launch_bounds__(NB_THREADS) findNeighborsKernel(const T* __res
 #pragma unroll
             for (int half = 0; half < NB_STAGE / 32; ++half)
             {
+                if (base + half * 32 >= je) { break; }
                 const uint32_t j = base + half * 32 + lane;
                 bool keep        = false;
                 float4 c;
@@ -309,22 +322,18 @@ __global__ void __launch_bounds__(NB_THREADS) findNeighborsKernel(const T* __res
                     float dy       = c.y - tyf;
                     float dz       = c.z - tzf;
                     float s2       = fmaf(dx, dx, fmaf(dy, dy, dz * dz));
-                    if (!(s2 > bandB))
+                    const uint32_t j = __float_as_uint(c.w);
+                    bool in          = s2 < bandA;
+                    // inside the uncertainty band (rare, < 1 % of the neighbours): the reference's own expression
+                    // decides; the vote keeps the common path free of divergence bookkeeping
+                    if (__any_sync(0xffffffffu, !in && !(s2 > bandB)))
                     {
-                        const uint32_t j = __float_as_uint(c.w);
-                        if (s2 < bandA)
-                        {
-                            if (j != i) { append(j); }
-                        }
-                        else if (mine)
-                        {
-                            // inside the uncertainty band: the reference's own expression decides
-                            T ex = x[j] - t.x;
-                            T ey = y[j] - t.y;
-                            T ez = z[j] - t.z;
-                            if (ex * ex + ey * ey + ez * ez < t.radiusSq && j != i) { append(j); }
-                        }
+                        if (!in && !(s2 > bandB) && mine) { in = exactInside(x, y, z, j, t.x, t.y, t.z, t.radiusSq); }
                     }
+                    in = in && j != i;
+                    if (in && numFound < ngmax) { *out = j; }
+                    out += in;
+                    numFound += in;
                 }
             }
             else
@@ -359,6 +368,7 @@ __global__ void __launch_bounds__(NB_THREADS) findNeighborsKernel(const T* __res
             return bits;
         }
         __syncwarp();
+        bool reach = false;
         if (lane < 8)
         {
             int node = child0 + int(lane);
@@ -375,13 +385,20 @@ __global__ void __launch_bounds__(NB_THREADS) findNeighborsKernel(const T* __res
             gs.w          = D * D * 0x1p-27f;
             sh.geoC[lane] = gc;
             sh.geoS[lane] = gs;
+            // warp-level cull: a child whose box is certainly farther from the targets' bounding box than the
+            // largest radius fails the continuation test of every lane
+            float ex = fmaxf(fmaxf(lox - (gc.x + gs.x), (gc.x - gs.x) - hix), 0.0f);
+            float ey = fmaxf(fmaxf(loy - (gc.y + gs.y), (gc.y - gs.y) - hiy), 0.0f);
+            float ez = fmaxf(fmaxf(loz - (gc.z + gs.z), (gc.z - gs.z) - hiz), 0.0f);
+            reach    = !(fmaf(ex, ex, fmaf(ey, ey, ez * ez)) > fmaf(gs.w, BAND_SB, r2bMax));
         }
-        __syncwarp();
+        const unsigned reachable = __ballot_sync(0xffffffffu, reach);
         if (mine)
         {
 #pragma unroll
             for (int c = 0; c < 8; ++c)
             {
+                if (!((reachable >> c) & 1u)) { continue; }
                 const float4 gc = sh.geoC[c];
                 const float4 gs = sh.geoS[c];
                 bool pass;
@@ -424,32 +441,40 @@ __global__ void __launch_bounds__(NB_THREADS) findNeighborsKernel(const T* __res
         if (rootChild == 0) { scanLeaf(0, rootMine); }
         else
         {
+            // depth-first walk in SFC order over the children that at least one lane enters: `lm` holds this lane's
+            // decisions for the 8 siblings starting at `base` (kept per depth in shared memory for the way back up),
+            // `wm` the siblings still to visit for the warp
             int depth        = 1;
-            int node         = rootChild;
-            sh.mask[1][lane] = uint8_t(testChildren(rootChild, rootMine));
+            int base         = rootChild;
+            uint32_t lm      = testChildren(rootChild, rootMine);
+            sh.mask[1][lane] = uint8_t(lm);
+            uint32_t wm      = __reduce_or_sync(0xffffffffu, lm);
             while (true)
             {
-                const bool mine = (sh.mask[depth][lane] >> ((node - 1) & 7)) & 1u;
-                if (__any_sync(0xffffffffu, mine))
+                if (wm == 0)
                 {
-                    const int child = childOffsets[node];
-                    if (child == 0) { scanLeaf(node, mine); }
-                    else
-                    {
-                        ++depth;
-                        sh.mask[depth][lane] = uint8_t(testChildren(child, mine));
-                        node                 = child;
-                        continue;
-                    }
-                }
-                while (((node - 1) & 7) == 7)
-                {
-                    node = parents[(node - 1) >> 3];
+                    if (depth == 1) { break; }
+                    const int up = parents[(base - 1) >> 3];
                     --depth;
-                    if (node == 0) { break; }
+                    base = ((up - 1) & ~7) + 1;
+                    lm   = sh.mask[depth][lane];
+                    wm   = __reduce_or_sync(0xffffffffu, lm) & ~((2u << ((up - 1) & 7)) - 1u);
+                    continue;
                 }
-                if (node == 0) { break; }
-                ++node;
+                const int c = __ffs(int(wm)) - 1;
+                wm &= wm - 1;
+                const int node  = base + c;
+                const bool mine = (lm >> c) & 1u;
+                const int child = childOffsets[node];
+                if (child == 0) { scanLeaf(node, mine); }
+                else
+                {
+                    ++depth;
+                    lm                   = testChildren(child, mine);
+                    sh.mask[depth][lane] = uint8_t(lm);
+                    wm                   = __reduce_or_sync(0xffffffffu, lm);
+                    base                 = child;
+                }
             }
         }
     }
