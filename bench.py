@@ -193,8 +193,9 @@ def stage_rooflines(n, dev, x, y, z, h, reps=3):
     outs = [torch.empty_like(x) for _ in range(4)]
     src_a = (C.c_void_p * 4)(*[t.data_ptr() for t in (x, y, z, h)])
     dst_a = (C.c_void_p * 4)(*[t.data_ptr() for t in outs])
-    timeit("gather", lambda: capi._check(capi.lib().cs_gather4(capi._ptr(order), C.c_size_t(n), src_a, dst_a,
-                                                               C.c_int(8), capi._stream()), "gather4"))
+    timeit("gather", lambda: capi._check(capi.lib().cs_gather_arrays4(capi._ptr(order), C.c_size_t(n), C.c_size_t(n),
+                                                                      src_a, dst_a, C.c_int(8), capi._stream()),
+                                         "gather_arrays4"))
     leaves, counts = capi.compute_octree(keys, BUCKET)
     timeit("counts", lambda: capi.compute_node_counts(leaves, keys))
     res["num_leaves"] = leaves.numel() - 1

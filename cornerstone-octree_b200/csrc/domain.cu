@@ -287,7 +287,8 @@ public:
         {
             const void* src[4] = {x_.p, y_.p, z_.p, h_.p};
             void* dst[4]       = {sx_.p, sy_.p, sz_.p, sh_.p};
-            CSB_TRY(cs_gather4(ordering_.p + numSendDown, numAssigned, src, dst, int(sizeof(T)), s));
+            CSB_TRY(cs_gather_arrays4(ordering_.p + numSendDown, numAssigned, size_t(start_) + numPart, src, dst,
+                                      int(sizeof(T)), s));
         }
 
         /* ---- focus tree (domain.hpp:189-213) */

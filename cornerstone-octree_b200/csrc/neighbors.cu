@@ -324,11 +324,15 @@ __global__ void __launch_bounds__(NB_THREADS) findNeighborsKernel(const T* __res
                     float s2       = fmaf(dx, dx, fmaf(dy, dy, dz * dz));
                     const uint32_t j = __float_as_uint(c.w);
                     bool in          = s2 < bandA;
-                    // inside the uncertainty band (rare, < 1 % of the neighbours): the reference's own expression
-                    // decides; the vote keeps the common path free of divergence bookkeeping
-                    if (__any_sync(0xffffffffu, !in && !(s2 > bandB)))
+                    // inside the uncertainty band (rare, < 1 % of the neighbours; never for lanes that do not own
+                    // the leaf, their band is empty): the reference's own expression decides.  The branch is
+                    // warp-uniform and the callee is evaluated by all lanes, so the common path carries no
+                    // divergence bookkeeping.
+                    const bool amb = !in && !(s2 > bandB);
+                    if (__any_sync(0xffffffffu, amb))
                     {
-                        if (!in && !(s2 > bandB) && mine) { in = exactInside(x, y, z, j, t.x, t.y, t.z, t.radiusSq); }
+                        const bool e = exactInside(x, y, z, j, t.x, t.y, t.z, t.radiusSq);
+                        in           = amb ? e : in;
                     }
                     in = in && j != i;
                     if (in && numFound < ngmax) { *out = j; }

@@ -426,6 +426,64 @@ __global__ void gather4Kernel(const uint32_t* __restrict__ ord, size_t n, Ptr4<E
     }
 }
 
+/* Random gathers of 8-byte elements cost a 128-byte DRAM fetch each on B200 (measured: 520 B read per particle for four
+ * arrays, independent of cudaLimitMaxL2FetchGranularity).  gatherArrays therefore first interleaves the four source
+ * arrays into one array of 4-element records with fully coalesced traffic and then gathers whole records: one
+ * 16/32-byte sector-aligned random read per particle instead of four scattered ones. */
+template<class E>
+struct alignas(4 * sizeof(E)) Rec4
+{
+    E v[4];
+};
+
+template<class E>
+__global__ void packRec4Kernel(size_t n, const E* __restrict__ a, const E* __restrict__ b, const E* __restrict__ c,
+                               const E* __restrict__ d, Rec4<E>* __restrict__ rec)
+{
+    size_t i = size_t(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i < n)
+    {
+        Rec4<E> r;
+        r.v[0] = a[i];
+        r.v[1] = b[i];
+        r.v[2] = c[i];
+        r.v[3] = d[i];
+        rec[i] = r;
+    }
+}
+
+template<class E>
+__global__ void gatherRec4Kernel(const uint32_t* __restrict__ ord, size_t n, const Rec4<E>* __restrict__ rec, E* __restrict__ a,
+                                 E* __restrict__ b, E* __restrict__ c, E* __restrict__ d)
+{
+    size_t i = size_t(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i < n)
+    {
+        Rec4<E> r = rec[ord[i]];
+        a[i]      = r.v[0];
+        b[i]      = r.v[1];
+        c[i]      = r.v[2];
+        d[i]      = r.v[3];
+    }
+}
+
+template<class E>
+int gatherArrays4(const uint32_t* ordering, size_t n, size_t srcCount, const void* const* src4, void* const* dst4,
+                  cudaStream_t s)
+{
+    CSB_SCRATCH(rec, Rec4<E>*, s, SCRATCH_D, srcCount * sizeof(Rec4<E>));
+    packRec4Kernel<E><<<iceil(srcCount, 256), 256, 0, s>>>(srcCount, static_cast<const E*>(src4[0]),
+                                                           static_cast<const E*>(src4[1]),
+                                                           static_cast<const E*>(src4[2]),
+                                                           static_cast<const E*>(src4[3]), rec);
+    CSB_LAUNCH_CHECK();
+    gatherRec4Kernel<E><<<iceil(n, 256), 256, 0, s>>>(ordering, n, rec, static_cast<E*>(dst4[0]),
+                                                      static_cast<E*>(dst4[1]), static_cast<E*>(dst4[2]),
+                                                      static_cast<E*>(dst4[3]));
+    CSB_LAUNCH_CHECK();
+    return 0;
+}
+
 } // namespace
 
 int sortByKeyU64(uint64_t* keys, uint32_t* values, size_t n, uint64_t* keyBuf, uint32_t* valueBuf, void* tmp,
@@ -528,6 +586,17 @@ int cs_gather4(const uint32_t* ordering, size_t n, const void* const* src4, void
     }
     CSB_LAUNCH_CHECK();
     return 0;
+}
+
+int cs_gather_arrays4(const uint32_t* ordering, size_t n, size_t srcCount, const void* const* src4, void* const* dst4,
+                      int elemBytes, void* stream)
+{
+    CSB_REQUIRE(elemBytes == 4 || elemBytes == 8, "gather supports 4- and 8-byte elements");
+    if (n == 0) { return 0; }
+    // small inputs are launch-latency bound: one direct pass
+    if (srcCount < (size_t(1) << 16)) { return cs_gather4(ordering, n, src4, dst4, elemBytes, stream); }
+    if (elemBytes == 4) { return csb::gatherArrays4<uint32_t>(ordering, n, srcCount, src4, dst4, cudaStream_t(stream)); }
+    return csb::gatherArrays4<uint64_t>(ordering, n, srcCount, src4, dst4, cudaStream_t(stream));
 }
 
 } // extern "C"

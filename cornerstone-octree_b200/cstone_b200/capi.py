@@ -122,6 +122,17 @@ def gather4(ordering, srcs):
     return dsts
 
 
+def gather_arrays4(ordering, srcs):
+    """gatherArrays(x,y,z,h): record-packed gather of four equally long arrays (cs_gather_arrays4)"""
+    n = ordering.numel()
+    dsts = [torch.empty(n, dtype=s.dtype, device=s.device) for s in srcs]
+    src_a = (C.c_void_p * 4)(*[s.data_ptr() for s in srcs])
+    dst_a = (C.c_void_p * 4)(*[d.data_ptr() for d in dsts])
+    _check(lib().cs_gather_arrays4(_ptr(ordering), C.c_size_t(n), C.c_size_t(srcs[0].numel()), src_a, dst_a,
+                                   C.c_int(srcs[0].element_size()), _stream()), "cs_gather_arrays4")
+    return dsts
+
+
 def exclusive_scan(values):
     n = values.numel()
     out = torch.empty_like(values)

@@ -71,6 +71,12 @@ int cs_gather(const uint32_t* ordering, size_t n, const void* src, void* dst, in
 int cs_gather4(const uint32_t* ordering, size_t n, const void* const* src4, void* const* dst4, int elemBytes,
                void* stream);
 
+/* gatherArrays(gatherFunc, ordering, n, inOffset = 0, outOffset = 0, {x,y,z,h}, scratch) (domain/layout.hpp:230-261)
+ * for four arrays of srcCount elements each (every ordering[i] < srcCount): dst4[k][i] = src4[k][ordering[i]].  Uses
+ * library scratch (4 * elemBytes * srcCount) to turn four scattered reads per particle into one record read. */
+int cs_gather_arrays4(const uint32_t* ordering, size_t n, size_t srcCount, const void* const* src4, void* const* dst4,
+                      int elemBytes, void* stream);
+
 /* exclusiveScan(Gpu, in, in+n, out)  primitives_gpu.h:66-72 ; tmp >= cs_scan_temp_bytes(n) */
 size_t cs_scan_temp_bytes(size_t n);
 int cs_exclusive_scan_u32(const uint32_t* in, uint32_t* out, size_t n, void* tmp, void* stream);

@@ -145,6 +145,15 @@ def test_gather_and_scan(T):
     for g, a in zip(got, arrs):
         assert np.array_equal(host(g), a[order])
     assert np.array_equal(host(capi().gather(do, dev(arrs[0]))), arrs[0][order])
+    # record-packed gatherArrays: partial orderings (n < srcCount), both the direct (small) and the packed path
+    for sub in (order, order[: n // 3], order[:7]):
+        got = capi().gather_arrays4(dev(sub), [dev(a) for a in arrs])
+        for g, a in zip(got, arrs):
+            assert np.array_equal(host(g), a[sub])
+    small = [a[:1000] for a in arrs]
+    so = rng.permutation(1000).astype(np.uint32)
+    for g, a in zip(capi().gather_arrays4(dev(so), [dev(a) for a in small]), small):
+        assert np.array_equal(host(g), a[so])
     for m in (1, 2, 4095, 4096, 4097, 1 << 21):
         v = rng.integers(0, 5000, m).astype(np.uint32)
         want = np.zeros(m, dtype=np.uint32)
