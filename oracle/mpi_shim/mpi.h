@@ -12,6 +12,8 @@
 
 #include <condition_variable>
 #include <cstdint>
+#include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <deque>
 #include <mutex>
@@ -144,6 +146,22 @@ inline int& rankRef()
     return r;
 }
 
+inline bool trace()
+{
+    static bool t = getenv("CS_MPI_TRACE") != nullptr;
+    return t;
+}
+#define MPISHIM_TRACE(...)                                                                                             \
+    do                                                                                                                 \
+    {                                                                                                                  \
+        if (::mpishim::trace())                                                                                        \
+        {                                                                                                              \
+            fprintf(stderr, "[r%d] ", ::mpishim::rankRef());                                                           \
+            fprintf(stderr, __VA_ARGS__);                                                                              \
+            fputc('\n', stderr);                                                                                       \
+        }                                                                                                              \
+    } while (0)
+
 inline void barrier()
 {
     World& w = world();
@@ -240,6 +258,7 @@ inline int MPI_Comm_size(MPI_Comm, int* s)
 }
 inline int MPI_Barrier(MPI_Comm)
 {
+    MPISHIM_TRACE("Barrier");
     mpishim::barrier();
     return 0;
 }
@@ -255,6 +274,7 @@ inline int MPI_Op_free(MPI_Op*) { return 0; }
 inline int
 MPI_Allreduce(const void* sendbuf, void* recvbuf, int count, MPI_Datatype t, const MPI_Op& op, MPI_Comm)
 {
+    MPISHIM_TRACE("Allreduce count=%d", count);
     using namespace mpishim;
     World& w     = world();
     int me       = rankRef();
@@ -274,6 +294,7 @@ MPI_Allreduce(const void* sendbuf, void* recvbuf, int count, MPI_Datatype t, con
 
 inline int MPI_Alltoall(const void* sendbuf, int sendcount, MPI_Datatype st, void* recvbuf, int, MPI_Datatype, MPI_Comm)
 {
+    MPISHIM_TRACE("Alltoall");
     using namespace mpishim;
     World& w     = world();
     int me       = rankRef();
@@ -297,6 +318,7 @@ inline int MPI_Allgatherv(const void* sendbuf,
                           MPI_Datatype rt,
                           MPI_Comm)
 {
+    MPISHIM_TRACE("Allgatherv");
     using namespace mpishim;
     World& w  = world();
     int me    = rankRef();
@@ -317,6 +339,7 @@ inline int MPI_Allgatherv(const void* sendbuf,
 
 inline int MPI_Isend(const void* buf, int count, MPI_Datatype t, int dest, int tag, MPI_Comm, MPI_Request* req)
 {
+    MPISHIM_TRACE("Isend dest=%d tag=%d count=%d", dest, tag, count);
     using namespace mpishim;
     World& w = world();
     Message m;
@@ -334,22 +357,41 @@ inline int MPI_Isend(const void* buf, int count, MPI_Datatype t, int dest, int t
 
 inline int MPI_Irecv(void* buf, int count, MPI_Datatype t, int src, int tag, MPI_Comm, MPI_Request* req)
 {
+    MPISHIM_TRACE("Irecv src=%d tag=%d count=%d", src, tag, count);
+    // a message that is already here is matched right away (required by the Probe -> Irecv idiom of
+    // focus/exchange_focus.hpp: a second Probe must not see the same message again); otherwise the receive stays
+    // pending and is matched in Waitall
+    using namespace mpishim;
+    World& w = world();
+    int me   = rankRef();
     req->kind_  = 1;
     req->buf_   = buf;
-    req->bytes_ = (long long)count * mpishim::typeSize(t);
+    req->bytes_ = (long long)count * typeSize(t);
     req->src_   = src;
     req->tag_   = tag;
+    std::unique_lock<std::mutex> lk(w.mtx);
+    int idx = findMatch(w.mailbox[me], src, tag);
+    if (idx >= 0)
+    {
+        Message& m = w.mailbox[me][idx];
+        if ((long long)m.data.size() > req->bytes_) throw std::runtime_error("mpishim: message truncated");
+        std::memcpy(buf, m.data.data(), m.data.size());
+        w.mailbox[me].erase(w.mailbox[me].begin() + idx);
+        req->kind_ = 0;
+    }
     return 0;
 }
 
 inline int MPI_Recv(void* buf, int count, MPI_Datatype t, int src, int tag, MPI_Comm, MPI_Status* status)
 {
+    MPISHIM_TRACE("Recv src=%d tag=%d count=%d", src, tag, count);
     mpishim::blockingRecv(buf, (long long)count * mpishim::typeSize(t), src, tag, status);
     return 0;
 }
 
 inline int MPI_Probe(int src, int tag, MPI_Comm, MPI_Status* status)
 {
+    MPISHIM_TRACE("Probe src=%d tag=%d", src, tag);
     using namespace mpishim;
     World& w = world();
     int me   = rankRef();
@@ -373,6 +415,7 @@ inline int MPI_Get_count(const MPI_Status* status, MPI_Datatype t, int* count)
 
 inline int MPI_Waitall(int n, MPI_Request* reqs, MPI_Status*)
 {
+    MPISHIM_TRACE("Waitall n=%d", n);
     for (int i = 0; i < n; ++i)
     {
         if (reqs[i].kind_ == 1)
