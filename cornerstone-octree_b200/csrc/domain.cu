@@ -20,6 +20,8 @@
 #include <limits>
 #include <vector>
 
+#include "assignment.cuh"
+#include "comm.cuh"
 #include "common.cuh"
 #include "cstone_b200.h"
 #include "focus.cuh"
@@ -151,6 +153,7 @@ struct DomainBase
     virtual int neighbors(uint32_t ngmax, uint32_t* nb, uint32_t* nc, cudaStream_t s)              = 0;
     virtual int download(void* x, void* y, void* z, void* h, void* keys, cudaStream_t s)           = 0;
     virtual int reset(cudaStream_t s)                                                              = 0;
+    virtual int attachComm(Comm* c)                                                                = 0;
     int keyBytes{0}, realBytes{0};
 };
 
@@ -184,15 +187,19 @@ public:
 
     int init(cudaStream_t s)
     {
-        // GlobalAssignment ctor (assignment.hpp:53-74) for one rank: the spanning tree of {0, 2^(3L)} is the root
-        // node; its count starts at bucketSize - 1
-        K root[2]   = {0, nodeRange<K>(0)};
-        uint32_t c0 = bucket_ - 1;
-        CSB_TRY(gLeaves_.resize(2, s));
-        CSB_TRY(gCounts_.resize(1, s));
-        CSB_CHECK(cudaMemcpyAsync(gLeaves_.p, root, sizeof(root), cudaMemcpyHostToDevice, s));
-        CSB_CHECK(cudaMemcpyAsync(gCounts_.p, &c0, sizeof(c0), cudaMemcpyHostToDevice, s));
-        numGlobalLeaves_ = 1;
+        // GlobalAssignment ctor (assignment.hpp:53-74): spanning tree of the initial rank splits, counts start at
+        // bucketSize - 1 (for one rank this is the root node)
+        K root[2] = {0, nodeRange<K>(0)};
+        {
+            std::vector<K> initial = initialGlobalTree<K>(numRanks_);
+            numGlobalLeaves_       = int(initial.size()) - 1;
+            std::vector<uint32_t> c0(numGlobalLeaves_, bucket_ - 1);
+            CSB_TRY(gLeaves_.resize(initial.size(), s));
+            CSB_TRY(gCounts_.resize(numGlobalLeaves_, s));
+            CSB_CHECK(cudaMemcpyAsync(gLeaves_.p, initial.data(), initial.size() * sizeof(K), cudaMemcpyHostToDevice, s));
+            CSB_CHECK(cudaMemcpyAsync(gCounts_.p, c0.data(), c0.size() * sizeof(uint32_t), cudaMemcpyHostToDevice, s));
+            CSB_CHECK(cudaStreamSynchronize(s));
+        }
 
         // FocusedOctree ctor (octree_focus_mpi.hpp:56-83): root leaf with count bucketSizeFocus + 1
         uint32_t c1 = bucketFocus_ + 1;
@@ -206,7 +213,7 @@ public:
         CSB_TRY(scalars_.resize(64, s, false, true));
         CSB_CHECK(cudaStreamSynchronize(s));
         CSB_TRY(linkTree(fLeaves_, 1, fTree_, s));
-        CSB_TRY(linkTree(gLeaves_, 1, gTree_, s));
+        CSB_TRY(linkTree(gLeaves_, numGlobalLeaves_, gTree_, s));
         return 0;
     }
 
@@ -242,15 +249,20 @@ public:
         }
         else { CSB_REQUIRE(!firstCall_, "the first sync needs input arrays"); }
         CSB_REQUIRE(size_t(bufSize_) < (size_t(1) << 30), "at most 2^30 - 1 particles per rank");
+        CSB_REQUIRE(comm_->size() == numRanks_, "multi-rank domains need cs_domain_attach_comm before the first sync");
 
         const size_t numPart = end_ - start_;
+        Comm& comm           = *comm_;
+        const int P          = comm.size();
+        const int me         = comm.rank();
 
         /* ---- GlobalAssignment::assign (assignment.hpp:92-144) */
         CSB_TRY(updateBox(numPart, s));
         CSB_TRY(keysDispatch(0, x_.p + start_, y_.p + start_, z_.p + start_, keys_.p + start_, numPart, lim_, bnd_, s));
-        CSB_TRY(ordering_.resize(numPart, s));
-        CSB_TRY(cs_sequence_u32(start_, numPart, ordering_.p, s));
-        CSB_TRY(sortPairs(keys_.p + start_, ordering_.p, numPart, s));
+        // the ordering is indexed by buffer position (primitives_acc.hpp:97-103): ordering[start + i] = start + i
+        CSB_TRY(ordering_.resize(std::max<size_t>(bufSize_, 1), s));
+        CSB_TRY(cs_sequence_u32(start_, numPart, ordering_.p + start_, s));
+        CSB_TRY(sortPairs(keys_.p + start_, ordering_.p + start_, numPart, s));
 
         unsigned maxCount = 0;
         CSB_TRY(updateGlobalTree(keys_.p + start_, numPart, &maxCount, s));
@@ -263,21 +275,71 @@ public:
         }
         CSB_TRY(linkTree(gLeaves_, numGlobalLeaves_, gTree_, s));
 
-        // one rank: assignment = whole curve; particles with key >= 2^(3L) (removeKey) fall outside of it
-        K boundaries[2] = {0, nodeRange<K>(0)};
-        CSB_TRY(boundaryKeys_.resize(2, s));
-        CSB_CHECK(cudaMemcpyAsync(boundaryKeys_.p, boundaries, sizeof(boundaries), cudaMemcpyHostToDevice, s));
-        uint32_t* sendIdxDev = scalars_.p + 8;
-        CSB_TRY(lowerBounds<K>(keys_.p + start_, numPart, boundaryKeys_.p, 2, sendIdxDev, s));
-        uint32_t sendIdx[2];
-        CSB_CHECK(cudaMemcpyAsync(sendIdx, sendIdxDev, sizeof(sendIdx), cudaMemcpyDeviceToHost, s));
-        CSB_CHECK(cudaStreamSynchronize(s));
-        const LocalIndex numSendDown = sendIdx[0];
-        const LocalIndex numAssigned = sendIdx[1] - sendIdx[0];
+        // makeSfcAssignment on the host from the replicated leaves and counts (assignment.hpp:125-134)
+        if (P == 1)
+        {
+            // one rank: the assignment is the whole curve whatever the counts are; skip the downloads
+            assignment_.boundaries  = {K(0), nodeRange<K>(0)};
+            assignment_.treeOffsets = {0, numGlobalLeaves_};
+            assignment_.counts      = {0};
+        }
+        else
+        {
+            gLeavesHost_.resize(size_t(numGlobalLeaves_) + 1);
+            gCountsHost_.resize(numGlobalLeaves_);
+            CSB_CHECK(cudaMemcpyAsync(gLeavesHost_.data(), gLeaves_.p, gLeavesHost_.size() * sizeof(K),
+                                      cudaMemcpyDeviceToHost, s));
+            CSB_CHECK(cudaMemcpyAsync(gCountsHost_.data(), gCounts_.p, gCountsHost_.size() * sizeof(uint32_t),
+                                      cudaMemcpyDeviceToHost, s));
+            CSB_CHECK(cudaStreamSynchronize(s));
+            assignment_ = makeSfcAssignment<K>(P, gCountsHost_, gLeavesHost_.data());
+        }
 
-        /* ---- GlobalAssignment::distribute (assignment.hpp:167-203): nothing to exchange on one rank; the envelope
-         *      is already sorted, so the second sort of the reference is the identity and is skipped */
-        const K* keyView = keys_.p + start_ + numSendDown;
+        // createSendRangesGpu (domaindecomp.hpp:178-191): particles with key >= 2^(3L) (removeKey) fall outside
+        CSB_TRY(boundaryKeys_.resize(size_t(P) + 1, s));
+        CSB_CHECK(cudaMemcpyAsync(boundaryKeys_.p, assignment_.boundaries.data(), (size_t(P) + 1) * sizeof(K),
+                                  cudaMemcpyHostToDevice, s));
+        CSB_TRY(scalars_.resize(std::max<size_t>(64, 32 + size_t(P) + 1), s, true, true));
+        uint32_t* sendIdxDev = scalars_.p + 32;
+        CSB_TRY(lowerBounds<K>(keys_.p + start_, numPart, boundaryKeys_.p, P + 1, sendIdxDev, s));
+        std::vector<uint32_t> sendIdx(size_t(P) + 1);
+        CSB_CHECK(cudaMemcpyAsync(sendIdx.data(), sendIdxDev, sendIdx.size() * sizeof(uint32_t), cudaMemcpyDeviceToHost,
+                                  s));
+        CSB_CHECK(cudaStreamSynchronize(s));
+        const LocalIndex numSendDown = sendIdx[me];
+        const LocalIndex numPresent  = sendIdx[me + 1] - sendIdx[me];
+        const LocalIndex numAssigned = P == 1 ? numPresent : assignment_.counts[me];
+
+        /* ---- GlobalAssignment::distribute (assignment.hpp:167-203) */
+        LocalIndex envStart = start_, envEnd = end_;
+        if (P > 1)
+        {
+            CSB_REQUIRE(numAssigned >= numPresent, "global node counts are inconsistent with the local particles");
+            const LocalIndex numRecv = numAssigned - numPresent;
+            BufferDescription o1{start_, end_, bufSize_};
+            const LocalIndex exchangeSize = exchangeBufferSize(o1, numPresent, numAssigned);
+            // lowMemReallocate + zero fill of the new key range (domain.hpp:465-468)
+            CSB_TRY(x_.resize(exchangeSize, s, true));
+            CSB_TRY(y_.resize(exchangeSize, s, true));
+            CSB_TRY(z_.resize(exchangeSize, s, true));
+            CSB_TRY(h_.resize(exchangeSize, s, true));
+            CSB_TRY(keys_.resize(exchangeSize, s, true, true));
+            CSB_TRY(ordering_.resize(exchangeSize, s, true));
+            BufferDescription o1e{start_, end_, exchangeSize};
+            const LocalIndex recvStart = receiveStart(o1e, numRecv);
+            CSB_TRY(exchangeParticles(sendIdx, recvStart, numRecv, s));
+            assignedEnvelope(o1e, numRecv, &envStart, &envEnd);
+            bufSize_ = exchangeSize;
+            if (numRecv)
+            {
+                CSB_TRY(keysDispatch(0, x_.p + recvStart, y_.p + recvStart, z_.p + recvStart, keys_.p + recvStart,
+                                     numRecv, lim_, bnd_, s));
+                CSB_TRY(cs_sequence_u32(recvStart, numRecv, ordering_.p + recvStart, s));
+                CSB_TRY(sortPairs(keys_.p + envStart, ordering_.p + envStart, envEnd - envStart, s));
+            }
+        }
+        // one rank / nothing received: the envelope is already sorted, the reference's second sort is the identity
+        const K* keyView = keys_.p + envStart + numSendDown;
 
         /* ---- gatherArrays(x,y,z,h) to offset 0 (domain.hpp:187) */
         CSB_TRY(sx_.resize(std::max<size_t>(numAssigned, 1), s));
@@ -287,7 +349,7 @@ public:
         {
             const void* src[4] = {x_.p, y_.p, z_.p, h_.p};
             void* dst[4]       = {sx_.p, sy_.p, sz_.p, sh_.p};
-            CSB_TRY(cs_gather_arrays4(ordering_.p + numSendDown, numAssigned, size_t(start_) + numPart, src, dst,
+            CSB_TRY(cs_gather_arrays4(ordering_.p + envStart + numSendDown, numAssigned, bufSize_, src, dst,
                                       int(sizeof(T)), s));
         }
 
@@ -330,6 +392,15 @@ public:
         end_       = numAssigned;
         bufSize_   = numAssigned;
         firstCall_ = false;
+        return 0;
+    }
+
+    int attachComm(Comm* c) override
+    {
+        CSB_REQUIRE(c != nullptr, "null communicator");
+        CSB_REQUIRE(firstCall_, "the communicator must be attached before the first sync");
+        CSB_REQUIRE(c->size() == numRanks_ && c->rank() == rank_, "communicator rank/size differ from the domain's");
+        comm_ = c;
         return 0;
     }
 
@@ -438,6 +509,19 @@ private:
                 ext[2 * d + 1] = mx;
             }
         }
+        if (comm_->size() > 1 && anyOpen)
+        {
+            // MPI_Allreduce(MIN) over {min, -max} of sfc/box_mpi.hpp:78-86; ranks without particles contribute the
+            // previous limits, as in the reference
+            std::vector<T> all(size_t(6) * comm_->size());
+            CSB_TRY(comm_->allgatherHost(ext, sizeof(ext), all.data(), s));
+            for (int r = 0; r < comm_->size(); ++r)
+                for (int d = 0; d < 3; ++d)
+                {
+                    ext[2 * d]     = std::min(ext[2 * d], all[6 * r + 2 * d]);
+                    ext[2 * d + 1] = std::max(ext[2 * d + 1], all[6 * r + 2 * d + 1]);
+                }
+        }
         const T maxSide = std::max({ext[1] - ext[0], ext[3] - ext[2], ext[5] - ext[4]});
         for (int d = 0; d < 3; ++d)
             if (bnd_[d] == 3) { ext[2 * d + 1] = std::max(ext[2 * d + 1], ext[2 * d] + maxSide); }
@@ -454,6 +538,59 @@ private:
         }
         for (int i = 0; i < 6; ++i)
             lim_[i] = double(ext[i]);
+        return 0;
+    }
+
+    /* ------------------------------------------------------------ exchangeParticlesGpu
+     *  (domain/domaindecomp_mpi_gpu.cuh:70-166).  Outgoing ranges are gathered through the ordering into one packed
+     *  buffer per destination ([x | y | z | h], each block 16-byte aligned); incoming blocks land directly in the
+     *  particle arrays at [recvStart, recvStart + numRecv), sources in ascending rank order (the reference takes
+     *  them in arrival order, domaindecomp_mpi.hpp:116-140; the stable key sort that follows makes the final order
+     *  independent of it for distinct keys).  Keys are not sent, the receiver recomputes them (assignment.hpp:197). */
+    int exchangeParticles(const std::vector<uint32_t>& sendIdx, LocalIndex recvStart, LocalIndex numRecv, cudaStream_t s)
+    {
+        Comm& comm   = *comm_;
+        const int P  = comm.size();
+        const int me = comm.rank();
+
+        std::vector<uint32_t> sendCounts(P, 0), allCounts(size_t(P) * P);
+        for (int r = 0; r < P; ++r)
+            sendCounts[r] = r == me ? 0 : sendIdx[r + 1] - sendIdx[r];
+        CSB_TRY(comm.allgatherHost(sendCounts.data(), P * sizeof(uint32_t), allCounts.data(), s));
+
+        auto blockElems = [](size_t c) { return (c + 3) & ~size_t(3); }; // 16-byte multiples for 4- and 8-byte reals
+        size_t totalSend = 0;
+        for (int r = 0; r < P; ++r)
+            totalSend += 4 * blockElems(sendCounts[r]);
+        CSB_TRY(sendBuf_.resize(std::max<size_t>(totalSend, 1), s));
+
+        std::vector<CommMessage> sends, recvs;
+        size_t off = 0;
+        for (int r = 0; r < P; ++r)
+        {
+            size_t c = sendCounts[r];
+            if (c == 0) { continue; }
+            size_t be          = blockElems(c);
+            const void* src[4] = {x_.p, y_.p, z_.p, h_.p};
+            void* dst[4]       = {sendBuf_.p + off, sendBuf_.p + off + be, sendBuf_.p + off + 2 * be,
+                                  sendBuf_.p + off + 3 * be};
+            CSB_TRY(cs_gather4(ordering_.p + start_ + sendIdx[r], c, src, dst, int(sizeof(T)), s));
+            for (int k = 0; k < 4; ++k)
+                sends.push_back({r, dst[k], c * sizeof(T)});
+            off += 4 * be;
+        }
+        size_t received = 0;
+        T* arrays[4]    = {x_.p, y_.p, z_.p, h_.p};
+        for (int r = 0; r < P; ++r)
+        {
+            size_t c = allCounts[size_t(r) * P + me];
+            if (c == 0 || r == me) { continue; }
+            for (int k = 0; k < 4; ++k)
+                recvs.push_back({r, arrays[k] + recvStart + received, c * sizeof(T)});
+            received += c;
+        }
+        CSB_REQUIRE(received == numRecv, "exchangeParticles: incoming particle count does not match the assignment");
+        CSB_TRY(comm.exchange(sends, recvs, s));
         return 0;
     }
 
@@ -494,7 +631,15 @@ private:
         CSB_TRY(gCounts_.resize(newNumLeaves, s));
         CSB_TRY(computeNodeCounts<K>(gLeaves_.p, gCounts_.p, newNumLeaves, keys, n,
                                      std::numeric_limits<unsigned>::max(), s));
-        // (multi-rank: ncclAllReduce(sum) of the counts followed by max(local, reduced) goes here)
+        if (comm_->size() > 1)
+        {
+            // update_mpi.hpp:86-97: counts = max(local, sum over ranks); the sum saturates nowhere below 2^32
+            CSB_TRY(gCountsLocal_.resize(newNumLeaves, s));
+            CSB_CHECK(cudaMemcpyAsync(gCountsLocal_.p, gCounts_.p, size_t(newNumLeaves) * sizeof(uint32_t),
+                                      cudaMemcpyDeviceToDevice, s));
+            CSB_TRY(comm_->allreduceSumU32(gCounts_.p, newNumLeaves, s));
+            CSB_TRY(maxInto(gCounts_.p, gCountsLocal_.p, newNumLeaves, s));
+        }
         if (converged)
         {
             *maxCountOut = 0;
@@ -512,7 +657,8 @@ private:
     {
         const int numNodes  = fTree_.numNodes;
         const int numLeaves = fTree_.numLeaves;
-        const K focusStart = 0, focusEnd = nodeRange<K>(0);
+        const int me       = comm_->rank();
+        const K focusStart = assignment_.boundaries[me], focusEnd = assignment_.boundaries[me + 1];
 
         CSB_TRY(macs_.resize(numNodes, s));
         CSB_CHECK(cudaMemsetAsync(macs_.p, 0, size_t(numNodes), s)); // irrelevant when every node is in focus
@@ -524,8 +670,10 @@ private:
 
         CSB_TRY(essentialOps<K>(fTree_.prefixes.p, fTree_.childOffsets.p, fTree_.parents.p, fCounts_.p, macs_.p,
                                 focusStart, focusEnd, bucketFocus_, nodeOpsAll_.p, numNodes, s));
-        // mandatory keys: focus boundaries (trivial here) + the global leaves of the own assignment
-        CSB_TRY(enforceKeys<K>(gLeaves_.p, numGlobalLeaves_ + 1, fTree_.prefixes.p, fTree_.childOffsets.p,
+        // mandatory keys: the global leaves of the own assignment, boundaries included (octree_focus_mpi.hpp:121-122)
+        const int enforceFirst = assignment_.treeOffsets[me];
+        const int enforceCount = assignment_.treeOffsets[me + 1] - enforceFirst + 1;
+        CSB_TRY(enforceKeys<K>(gLeaves_.p + enforceFirst, enforceCount, fTree_.prefixes.p, fTree_.childOffsets.p,
                                fTree_.parents.p, nodeOpsAll_.p, statusDev, s));
         CSB_TRY(protectAncestors<K>(fTree_.prefixes.p, fTree_.parents.p, nodeOpsAll_.p, numNodes, changesDev, s));
 
@@ -553,7 +701,7 @@ private:
         if (status == ENFORCE_FAILED)
         {
             converged = false;
-            CSB_TRY(injectKeys(gLeaves_.p, numGlobalLeaves_ + 1, &numFocusLeaves, s));
+            CSB_TRY(injectKeys(gLeaves_.p + enforceFirst, enforceCount, &numFocusLeaves, s));
         }
 
         CSB_TRY(linkTree(fLeaves_, numFocusLeaves, fTree_, s));
@@ -607,6 +755,11 @@ private:
     }
 
     int rank_, numRanks_;
+    SelfComm selfComm_;
+    Comm* comm_{&selfComm_};
+    SfcAssignment<K> assignment_;
+    std::vector<K> gLeavesHost_;
+    std::vector<uint32_t> gCountsHost_;
     unsigned bucket_, bucketFocus_;
     float theta_;
     double lim_[6];
@@ -615,7 +768,7 @@ private:
     bool firstCall_{true};
     LocalIndex start_{0}, end_{0}, bufSize_{0};
 
-    DevBuf<T> x_, y_, z_, h_, sx_, sy_, sz_, sh_, partials_, geoCenters_, geoSizes_;
+    DevBuf<T> x_, y_, z_, h_, sx_, sy_, sz_, sh_, partials_, geoCenters_, geoSizes_, sendBuf_;
     DevBuf<K> keys_, keyBuf_, boundaryKeys_;
     DevBuf<uint32_t> ordering_, valueBuf_, scalars_, gapCounts_, layout_;
     DevBuf<unsigned char> sortTmp_, linkTmp_, opsTmp_, scanTmp_;
@@ -623,7 +776,7 @@ private:
 
     // global tree
     DevBuf<K> gLeaves_, gLeavesAlt_;
-    DevBuf<uint32_t> gCounts_;
+    DevBuf<uint32_t> gCounts_, gCountsLocal_;
     OctreeBufs<K> gTree_;
     int numGlobalLeaves_{0};
 
@@ -638,9 +791,9 @@ template<class K, class T>
 cs_domain_t* createDomain(int rank, int numRanks, unsigned bucket, unsigned bucketFocus, float theta,
                           const double* lim, const int* bnd)
 {
-    if (numRanks != 1 || rank != 0)
+    if (numRanks < 1 || rank < 0 || rank >= numRanks)
     {
-        setLastError("cs_domain_create: round 1 supports numRanks == 1 only (multi-rank sync is not implemented yet)");
+        setLastError("cs_domain_create: invalid rank / numRanks");
         return nullptr;
     }
     if (bucket < bucketFocus)
@@ -705,6 +858,12 @@ int cs_domain_find_neighbors(cs_domain_t* d, uint32_t ngmax, uint32_t* neighbors
 {
     CSB_REQUIRE(d != nullptr, "null domain");
     return csb::impl(d)->neighbors(ngmax, neighbors, neighborsCount, cudaStream_t(stream));
+}
+
+int cs_domain_attach_comm(cs_domain_t* d, cs_comm_t* comm)
+{
+    CSB_REQUIRE(d != nullptr, "null domain");
+    return csb::impl(d)->attachComm(reinterpret_cast<csb::Comm*>(comm));
 }
 
 int cs_domain_reset(cs_domain_t* d, void* stream)

@@ -343,6 +343,12 @@ __global__ void maxU32Kernel(const uint32_t* __restrict__ a, size_t n, uint32_t*
     if ((threadIdx.x & 31) == 0 && m) { atomicMax(result, m); }
 }
 
+__global__ void maxIntoKernel(uint32_t* __restrict__ a, const uint32_t* __restrict__ b, size_t n)
+{
+    size_t i = size_t(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i < n) { a[i] = max(a[i], b[i]); }
+}
+
 template<class K>
 __global__ void lowerBoundsKernel(const K* __restrict__ keys, size_t n, const K* __restrict__ targets, int numTargets,
                                   uint32_t* __restrict__ out)
@@ -448,6 +454,14 @@ int maxU32(const uint32_t* a, size_t n, uint32_t* resultDev, cudaStream_t s)
     if (n == 0) { return 0; }
     unsigned grid = unsigned(std::min<size_t>(592, (n + 255) / 256));
     maxU32Kernel<<<grid, 256, 0, s>>>(a, n, resultDev);
+    CSB_LAUNCH_CHECK();
+    return 0;
+}
+
+int maxInto(uint32_t* a, const uint32_t* b, size_t n, cudaStream_t s)
+{
+    if (n == 0) { return 0; }
+    maxIntoKernel<<<iceil(n, 256), 256, 0, s>>>(a, b, n);
     CSB_LAUNCH_CHECK();
     return 0;
 }

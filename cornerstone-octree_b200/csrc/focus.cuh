@@ -40,6 +40,8 @@ int layoutCounts(const uint32_t* leafCounts, const uint8_t* flags, const int* le
 template<class T>
 int minMaxPartials(const T* a, size_t n, T* partial, int numBlocks, cudaStream_t s);
 int maxU32(const uint32_t* a, size_t n, uint32_t* resultDev, cudaStream_t s);
+//! a[i] = max(a[i], b[i])
+int maxInto(uint32_t* a, const uint32_t* b, size_t n, cudaStream_t s);
 template<class K>
 int lowerBounds(const K* keys, size_t n, const K* targets, int numTargets, uint32_t* out, cudaStream_t s);
 template<class K>

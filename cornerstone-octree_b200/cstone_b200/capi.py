@@ -304,12 +304,72 @@ class _View:
         return {"shape": self.shape, "typestr": typestr, "data": (self.ptr, False), "version": 2}
 
 
+class LocalWorld:
+    """ranks as threads of this process (cs_local_world_*): lets multi-rank domains run on one GPU"""
+
+    def __init__(self, size):
+        lib().cs_local_world_create.restype = C.c_void_p
+        self.size = size
+        self.handle = lib().cs_local_world_create(C.c_int(size))
+        if not self.handle:
+            raise CstoneError(lib().cs_last_error().decode())
+
+    def comm(self, rank):
+        lib().cs_comm_create_local.restype = C.c_void_p
+        h = lib().cs_comm_create_local(C.c_void_p(self.handle), C.c_int(rank))
+        if not h:
+            raise CstoneError(lib().cs_last_error().decode())
+        return Comm(h, rank, self.size, keepalive=self)
+
+    def __del__(self):
+        try:
+            if getattr(self, "handle", None):
+                lib().cs_local_world_destroy(C.c_void_p(self.handle))
+                self.handle = None
+        except Exception:
+            pass
+
+
+class Comm:
+    """what MPI_Comm is to the reference's Domain: cs_comm_t (local threads or NCCL)"""
+
+    def __init__(self, handle, rank, size, keepalive=None):
+        self.handle, self.rank, self.size, self._keepalive = handle, rank, size, keepalive
+
+    @staticmethod
+    def nccl_unique_id():
+        buf = (C.c_ubyte * 128)()
+        _check(lib().cs_nccl_unique_id(buf), "cs_nccl_unique_id")
+        return bytes(buf)
+
+    @staticmethod
+    def nccl(rank, size, unique_id):
+        """collective over all ranks: one process per GPU, the current CUDA device is the rank's GPU"""
+        lib().cs_comm_create_nccl.restype = C.c_void_p
+        buf = (C.c_ubyte * 128).from_buffer_copy(unique_id)
+        h = lib().cs_comm_create_nccl(C.c_int(rank), C.c_int(size), buf)
+        if not h:
+            raise CstoneError(lib().cs_last_error().decode())
+        return Comm(h, rank, size)
+
+    @property
+    def bytes_sent(self):
+        lib().cs_comm_bytes_sent.restype = C.c_uint64
+        return int(lib().cs_comm_bytes_sent(C.c_void_p(self.handle)))
+
+    def close(self):
+        if getattr(self, "handle", None):
+            lib().cs_comm_destroy(C.c_void_p(self.handle))
+            self.handle = None
+
+
 class Domain:
     """host-side mirror of cstone::Domain<KeyType, T, Gpu> (domain/domain.hpp:38-664) over the cs_domain_* C ABI"""
 
     def __init__(self, rank, num_ranks, bucket_size, bucket_size_focus, theta, lim, bnd, key="u64", real="d",
-                 device="cuda:0"):
+                 device="cuda:0", comm=None):
         self.combo = key + real
+        self.comm = comm
         self.kt, self.real = key, real
         self.device = torch.device(device)
         lim_a, bnd_a = _box(lim, bnd)
@@ -322,6 +382,9 @@ class Domain:
             # the reference throws std::runtime_error from the constructor (domain.hpp:81-85)
             raise CstoneError(lib().cs_last_error().decode())
         lib().cs_domain_ptr.restype = C.c_void_p
+        if comm is not None:
+            _check(lib().cs_domain_attach_comm(C.c_void_p(self.handle), C.c_void_p(comm.handle)),
+                   "cs_domain_attach_comm")
 
     def close(self):
         if getattr(self, "handle", None):

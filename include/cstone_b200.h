@@ -173,6 +173,34 @@ int cs_find_neighbors_d(const double* x, const double* y, const double* z, const
                         const double* sizes, uint32_t ngmax, uint32_t* neighbors, uint32_t* neighborsCount,
                         void* stream);
 
+/* ---- host-side SFC domain decomposition (no device work; identical on every rank) ----
+ * uniformBins (domain/domaindecomp.hpp:33-55): bins[numBins+1] leaf indices with ~equal particle sums, binCounts[numBins] */
+int cs_uniform_bins(const uint32_t* counts, size_t numCounts, int numBins, int* bins, uint32_t* binCounts);
+/* the global tree every rank starts from: computeSpanningTree(initialDomainSplits(numRanks, log8ceil(100 numRanks)))
+ * (domain/assignment.hpp:62-65); returns the number of keys, writes them if capacity suffices */
+long cs_initial_global_tree_u32(int numRanks, uint32_t* leaves, long capacity);
+long cs_initial_global_tree_u64(int numRanks, uint64_t* leaves, long capacity);
+/* computeSpanningTree (tree/csarray.hpp:483-510) */
+long cs_spanning_tree_u64(const uint64_t* keys, long numKeys, uint64_t* leaves, long capacity);
+/* domain_exchange::{exchangeBufferSize, receiveStart, assignedEnvelope} (domain/buffer_description.hpp:98-125):
+ * out4 = {exchangeSize, receiveStart, envelopeStart, envelopeEnd} */
+int cs_exchange_buffer_layout(uint32_t start, uint32_t end, uint32_t size, uint32_t numPresent, uint32_t numAssigned,
+                              uint32_t* out4);
+
+/* ---- communicators: what MPI_Comm is to the reference's Domain (domain.hpp:63-86) ----
+ * local: ranks are threads of one process (any rank -> device mapping); nccl: one process per GPU, libnccl is
+ * dlopen()ed on first use.  cs_nccl_unique_id fills 128 bytes that rank 0 distributes to the other ranks. */
+typedef struct cs_comm cs_comm_t;
+void* cs_local_world_create(int size);
+void cs_local_world_destroy(void* world);
+cs_comm_t* cs_comm_create_local(void* world, int rank);
+int cs_nccl_unique_id(void* out128);
+cs_comm_t* cs_comm_create_nccl(int rank, int size, const void* id128);
+void cs_comm_destroy(cs_comm_t* comm);
+int cs_comm_rank(const cs_comm_t* comm);
+int cs_comm_size(const cs_comm_t* comm);
+uint64_t cs_comm_bytes_sent(const cs_comm_t* comm);
+
 /* ---- Domain: cstone::Domain<KeyType,T,Gpu> (domain/domain.hpp:38-664) ----
  * cs_domain_create_*  <-> Domain(exec, rank, nRanks, bucketSize, bucketSizeFocus, theta, comm, box)  domain.hpp:63-86
  *                         (returns NULL + cs_last_error() where the reference throws std::runtime_error)
@@ -230,6 +258,9 @@ int cs_domain_info(const cs_domain_t* d, uint64_t* out8, double* box6);
 void* cs_domain_ptr(cs_domain_t* d, int field);
 int cs_domain_find_neighbors(cs_domain_t* d, uint32_t ngmax, uint32_t* neighbors, uint32_t* neighborsCount,
                              void* stream);
+/* multi-rank domains (numRanks > 1): attach the communicator (same rank/size) before the first cs_domain_sync; the
+ * communicator must outlive the domain */
+int cs_domain_attach_comm(cs_domain_t* d, cs_comm_t* comm);
 /* forget all tree state so that the next cs_domain_sync behaves like the first call on a new Domain (device buffers
  * are kept; used by bench.py to time cold syncs without re-allocating) */
 int cs_domain_reset(cs_domain_t* d, void* stream);

@@ -1,0 +1,109 @@
+"""Multi-rank Domain parity (-m gpu): P ranks run as threads of this process over the library's thread-backed
+communicator (cs_comm_create_local), all on cuda:0, and are compared rank by rank with the UNMODIFIED reference run
+with P ranks (oracle/_ref, thread-backed MPI stand-in).  The same C++ code runs over NCCL with one process per GPU
+(bench.py --gpus N)."""
+import threading
+
+import numpy as np
+import pytest
+import torch
+
+from _libs import key_of, real_of, ref, ref_domain_run
+from _util import const_h, gaussian_particles, uniform_particles
+
+pytestmark = pytest.mark.gpu
+
+DEV = "cuda:0"
+
+
+def capi():
+    from cstone_b200 import capi as c
+    return c
+
+
+def run_ranks(P, fn):
+    """run fn(rank) on P threads (each with its own CUDA stream); re-raise the first failure"""
+    errors = [None] * P
+    results = [None] * P
+
+    def body(r):
+        try:
+            with torch.cuda.stream(torch.cuda.Stream(device=DEV)):
+                results[r] = fn(r)
+                torch.cuda.current_stream().synchronize()
+        except BaseException as e:  # noqa: BLE001
+            errors[r] = e
+
+    threads = [threading.Thread(target=body, args=(r,)) for r in range(P)]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join(timeout=120)
+    for t in threads:
+        assert not t.is_alive(), "rank thread hung"
+    for e in errors:
+        if e is not None:
+            raise e
+    return results
+
+
+def make_particles(combo, n, dist, seed):
+    T = real_of(combo)
+    if dist == "gaussian":
+        x, y, z = gaussian_particles(n, T, seed)
+        lim = (-1, 1, -1, 1, -1, 1)
+    else:
+        x, y, z = uniform_particles(n, T, seed)
+        lim = (0, 1, 0, 1, 0, 1)
+    return x, y, z, lim
+
+
+@pytest.mark.skipif(ref() is None, reason="needs oracle/_ref (built where /root/reference exists)")
+@pytest.mark.parametrize("combo,P,dist,pbc,bucket,bucket_focus", [
+    ("u64d", 2, "uniform", 0, 64, 8),
+    ("u64d", 3, "gaussian", 1, 128, 16),
+    ("u64d", 4, "uniform", 1, 64, 8),
+    ("u64f", 4, "gaussian", 0, 64, 64),
+    ("u32f", 2, "uniform", 0, 32, 8),
+    ("u64d", 8, "uniform", 0, 256, 16),
+])
+def test_assigned_particles_match_reference(combo, P, dist, pbc, bucket, bucket_focus):
+    """after sync every rank owns exactly the reference's particles in the reference's order: keys, x, y, z, h of
+    [startIndex, endIndex), the global tree and the coordinate box are bit-identical (two consecutive syncs)"""
+    n_per = 6000
+    n = n_per * P
+    x, y, z, lim = make_particles(combo, n, dist, 3)
+    T = real_of(combo)
+    h = const_h(n, 40, T, 8.0 if dist == "gaussian" else 1.0)
+    bnd = (pbc, pbc, pbc)
+    offsets = [n_per * r for r in range(P + 1)]
+    for num_syncs in (1, 2):
+        want = ref_domain_run(combo, P, bucket, bucket_focus, 0.5, lim, bnd, x, y, z, h, offsets, num_syncs=num_syncs)
+        world = capi().LocalWorld(P)
+
+        def rank_body(r):
+            c = capi()
+            comm = world.comm(r)
+            dom = c.Domain(r, P, bucket, bucket_focus, 0.5, lim, bnd, key=key_of(combo), real=combo[-1], device=DEV,
+                           comm=comm)
+            sl = slice(offsets[r], offsets[r + 1])
+            to = lambda a: torch.from_numpy(np.ascontiguousarray(a[sl])).to(DEV)  # noqa: E731
+            dom.sync(to(x), to(y), to(z), to(h))
+            for _ in range(num_syncs - 1):
+                dom.sync()
+            s, e = dom.start_index, dom.end_index
+            out = {k: dom.field(k)[s:e].cpu().numpy() for k in ("keys", "x", "y", "z", "h")}
+            out["global_leaves"] = dom.field("global_leaves").cpu().numpy()
+            out["box"] = dom.box
+            dom.close()
+            comm.close()
+            return out
+
+        got = run_ranks(P, rank_body)
+        for r in range(P):
+            w = want[r]
+            s, e = w["start"], w["end"]
+            assert np.array_equal(got[r]["global_leaves"], w["global_leaves"]), (r, "global leaves")
+            assert np.array_equal(np.asarray(got[r]["box"]), w["box"]), (r, "box")
+            for k in ("keys", "x", "y", "z", "h"):
+                assert np.array_equal(got[r][k], w[k][s:e]), (r, k, num_syncs)
