@@ -182,6 +182,12 @@ public:
         firstCall_ = true;
         start_ = end_ = bufSize_ = 0;
         std::copy(lim0_, lim0_ + 6, lim_);
+        const double unitBox[6] = {0, 1, 0, 1, 0, 1};
+        std::copy(unitBox, unitBox + 6, focusLim_);
+        fLeavesHost_.clear();
+        globDispl_.clear();
+        geoCenters_.n = geoSizes_.n = 0;
+        macs_.n                     = 0;
         return init(s);
     }
 
@@ -354,6 +360,7 @@ public:
         }
 
         /* ---- focus tree (domain.hpp:189-213) */
+        if (P > 1) { return syncFocusMultiRank(keyView, numAssigned, s); }
         if (firstCall_)
         {
             int converged = 0;
@@ -392,6 +399,587 @@ public:
         end_       = numAssigned;
         bufSize_   = numAssigned;
         firstCall_ = false;
+        return 0;
+    }
+
+    /* ============================================================ multi-rank: LET, halos (domain.hpp:189-217) */
+
+    int syncFocusMultiRank(const K* keyView, LocalIndex numAssigned, cudaStream_t s)
+    {
+        Comm& comm           = *comm_;
+        const int P          = comm.size();
+        const float invTheta = 1.0f / theta_ + 0.5f; // invThetaMinMac (traversal/macs.hpp:28)
+
+        // 64-bit scan of the replicated global counts for rangeCount
+        {
+            std::vector<uint64_t> scan(gCountsHost_.size() + 1, 0);
+            for (size_t i = 0; i < gCountsHost_.size(); ++i)
+                scan[i + 1] = scan[i] + gCountsHost_[i];
+            CSB_TRY(gCountScan_.resize(scan.size(), s));
+            CSB_CHECK(cudaMemcpyAsync(gCountScan_.p, scan.data(), scan.size() * sizeof(uint64_t), cudaMemcpyHostToDevice,
+                                      s));
+            CSB_CHECK(cudaStreamSynchronize(s));
+        }
+
+        if (firstCall_)
+        {
+            // FocusedOctree::converge (octree_focus_mpi.hpp:584-602)
+            int numConverged = 0;
+            while (numConverged != P)
+            {
+                int converged = 0;
+                CSB_TRY(letUpdateMinMac(invTheta, false, s));
+                CSB_TRY(updateFocusTree(&converged, s));
+                CSB_TRY(letUpdateCounts(keyView, numAssigned, s));
+                CSB_TRY(allreduceSumInt(converged, &numConverged, s));
+            }
+        }
+
+        int fail = 0, maxRep = 10;
+        do
+        {
+            int converged = 0;
+            CSB_TRY(letUpdateMinMac(invTheta, true, s));
+            CSB_TRY(updateFocusTree(&converged, s));
+            CSB_TRY(letUpdateCounts(keyView, numAssigned, s));
+            CSB_TRY(letDiscoverHalos(s));
+            int localFail = 0;
+            CSB_TRY(letComputeLayout(&localFail, s));
+            CSB_TRY(allreduceSumInt(localFail, &fail, s));
+            CSB_TRY(haloExchangeRequests(s));
+        } while (fail && maxRep--);
+
+        /* ---- updateLayout (domain.hpp:490-537) */
+        const int me              = comm.rank();
+        const LocalIndex newStart = layoutHost_[fAssign_[me].first];
+        const LocalIndex newEnd   = layoutHost_[fAssign_[me].second];
+        const LocalIndex newSize  = layoutHost_.back();
+        CSB_REQUIRE(newEnd - newStart == numAssigned, "layout of the assigned leaves does not match the particles");
+        CSB_TRY(keyBuf_.resize(std::max<size_t>(numAssigned, 1), s));
+        CSB_CHECK(cudaMemcpyAsync(keyBuf_.p, keyView, size_t(numAssigned) * sizeof(K), cudaMemcpyDeviceToDevice, s));
+        CSB_TRY(keys_.resize(std::max<size_t>(newSize, 1), s));
+        CSB_CHECK(cudaMemsetAsync(keys_.p, 0, size_t(newSize) * sizeof(K), s));
+        CSB_CHECK(cudaMemcpyAsync(keys_.p + newStart, keyBuf_.p, size_t(numAssigned) * sizeof(K),
+                                  cudaMemcpyDeviceToDevice, s));
+        DevBuf<T>* dst[4] = {&x_, &y_, &z_, &h_};
+        DevBuf<T>* src[4] = {&sx_, &sy_, &sz_, &sh_};
+        for (int k = 0; k < 4; ++k)
+        {
+            CSB_TRY(dst[k]->resize(std::max<size_t>(newSize, 1), s));
+            CSB_CHECK(cudaMemcpyAsync(dst[k]->p + newStart, src[k]->p, size_t(numAssigned) * sizeof(T),
+                                      cudaMemcpyDeviceToDevice, s));
+            dst[k]->n = newSize;
+        }
+        keys_.n  = newSize;
+        start_   = newStart;
+        end_     = newEnd;
+        bufSize_ = newSize;
+
+        /* ---- setupHalos (domain.hpp:479-488) */
+        CSB_TRY(exchangeHalos(s));
+        CSB_TRY(keysDispatch(0, x_.p, y_.p, z_.p, keys_.p, start_, lim_, bnd_, s));
+        CSB_TRY(keysDispatch(0, x_.p + end_, y_.p + end_, z_.p + end_, keys_.p + end_, size_t(bufSize_) - end_, lim_,
+                             bnd_, s));
+        CSB_CHECK(cudaStreamSynchronize(s));
+        firstCall_ = false;
+        return 0;
+    }
+
+    int allreduceSumInt(int value, int* sum, cudaStream_t s)
+    {
+        std::vector<int> all(comm_->size());
+        CSB_TRY(comm_->allgatherHost(&value, sizeof(int), all.data(), s));
+        *sum = 0;
+        for (int v : all)
+            *sum += v;
+        return 0;
+    }
+
+    //! personalised all-to-all of host byte vectors (sizes exchanged first); the role of the Isend/Probe/Recv idiom
+    //! of focus/exchange_focus.hpp and domain/exchange_keys.hpp
+    int alltoallvHost(const std::vector<std::vector<char>>& send, std::vector<std::vector<char>>& recv, cudaStream_t s)
+    {
+        Comm& comm   = *comm_;
+        const int P  = comm.size();
+        const int me = comm.rank();
+        std::vector<uint64_t> sizes(P), all(size_t(P) * P);
+        for (int r = 0; r < P; ++r)
+            sizes[r] = send[r].size();
+        CSB_TRY(comm.allgatherHost(sizes.data(), P * sizeof(uint64_t), all.data(), s));
+        auto pad = [](size_t b) { return (b + 15) & ~size_t(15); };
+        size_t sendTotal = 0, recvTotal = 0;
+        for (int r = 0; r < P; ++r)
+        {
+            sendTotal += pad(send[r].size());
+            recvTotal += pad(all[size_t(r) * P + me]);
+        }
+        CSB_TRY(hostStage_.resize(std::max<size_t>(sendTotal + recvTotal, 16), s));
+        std::vector<CommMessage> sends, recvs;
+        size_t off = 0;
+        for (int r = 0; r < P; ++r)
+        {
+            if (r == me || send[r].empty()) { continue; }
+            CSB_CHECK(cudaMemcpyAsync(hostStage_.p + off, send[r].data(), send[r].size(), cudaMemcpyHostToDevice, s));
+            sends.push_back({r, hostStage_.p + off, send[r].size()});
+            off += pad(send[r].size());
+        }
+        std::vector<size_t> recvOff(P, 0);
+        off = sendTotal;
+        for (int r = 0; r < P; ++r)
+        {
+            size_t b = all[size_t(r) * P + me];
+            if (r == me || b == 0) { continue; }
+            recvOff[r] = off;
+            recvs.push_back({r, hostStage_.p + off, b});
+            off += pad(b);
+        }
+        CSB_TRY(comm.exchange(sends, recvs, s));
+        recv.assign(P, {});
+        for (int r = 0; r < P; ++r)
+        {
+            size_t b = all[size_t(r) * P + me];
+            if (r == me || b == 0) { continue; }
+            recv[r].resize(b);
+            CSB_CHECK(cudaMemcpyAsync(recv[r].data(), hostStage_.p + recvOff[r], b, cudaMemcpyDeviceToHost, s));
+        }
+        CSB_CHECK(cudaStreamSynchronize(s));
+        return 0;
+    }
+
+    static int nodeAbove(const std::vector<K>& leaves, K key)
+    {
+        return int(std::lower_bound(leaves.begin(), leaves.end(), key) - leaves.begin());
+    }
+    static int nodeBelow(const std::vector<K>& leaves, K key)
+    {
+        return int(std::upper_bound(leaves.begin(), leaves.end(), key) - leaves.begin()) - 1;
+    }
+
+    //! domaindecomp.hpp:129-157
+    void translateAssignment()
+    {
+        const int P = comm_->size();
+        fAssign_.assign(P, {0, 0});
+        for (int r = 0; r < P; ++r)
+        {
+            int a = nodeAbove(fLeavesHost_, assignment_.boundaries[r]);
+            int b = nodeBelow(fLeavesHost_, assignment_.boundaries[r + 1]);
+            if (b < a) { b = a; }
+            fAssign_[r] = {a, b};
+        }
+    }
+
+    //! domaindecomp.hpp:159-168
+    void extractPeerRanges()
+    {
+        peerRanges_.clear();
+        for (int p : extPeers_)
+            peerRanges_.push_back(fAssign_[p]);
+        peerRanges_.push_back(fAssign_[comm_->rank()]);
+        std::sort(peerRanges_.begin(), peerRanges_.end());
+    }
+
+    int downloadFocusLeaves(cudaStream_t s)
+    {
+        fLeavesHost_.resize(size_t(fTree_.numLeaves) + 1);
+        CSB_CHECK(cudaMemcpyAsync(fLeavesHost_.data(), fLeaves_.p, fLeavesHost_.size() * sizeof(K),
+                                  cudaMemcpyDeviceToHost, s));
+        CSB_CHECK(cudaStreamSynchronize(s));
+        return 0;
+    }
+
+    /*! the rank-to-rank part of FocusedOctree::updateTree (octree_focus_mpi.hpp:137-165): focus peers, treelet
+     *  exchange with rejection of keys the owner does not have (focus/exchange_focus.hpp:60-230), treelet indices */
+    int letSyncWithPeers(cudaStream_t s)
+    {
+        Comm& comm   = *comm_;
+        const int P  = comm.size();
+        const int me = comm.rank();
+        CSB_TRY(downloadFocusLeaves(s));
+        translateAssignment();
+
+        // focusPeers (focus/peer_flags.hpp:33-57) with the global offsets of the PREVIOUS call (globDispl_)
+        std::vector<int> extFlags(P, 0), allFlags(size_t(P) * P);
+        if (globDispl_.empty()) { globDispl_.assign(size_t(P) + 1, 0); }
+        for (int r = 0; r < P; ++r)
+        {
+            if (r == me) { continue; }
+            auto gs = gLeavesHost_.begin() + globDispl_[r], ge = gLeavesHost_.begin() + globDispl_[r + 1];
+            auto fs = fLeavesHost_.begin() + fAssign_[r].first, fe = fLeavesHost_.begin() + fAssign_[r].second;
+            bool isPeer = (fe - fs > ge - gs) ? true : !std::includes(gs, ge, fs, fe);
+            extFlags[r] = isPeer ? 1 : 0;
+        }
+        CSB_TRY(comm.allgatherHost(extFlags.data(), P * sizeof(int), allFlags.data(), s));
+        extPeers_.clear();
+        intPeers_.clear();
+        for (int r = 0; r < P; ++r)
+        {
+            if (extFlags[r]) { extPeers_.push_back(r); }
+            if (allFlags[size_t(r) * P + me]) { intPeers_.push_back(r); }
+        }
+        extractPeerRanges();
+
+        // exchangeTreelets: my view of the peer's domain goes to the peer
+        std::vector<std::vector<char>> send(P), recv;
+        for (int p : extPeers_)
+        {
+            const K* b = fLeavesHost_.data() + fAssign_[p].first;
+            size_t cnt = size_t(fAssign_[p].second - fAssign_[p].first) + 1;
+            send[p].assign(reinterpret_cast<const char*>(b), reinterpret_cast<const char*>(b + cnt));
+        }
+        CSB_TRY(alltoallvHost(send, recv, s));
+        treelets_.assign(P, {});
+        std::vector<std::vector<char>> rejected(P);
+        const int numLeaves = fTree_.numLeaves;
+        for (int p : intPeers_)
+        {
+            const K* b = reinterpret_cast<const K*>(recv[p].data());
+            size_t cnt = recv[p].size() / sizeof(K);
+            std::vector<K>& tl = treelets_[p];
+            tl.reserve(cnt);
+            // checkTreelets + pruneTreelets: keys that are not leaf boundaries here are reported back and dropped
+            for (size_t i = 0; i < cnt; ++i)
+            {
+                K k        = b[i];
+                bool valid = true;
+                if (i + 1 < cnt && k != 0 && k != nodeRange<K>(0))
+                {
+                    int j = int(std::lower_bound(fLeavesHost_.begin(), fLeavesHost_.begin() + numLeaves, k) -
+                                fLeavesHost_.begin());
+                    valid = (k == fLeavesHost_[j]);
+                }
+                if (valid) { tl.push_back(k); }
+                else
+                {
+                    const char* kb = reinterpret_cast<const char*>(&k);
+                    rejected[p].insert(rejected[p].end(), kb, kb + sizeof(K));
+                }
+            }
+        }
+        // exchangeRejectedKeys: leaves of mine that the owner does not have are removed (nodeOps = 0)
+        std::vector<std::vector<char>> rejRecv;
+        CSB_TRY(alltoallvHost(rejected, rejRecv, s));
+        std::vector<int> nodeOps(size_t(numLeaves) + 1, 1);
+        bool changed = false;
+        for (int p : extPeers_)
+        {
+            const K* b = reinterpret_cast<const K*>(rejRecv[p].data());
+            size_t cnt = rejRecv[p].size() / sizeof(K);
+            for (size_t i = 0; i < cnt; ++i)
+            {
+                nodeOps[nodeAbove(fLeavesHost_, b[i])] = 0;
+                changed                               = true;
+            }
+        }
+        if (changed)
+        {
+            std::vector<int> scan(nodeOps.size());
+            int sum = 0;
+            for (size_t i = 0; i < nodeOps.size(); ++i)
+            {
+                scan[i] = sum;
+                sum += nodeOps[i];
+            }
+            int newNumLeaves = scan[numLeaves];
+            CSB_TRY(nodeOps_.resize(scan.size(), s));
+            CSB_CHECK(cudaMemcpyAsync(nodeOps_.p, scan.data(), scan.size() * sizeof(int), cudaMemcpyHostToDevice, s));
+            CSB_TRY(fLeavesAlt_.resize(size_t(newNumLeaves) + 1, s));
+            CSB_TRY(rebalanceTree<K>(fLeaves_.p, numLeaves, newNumLeaves, nodeOps_.p, fLeavesAlt_.p, s));
+            CSB_CHECK(cudaStreamSynchronize(s));
+            fLeaves_.swap(fLeavesAlt_);
+            CSB_TRY(linkTree(fLeaves_, newNumLeaves, fTree_, s));
+            CSB_TRY(downloadFocusLeaves(s));
+        }
+
+        // indexTreelets (exchange_focus.hpp:286-308) on the host copy of the prefixes
+        fPrefixesHost_.resize(fTree_.numNodes);
+        CSB_CHECK(cudaMemcpyAsync(fPrefixesHost_.data(), fTree_.prefixes.p, fPrefixesHost_.size() * sizeof(K),
+                                  cudaMemcpyDeviceToHost, s));
+        CSB_CHECK(cudaStreamSynchronize(s));
+        treeletOffsets_.assign(size_t(P) + 1, 0);
+        std::vector<int> tlIdx;
+        const std::vector<int>& lr = fTree_.levelRangeHost;
+        for (int p = 0; p < P; ++p)
+        {
+            treeletOffsets_[p] = int(tlIdx.size());
+            const std::vector<K>& tl = treelets_[p];
+            for (size_t i = 0; i + 1 < tl.size(); ++i)
+            {
+                K a = tl[i], b = tl[i + 1];
+                unsigned level = treeLevel<K>(b - a);
+                K prefix       = encodePlaceholderBit(a, int(3 * level));
+                auto first     = fPrefixesHost_.begin() + lr[level];
+                auto last      = fPrefixesHost_.begin() + lr[level + 1];
+                auto it        = std::lower_bound(first, last, prefix);
+                CSB_REQUIRE(it != last && *it == prefix, "treelet node of a peer does not exist in the LET");
+                tlIdx.push_back(int(it - fPrefixesHost_.begin()));
+            }
+        }
+        treeletOffsets_[P] = int(tlIdx.size());
+        CSB_TRY(treeletIdx_.resize(std::max<size_t>(tlIdx.size(), 1), s));
+        CSB_CHECK(cudaMemcpyAsync(treeletIdx_.p, tlIdx.data(), tlIdx.size() * sizeof(int), cudaMemcpyHostToDevice, s));
+        CSB_CHECK(cudaStreamSynchronize(s));
+
+        translateAssignment();
+        extractPeerRanges();
+        globDispl_ = assignment_.treeOffsets;
+        return 0;
+    }
+
+    /*! FocusedOctree::updateMinMac + updateMacs (octree_focus_mpi.hpp:422-499): MAC spheres from the geometric centres
+     *  of the last tree update, then mark every node outside the focus that fails the MAC against a focus leaf */
+    int letUpdateMinMac(float invTheta, bool accumulate, cudaStream_t s)
+    {
+        const int me       = comm_->rank();
+        const int numNodes = fTree_.numNodes;
+        if (geoCenters_.n != size_t(3) * numNodes) { CSB_TRY(updateGeoCenters(s)); } // first call: box (0,1)
+        if (fLeavesHost_.empty()) { CSB_TRY(downloadFocusLeaves(s)); }
+        CSB_TRY(centers4_.resize(size_t(4) * numNodes, s));
+        CSB_TRY(minMacCenters<T>(geoCenters_.p, geoSizes_.p, numNodes, invTheta, centers4_.p, s));
+        if (accumulate) { CSB_REQUIRE(macs_.n == size_t(numNodes), "MAC flags not correctly allocated"); }
+        CSB_TRY(macs_.resize(numNodes, s, true));
+        if (!accumulate) { CSB_CHECK(cudaMemsetAsync(macs_.p, 0, size_t(numNodes), s)); }
+        int fStart = nodeAbove(fLeavesHost_, assignment_.boundaries[me]);
+        int fEnd   = nodeAbove(fLeavesHost_, assignment_.boundaries[me + 1]);
+        fStart     = std::min(fStart, fTree_.numLeaves);
+        fEnd       = std::min(fEnd, fTree_.numLeaves);
+        return markMacs<K, T>(fTree_.prefixes.p, fTree_.childOffsets.p, fTree_.parents.p, centers4_.p, focusLim_, bnd_,
+                              fLeaves_.p + fStart, fEnd - fStart, macs_.p, s);
+    }
+
+    //! FocusedOctree::updateCounts (octree_focus_mpi.hpp:193-252)
+    int letUpdateCounts(const K* keyView, size_t numKeys, cudaStream_t s)
+    {
+        Comm& comm          = *comm_;
+        const int numLeaves = fTree_.numLeaves;
+        // leaves outside my and my peers' ranges take their counts from the global tree (layout.hpp:59-91)
+        std::vector<int> idxFromGlob;
+        {
+            int cur = 0;
+            for (auto r : peerRanges_)
+            {
+                if (r.first == r.second) { continue; }
+                for (int i = cur; i < r.first; ++i)
+                    idxFromGlob.push_back(i);
+                cur = r.second;
+            }
+            for (int i = cur; i < numLeaves; ++i)
+                idxFromGlob.push_back(i);
+        }
+        CSB_TRY(fLeafCounts_.resize(numLeaves, s));
+        CSB_TRY(computeNodeCounts<K>(fLeaves_.p, fLeafCounts_.p, numLeaves, keyView, numKeys,
+                                     std::numeric_limits<unsigned>::max(), s));
+        CSB_TRY(idxBuf_.resize(std::max<size_t>(idxFromGlob.size(), 1), s));
+        CSB_CHECK(cudaMemcpyAsync(idxBuf_.p, idxFromGlob.data(), idxFromGlob.size() * sizeof(int), cudaMemcpyHostToDevice,
+                                  s));
+        CSB_TRY(rangeCount<K>(gLeaves_.p, numGlobalLeaves_, gCountScan_.p, fLeaves_.p, idxBuf_.p, int(idxFromGlob.size()),
+                              fLeafCounts_.p, s));
+        CSB_CHECK(cudaStreamSynchronize(s)); // idxFromGlob is a host temporary
+
+        CSB_TRY(fCounts_.resize(fTree_.numNodes, s));
+        CSB_TRY(scatterCounts(fTree_.leafToInternalLeaves(), numLeaves, fLeafCounts_.p, fCounts_.p, s));
+        CSB_TRY(upsweepSum(KeyTraits<K>::maxLevel, fTree_.levelRangeHost.data(), fTree_.childOffsets.p, fCounts_.p, s));
+
+        // peerExchange (exchangeTreeletGeneral, exchange_focus.hpp:310-366): counts of the peers' treelet nodes go out,
+        // the owners' counts of my leaves in their domains come in
+        size_t sendTotal = size_t(treeletOffsets_.back()), recvTotal = 0;
+        for (int p : extPeers_)
+            recvTotal += size_t(fAssign_[p].second - fAssign_[p].first);
+        CSB_TRY(peerBuf_.resize(std::max<size_t>(sendTotal + recvTotal, 1), s));
+        std::vector<CommMessage> sends, recvs;
+        for (int p : intPeers_)
+        {
+            int n = treeletOffsets_[p + 1] - treeletOffsets_[p];
+            CSB_TRY(gatherU32(treeletIdx_.p + treeletOffsets_[p], n, fCounts_.p, peerBuf_.p + treeletOffsets_[p], s));
+            sends.push_back({p, peerBuf_.p + treeletOffsets_[p], size_t(n) * sizeof(uint32_t)});
+        }
+        size_t off = sendTotal;
+        for (int p : extPeers_)
+        {
+            size_t n = size_t(fAssign_[p].second - fAssign_[p].first);
+            recvs.push_back({p, peerBuf_.p + off, n * sizeof(uint32_t)});
+            off += n;
+        }
+        CSB_TRY(comm.exchange(sends, recvs, s));
+        off = sendTotal;
+        for (int p : extPeers_)
+        {
+            int n = fAssign_[p].second - fAssign_[p].first;
+            CSB_TRY(scatterU32(fTree_.leafToInternalLeaves() + fAssign_[p].first, n, peerBuf_.p + off, fCounts_.p, s));
+            off += size_t(n);
+        }
+        CSB_TRY(upsweepSum(KeyTraits<K>::maxLevel, fTree_.levelRangeHost.data(), fTree_.childOffsets.p, fCounts_.p, s));
+        CSB_TRY(gatherU32(fTree_.leafToInternalLeaves(), numLeaves, fCounts_.p, fLeafCounts_.p, s));
+        return 0;
+    }
+
+    //! FocusedOctree::discoverHalos (octree_focus_mpi.hpp:511-568); the assigned particles are at offset 0 of sx_..
+    int letDiscoverHalos(cudaStream_t s)
+    {
+        const int me        = comm_->rank();
+        const int firstNode = fAssign_[me].first, lastNode = fAssign_[me].second;
+        const int numLeaves = fTree_.numLeaves;
+        CSB_TRY(macs_.resize(fTree_.numNodes, s));
+        CSB_TRY(searchCenters_.resize(size_t(3) * numLeaves, s));
+        CSB_TRY(searchSizes_.resize(size_t(3) * numLeaves, s));
+        CSB_TRY(gatherVec3<T>(fTree_.leafToInternalLeaves(), numLeaves, geoCenters_.p, searchCenters_.p, s));
+        CSB_TRY(layout_.resize(size_t(numLeaves) + 1, s));
+        // layout[firstNode] = 0, inclusive scan of the own leaf counts behind it
+        size_t cnt = size_t(lastNode - firstNode);
+        CSB_CHECK(cudaMemcpyAsync(layout_.p + firstNode, fLeafCounts_.p + firstNode, cnt * sizeof(uint32_t),
+                                  cudaMemcpyDeviceToDevice, s));
+        CSB_CHECK(cudaMemsetAsync(layout_.p + lastNode, 0, sizeof(uint32_t), s));
+        CSB_TRY(scanTmp_.resize(scanTempBytes(cnt + 1), s));
+        CSB_TRY(exclusiveScanU32(layout_.p + firstNode, layout_.p + firstNode, cnt + 1, scanTmp_.p, s));
+        CSB_TRY(computeBoundingBoxes<T>(sx_.p, sy_.p, sz_.p, sh_.p, layout_.p, firstNode, lastNode, T(2),
+                                        searchCenters_.p, searchSizes_.p, s));
+        CSB_CHECK(cudaMemsetAsync(macs_.p, 0, size_t(fTree_.numNodes), s));
+        return findHalos<K, T>(fTree_.prefixes.p, fTree_.childOffsets.p, fTree_.parents.p, geoCenters_.p, geoSizes_.p,
+                               fLeaves_.p, searchCenters_.p, searchSizes_.p, focusLim_, bnd_, firstNode, lastNode,
+                               macs_.p, s);
+    }
+
+    //! FocusedOctree::computeLayout (octree_focus_mpi.hpp:570-582) + checkLayout (domain/layout.hpp:187-219)
+    int letComputeLayout(int* fail, cudaStream_t s)
+    {
+        const int me        = comm_->rank();
+        const int numLeaves = fTree_.numLeaves;
+        CSB_TRY(layoutCounts(fLeafCounts_.p, macs_.p, fTree_.leafToInternalLeaves(), numLeaves, fAssign_[me].first,
+                             fAssign_[me].second, layout_.p, s));
+        CSB_TRY(scanTmp_.resize(scanTempBytes(size_t(numLeaves) + 1), s));
+        CSB_TRY(exclusiveScanU32(layout_.p, layout_.p, size_t(numLeaves) + 1, scanTmp_.p, s));
+        layoutHost_.resize(size_t(numLeaves) + 1);
+        CSB_CHECK(cudaMemcpyAsync(layoutHost_.data(), layout_.p, layoutHost_.size() * sizeof(uint32_t),
+                                  cudaMemcpyDeviceToHost, s));
+        CSB_CHECK(cudaStreamSynchronize(s));
+        int ret                  = 0;
+        const unsigned maxParts  = 512u * bucketFocus_;
+        const int ranges[2][2]   = {{0, fAssign_[me].first}, {fAssign_[me].second, numLeaves}};
+        for (auto& rg : ranges)
+            for (int i = rg[0]; i < rg[1]; ++i)
+            {
+                if (layoutHost_[i + 1] > layoutHost_[i])
+                {
+                    bool peerFound = false;
+                    for (auto pr : fAssign_)
+                        if (pr.first <= i && i < pr.second) { peerFound = true; }
+                    if (!peerFound) { ret = 1; }
+                }
+                if (layoutHost_[i + 1] - layoutHost_[i] > maxParts) { ret = -1; }
+            }
+        *fail = ret;
+        return 0;
+    }
+
+    //! Halos::exchangeRequests (halos/halos.hpp:64-80, halos/halo_peers.hpp:20-48, domain/exchange_keys.hpp:45-99)
+    int haloExchangeRequests(cudaStream_t s)
+    {
+        Comm& comm   = *comm_;
+        const int P  = comm.size();
+        const int me = comm.rank();
+        std::vector<int> extFlags(P, 0), allFlags(size_t(P) * P);
+        for (int r = 0; r < P; ++r)
+            if (r != me) { extFlags[r] = layoutHost_[fAssign_[r].second] > layoutHost_[fAssign_[r].first] ? 1 : 0; }
+        CSB_TRY(comm.allgatherHost(extFlags.data(), P * sizeof(int), allFlags.data(), s));
+        haloExtPeers_.clear();
+        haloIntPeers_.clear();
+        for (int r = 0; r < P; ++r)
+        {
+            if (extFlags[r]) { haloExtPeers_.push_back(r); }
+            if (allFlags[size_t(r) * P + me]) { haloIntPeers_.push_back(r); }
+        }
+        // request keys: extractMarkedElements (domain/layout.hpp:110-141)
+        std::vector<std::vector<char>> send(P), recv;
+        for (int p : haloExtPeers_)
+        {
+            std::vector<K> req;
+            int a = fAssign_[p].first, b = fAssign_[p].second;
+            while (a != b)
+            {
+                while (a < b && layoutHost_[a + 1] == layoutHost_[a])
+                    ++a;
+                if (a != b)
+                {
+                    req.push_back(fLeavesHost_[a]);
+                    while (a < b && layoutHost_[a + 1] > layoutHost_[a])
+                        ++a;
+                    req.push_back(fLeavesHost_[a]);
+                }
+            }
+            const char* rb = reinterpret_cast<const char*>(req.data());
+            send[p].assign(rb, rb + req.size() * sizeof(K));
+        }
+        CSB_TRY(alltoallvHost(send, recv, s));
+        outgoing_.assign(P, {});
+        for (int p : haloIntPeers_)
+        {
+            const K* b = reinterpret_cast<const K*>(recv[p].data());
+            size_t cnt = recv[p].size() / sizeof(K);
+            for (size_t i = 0; i + 1 < cnt; i += 2)
+            {
+                uint32_t lo = layoutHost_[nodeAbove(fLeavesHost_, b[i])];
+                uint32_t hi = layoutHost_[nodeAbove(fLeavesHost_, b[i + 1])];
+                if (lo != hi) { outgoing_[p].push_back({lo, hi}); }
+            }
+        }
+        incoming_.assign(P, {0, 0});
+        for (int p : haloExtPeers_)
+            incoming_[p] = {layoutHost_[fAssign_[p].first], layoutHost_[fAssign_[p].second]};
+        return 0;
+    }
+
+    /*! haloExchangeGpu (halos/exchange_halos_gpu.cuh:34-119) for x, y, z, h: outgoing index ranges are packed per peer
+     *  into [x | y | z | h] blocks, incoming halos of a peer are contiguous and land directly in the arrays */
+    int exchangeHalos(cudaStream_t s)
+    {
+        Comm& comm  = *comm_;
+        const int P = comm.size();
+        auto blockElems = [](size_t c) { return (c + 3) & ~size_t(3); };
+        std::vector<uint32_t> tables; // per peer: scan[numRanges] then start[numRanges]
+        std::vector<size_t> tableOff(P, 0), totals(P, 0);
+        size_t sendTotal = 0;
+        for (int p = 0; p < P; ++p)
+        {
+            if (outgoing_[p].empty()) { continue; }
+            tableOff[p]   = tables.size();
+            uint32_t scan = 0;
+            for (auto& r : outgoing_[p])
+            {
+                tables.push_back(scan);
+                scan += r.second - r.first;
+            }
+            for (auto& r : outgoing_[p])
+                tables.push_back(r.first);
+            totals[p] = scan;
+            sendTotal += 4 * blockElems(scan);
+        }
+        CSB_TRY(rangeTables_.resize(std::max<size_t>(tables.size(), 1), s));
+        CSB_CHECK(cudaMemcpyAsync(rangeTables_.p, tables.data(), tables.size() * sizeof(uint32_t), cudaMemcpyHostToDevice,
+                                  s));
+        CSB_TRY(sendBuf_.resize(std::max<size_t>(sendTotal, 1), s));
+        std::vector<CommMessage> sends, recvs;
+        size_t off = 0;
+        for (int p = 0; p < P; ++p)
+        {
+            if (outgoing_[p].empty()) { continue; }
+            int nr    = int(outgoing_[p].size());
+            size_t be = blockElems(totals[p]);
+            CSB_TRY(gatherRanges4<T>(rangeTables_.p + tableOff[p], rangeTables_.p + tableOff[p] + nr, nr,
+                                     uint32_t(totals[p]), x_.p, y_.p, z_.p, h_.p, sendBuf_.p + off, be, s));
+            for (int k = 0; k < 4; ++k)
+                sends.push_back({p, sendBuf_.p + off + k * be, totals[p] * sizeof(T)});
+            off += 4 * be;
+        }
+        T* arrays[4] = {x_.p, y_.p, z_.p, h_.p};
+        for (int p = 0; p < P; ++p)
+        {
+            size_t c = size_t(incoming_[p].second - incoming_[p].first);
+            if (c == 0) { continue; }
+            for (int k = 0; k < 4; ++k)
+                recvs.push_back({p, arrays[k] + incoming_[p].first, c * sizeof(T)});
+        }
+        CSB_TRY(comm.exchange(sends, recvs, s));
+        CSB_CHECK(cudaStreamSynchronize(s)); // `tables` is a host temporary
         return 0;
     }
 
@@ -660,8 +1248,12 @@ private:
         const int me       = comm_->rank();
         const K focusStart = assignment_.boundaries[me], focusEnd = assignment_.boundaries[me + 1];
 
-        CSB_TRY(macs_.resize(numNodes, s));
-        CSB_CHECK(cudaMemsetAsync(macs_.p, 0, size_t(numNodes), s)); // irrelevant when every node is in focus
+        if (comm_->size() == 1)
+        {
+            CSB_TRY(macs_.resize(numNodes, s));
+            CSB_CHECK(cudaMemsetAsync(macs_.p, 0, size_t(numNodes), s)); // irrelevant when every node is in focus
+        }
+        else { CSB_REQUIRE(macs_.n == size_t(numNodes), "update of criteria required before updating the tree"); }
         CSB_TRY(nodeOpsAll_.resize(numNodes, s));
         int* statusDev  = reinterpret_cast<int*>(scalars_.p + 16);
         int* changesDev = statusDev + 1;
@@ -705,12 +1297,20 @@ private:
         }
 
         CSB_TRY(linkTree(fLeaves_, numFocusLeaves, fTree_, s));
+        *convergedOut = converged ? 1 : 0;
+        if (comm_->size() > 1) { CSB_TRY(letSyncWithPeers(s)); }
+        // FocusedOctree::updateTree stores the box for all property updates until the next call and recomputes the
+        // geometric centres (octree_focus_mpi.hpp:166-175)
+        std::copy(lim_, lim_ + 6, focusLim_);
+        return updateGeoCenters(s);
+    }
+
+    int updateGeoCenters(cudaStream_t s)
+    {
         CSB_TRY(geoCenters_.resize(size_t(3) * fTree_.numNodes, s));
         CSB_TRY(geoSizes_.resize(size_t(3) * fTree_.numNodes, s));
-        CSB_TRY((computeGeoCenters<K, T>(0, fTree_.prefixes.p, fTree_.numNodes, geoCenters_.p, geoSizes_.p, lim_, bnd_,
-                                         s)));
-        *convergedOut = converged ? 1 : 0;
-        return 0;
+        return computeGeoCenters<K, T>(0, fTree_.prefixes.p, fTree_.numNodes, geoCenters_.p, geoSizes_.p, focusLim_,
+                                       bnd_, s);
     }
 
     //! focus/inject.hpp:50-84: leaves <- span(sort(leaves U keys))
@@ -753,6 +1353,21 @@ private:
         CSB_TRY(upsweepSum(KeyTraits<K>::maxLevel, fTree_.levelRangeHost.data(), fTree_.childOffsets.p, fCounts_.p, s));
         return 0;
     }
+
+    // multi-rank LET state (host mirrors are what the reference keeps on the host as well)
+    double focusLim_[6]{0, 1, 0, 1, 0, 1};
+    std::vector<K> fLeavesHost_, fPrefixesHost_;
+    std::vector<std::pair<int, int>> fAssign_, peerRanges_;
+    std::vector<int> extPeers_, intPeers_, haloExtPeers_, haloIntPeers_, globDispl_, treeletOffsets_;
+    std::vector<std::vector<K>> treelets_;
+    std::vector<uint32_t> layoutHost_;
+    std::vector<std::vector<std::pair<uint32_t, uint32_t>>> outgoing_;
+    std::vector<std::pair<uint32_t, uint32_t>> incoming_;
+    DevBuf<int> treeletIdx_, idxBuf_;
+    DevBuf<uint64_t> gCountScan_;
+    DevBuf<uint32_t> peerBuf_, rangeTables_;
+    DevBuf<T> centers4_, searchCenters_, searchSizes_;
+    DevBuf<char> hostStage_;
 
     int rank_, numRanks_;
     SelfComm selfComm_;

@@ -47,6 +47,21 @@ int lowerBounds(const K* keys, size_t n, const K* targets, int numTargets, uint3
 template<class K>
 int spanSfcRangeHost(K a, K b, K* output);
 
+/* let.cu */
+template<class T>
+int minMacCenters(const T* geoCenters, const T* geoSizes, int numNodes, float invThetaEff, T* centers4, cudaStream_t s);
+template<class K, class T>
+int markMacs(const K* prefixes, const int* childOffsets, const int* parents, const T* centers4, const double* lim,
+             const int* bnd, const K* focusNodes, int numFocusNodes, uint8_t* markings, cudaStream_t s);
+template<class K>
+int rangeCount(const K* gLeaves, int numGlobalLeaves, const uint64_t* gCountScan, const K* fLeaves, const int* idx,
+               int numIdx, uint32_t* leafCounts, cudaStream_t s);
+int gatherU32(const int* idx, int n, const uint32_t* src, uint32_t* dst, cudaStream_t s);
+int scatterU32(const int* idx, int n, const uint32_t* src, uint32_t* dst, cudaStream_t s);
+template<class E>
+int gatherRanges4(const uint32_t* rangeScan, const uint32_t* rangeStart, int numRanges, uint32_t total, const E* a,
+                  const E* b, const E* c, const E* d, E* out, size_t blockElems, cudaStream_t s);
+
 /* csarray.cu */
 template<class K>
 int computeNodeCounts(const K* leaves, uint32_t* counts, int numLeaves, const K* keys, size_t n, uint32_t maxCount,

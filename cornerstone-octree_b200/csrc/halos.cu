@@ -4,6 +4,7 @@
  * traversal/boxoverlap.hpp:127-152,280-291).
  */
 #include "common.cuh"
+#include "hilbert.cuh"
 #include "cstone_b200.h"
 
 namespace csb
@@ -78,41 +79,6 @@ __global__ void __launch_bounds__(256) boundingBoxKernel(const T* __restrict__ x
 }
 
 /* ---------------------------------------------------------------- collisions */
-
-//! per-level Hilbert encode (sfc/hilbert.hpp:43-94); only used for the two corner keys of a search box
-template<class K>
-__device__ inline K iHilbertLoop(unsigned px, unsigned py, unsigned pz)
-{
-    K key = 0;
-    for (int level = KeyTraits<K>::maxLevel - 1; level >= 0; --level)
-    {
-        unsigned xi     = (px >> level) & 1u;
-        unsigned yi     = (py >> level) & 1u;
-        unsigned zi     = (pz >> level) & 1u;
-        unsigned octant = (xi << 2) | (yi << 1) | zi;
-        // mortonToHilbert = {0, 1, 3, 2, 7, 6, 4, 5} packed into one word, 3 bits per entry
-        key = (key << 3) + K((0b101100110111010011001000u >> (3 * octant)) & 7u);
-
-        px ^= -(xi & ((!yi) | zi));
-        py ^= -((xi & (yi | zi)) | (yi & (!zi)));
-        pz ^= -((xi & (!yi) & (!zi)) | (yi & (!zi)));
-
-        if (zi)
-        {
-            unsigned pt = px;
-            px          = py;
-            py          = pz;
-            pz          = pt;
-        }
-        else if (!yi)
-        {
-            unsigned pt = px;
-            px          = pz;
-            pz          = pt;
-        }
-    }
-    return key;
-}
 
 template<class K, class T>
 __device__ inline K sfc3DHilbert(T x, T y, T z, const Box<T>& box)

@@ -7,6 +7,7 @@
 #include <algorithm>
 
 #include "common.cuh"
+#include "hilbert.cuh"
 #include "cstone_b200.h"
 
 namespace csb
@@ -133,57 +134,6 @@ __global__ void upsweepSumKernel(int first, int last, const int* __restrict__ ch
 }
 
 /* ---------------------------------------------------------------- geometric centres */
-
-template<class K>
-__device__ inline void decodeHilbert(K key, unsigned& ox, unsigned& oy, unsigned& oz)
-{
-    unsigned px = 0, py = 0, pz = 0;
-    for (unsigned level = 0; level < unsigned(KeyTraits<K>::maxLevel); ++level)
-    {
-        unsigned octant = unsigned((key >> (3 * level)) & 7u);
-        unsigned xi     = octant >> 2u;
-        unsigned yi     = (octant >> 1u) & 1u;
-        unsigned zi     = octant & 1u;
-
-        if (yi ^ zi)
-        {
-            unsigned pt = px;
-            px          = pz;
-            pz          = py;
-            py          = pt;
-        }
-        else if ((!xi & !yi & !zi) || (xi & yi & zi))
-        {
-            unsigned pt = px;
-            px          = pz;
-            pz          = pt;
-        }
-
-        unsigned mask = (1u << level) - 1;
-        px ^= mask & (-(xi & (yi | zi)));
-        py ^= mask & (-((xi & ((!yi) | (!zi))) | ((!xi) & yi & zi)));
-        pz ^= mask & (-((xi & (!yi) & (!zi)) | (yi & zi)));
-
-        px |= (xi << level);
-        py |= ((xi ^ yi) << level);
-        pz |= ((yi ^ zi) << level);
-    }
-    ox = px, oy = py, oz = pz;
-}
-
-template<class K>
-__device__ inline void decodeMorton(K key, unsigned& ox, unsigned& oy, unsigned& oz)
-{
-    unsigned x = 0, y = 0, z = 0;
-    for (unsigned b = 0; b < unsigned(KeyTraits<K>::maxLevel); ++b)
-    {
-        unsigned d = unsigned((key >> (3 * b)) & 7u);
-        x |= ((d >> 2) & 1u) << b;
-        y |= ((d >> 1) & 1u) << b;
-        z |= (d & 1u) << b;
-    }
-    ox = x, oy = y, oz = z;
-}
 
 template<class K, class T>
 __global__ void geoCentersKernel(int kind, const K* __restrict__ prefixes, int numNodes, T* __restrict__ centers,

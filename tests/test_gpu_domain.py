@@ -149,4 +149,9 @@ def test_domain_rejects_unsupported_configurations():
     with pytest.raises(capi().CstoneError):
         capi().Domain(0, 1, 8, 64, 0.5, (0, 1, 0, 1, 0, 1), (0, 0, 0))  # bucketSize < bucketSizeFocus
     with pytest.raises(capi().CstoneError):
-        capi().Domain(0, 2, 64, 64, 0.5, (0, 1, 0, 1, 0, 1), (0, 0, 0))  # multi-rank: not in round 1
+        capi().Domain(2, 2, 64, 64, 0.5, (0, 1, 0, 1, 0, 1), (0, 0, 0))  # rank out of range
+    # a multi-rank domain without a communicator must refuse to sync
+    dom = capi().Domain(0, 2, 64, 64, 0.5, (0, 1, 0, 1, 0, 1), (0, 0, 0))
+    v = torch.rand(100, dtype=torch.float64, device=DEV)
+    with pytest.raises(capi().CstoneError):
+        dom.sync(v, v, v, v)

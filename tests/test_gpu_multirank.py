@@ -107,3 +107,68 @@ def test_assigned_particles_match_reference(combo, P, dist, pbc, bucket, bucket_
             assert np.array_equal(np.asarray(got[r]["box"]), w["box"]), (r, "box")
             for k in ("keys", "x", "y", "z", "h"):
                 assert np.array_equal(got[r][k], w[k][s:e]), (r, k, num_syncs)
+
+
+@pytest.mark.skipif(ref() is None, reason="needs oracle/_ref (built where /root/reference exists)")
+@pytest.mark.parametrize("combo,P,dist,pbc,bucket,bucket_focus", [
+    ("u64d", 2, "uniform", 0, 64, 8),
+    ("u64d", 2, "uniform", 1, 64, 8),
+    ("u64d", 3, "gaussian", 1, 128, 16),
+    ("u64d", 4, "uniform", 1, 64, 8),
+    ("u64f", 4, "gaussian", 0, 64, 64),
+    ("u32f", 2, "uniform", 0, 32, 8),
+    ("u64d", 8, "uniform", 0, 256, 16),
+    ("u64d", 5, "gaussian", 0, 1024, 32),
+])
+def test_full_domain_with_halos_matches_reference(combo, P, dist, pbc, bucket, bucket_focus):
+    """everything Domain::sync leaves behind on every rank is bit-identical with the reference: start/end/size, the
+    complete key and coordinate arrays including halos, the LET (leaves, counts, linked tree, halo flags), the layout"""
+    n_per = 5000
+    n = n_per * P
+    x, y, z, lim = make_particles(combo, n, dist, 5)
+    T = real_of(combo)
+    h = const_h(n, 40, T, 8.0 if dist == "gaussian" else 1.0)
+    bnd = (pbc, pbc, pbc)
+    offsets = [n_per * r for r in range(P + 1)]
+    tree_fields = ("focus_leaves", "layout", "prefixes", "child_offsets", "internal_to_leaf", "leaf_to_internal",
+                   "level_range")
+    for num_syncs in (1, 3):
+        want = ref_domain_run(combo, P, bucket, bucket_focus, 0.5, lim, bnd, x, y, z, h, offsets, num_syncs=num_syncs,
+                              ngmax=64)
+        world = capi().LocalWorld(P)
+
+        def rank_body(r):
+            c = capi()
+            comm = world.comm(r)
+            dom = c.Domain(r, P, bucket, bucket_focus, 0.5, lim, bnd, key=key_of(combo), real=combo[-1], device=DEV,
+                           comm=comm)
+            sl = slice(offsets[r], offsets[r + 1])
+            to = lambda a: torch.from_numpy(np.ascontiguousarray(a[sl])).to(DEV)  # noqa: E731
+            dom.sync(to(x), to(y), to(z), to(h))
+            for _ in range(num_syncs - 1):
+                dom.sync()
+            out = {k: dom.field(k).cpu().numpy() for k in ("keys", "x", "y", "z", "h") + tree_fields}
+            out["focus_counts"] = dom.field("focus_leaf_counts").cpu().numpy()
+            out["flags"] = dom.field("halo_flags").cpu().numpy()
+            out["parents"] = dom.field("parents").cpu().numpy()
+            out["start"], out["end"], out["size"] = dom.start_index, dom.end_index, dom.n_particles_with_halos
+            nb, nc = dom.find_neighbors(64)
+            out["nb"], out["nc"] = nb.cpu().numpy(), nc.cpu().numpy()
+            dom.close()
+            comm.close()
+            return out
+
+        got = run_ranks(P, rank_body)
+        for r in range(P):
+            w, g = want[r], got[r]
+            assert (g["start"], g["end"], g["size"]) == (w["start"], w["end"], w["keys"].size), (r, num_syncs)
+            for k in tree_fields + ("focus_counts",):
+                assert np.array_equal(g[k], w[k]), (r, k, num_syncs)
+            nn = w["prefixes"].size
+            assert np.array_equal(g["parents"][:(nn - 1) // 8], w["parents"]), (r, "parents")
+            assert np.array_equal(g["flags"], w["flags"]), (r, "halo flags", num_syncs)
+            for k in ("keys", "x", "y", "z", "h"):
+                assert np.array_equal(g[k], w[k]), (r, k, num_syncs)
+            assert np.array_equal(g["nc"], w["neighbors_count"]), (r, "neighbour counts")
+            m = np.arange(64)[None, :] < np.minimum(w["neighbors_count"], 64)[:, None]
+            assert np.array_equal(g["nb"][m], w["neighbors"].reshape(-1, 64)[m]), (r, "neighbour lists")
