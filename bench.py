@@ -7,7 +7,9 @@
 One "step" = one pass of the hot path over one batch of synthetic particles:
 SFC keys -> key+index sort -> fused x,y,z,h gather -> leaf-array update -> internal-tree link -> node centres ->
 layout -> radius neighbour search.  At N=1 the workload is BASELINE.json configs[1] (64 Mi uniform particles, 64-bit
-Hilbert keys, double).  For N>1 every rank processes its own 64 Mi shard (weak scaling).
+Hilbert keys, double).  For N>1 it is BASELINE.json configs[3]: ONE Domain over N ranks (64 Mi particles per GPU drawn
+over the whole periodic box, so the first sync moves (N-1)/N of them), global-tree ncclAllReduce, exchangeParticles,
+LET and exchangeHalos over NCCL (weak scaling).
 
 Prints ONE JSON line (rank 0).  `value` is measured with inputs resident in HBM; `e2e` goes through the same C-ABI
 calls but starts from pinned HOST buffers and ends with the results' D2H copies inside the timed region.
@@ -223,14 +225,31 @@ def run_ours(args):
     n = args.n
     g = torch.Generator(device=dev)
     g.manual_seed(42 + rank)
+    # every rank draws its particles over the WHOLE box (BASELINE configs[3]): the first sync moves (P-1)/P of them
     x, y, z = (torch.rand(n, dtype=torch.float64, device=dev, generator=g) for _ in range(3))
-    h = torch.full((n,), h_for(n, NG0), dtype=torch.float64, device=dev)
-    lim, bnd = (0, 1, 0, 1, 0, 1), (0, 0, 0)
+    h = torch.full((n,), h_for(n * world, NG0), dtype=torch.float64, device=dev)
+    lim = (0, 1, 0, 1, 0, 1)
 
-    # Round 1: every rank synchronises its own shard as an independent single-rank Domain (no exchange yet)
-    dom = capi.Domain(0, 1, BUCKET, BUCKET, 0.5, lim, bnd, key="u64", real="d", device=str(dev))
-    nb = torch.empty(n * NGMAX, dtype=torch.uint32, device=dev)
-    nc = torch.empty(n, dtype=torch.uint32, device=dev)
+    if world == 1:
+        # BASELINE configs[1]: open box, one rank
+        bnd, bucket = (0, 0, 0), BUCKET
+        comm = None
+    else:
+        # BASELINE configs[3]: periodic box, ONE multi-rank Domain over NCCL (global-tree ncclAllReduce,
+        # exchangeParticles, LET + halo exchange); bucketSize = N_total / (100 P) as in the reference's
+        # test/performance/domain_gpu.cpp, bucketSizeFocus = 64
+        bnd, bucket = (1, 1, 1), max(BUCKET, (n * world) // (100 * world))
+        uid = torch.zeros(128, dtype=torch.uint8, device=dev)
+        if rank == 0:
+            uid.copy_(torch.frombuffer(bytearray(capi.Comm.nccl_unique_id()), dtype=torch.uint8))
+        dist.broadcast(uid, 0)
+        comm = capi.Comm.nccl(rank, world, bytes(uid.cpu().numpy().tobytes()))
+    dom = capi.Domain(rank, world, bucket, BUCKET, 0.5, lim, bnd, key="u64", real="d", device=str(dev), comm=comm)
+    # the assigned share is n +- the granularity of the global leaves; halos add a shell around it
+    cap = n if world == 1 else int(n * 1.05)
+    cap_halo = n if world == 1 else int(n * 1.6)
+    nb = torch.empty(cap * NGMAX, dtype=torch.uint32, device=dev)
+    nc = torch.empty(cap, dtype=torch.uint32, device=dev)
 
     def barrier():
         if world > 1:
@@ -252,6 +271,9 @@ def run_ours(args):
         e0.record()
         dom.reset()
         dom.sync(x, y, z, h)
+        if dom.end_index - dom.start_index > cap or dom.n_particles_with_halos > cap_halo:
+            raise SystemExit(f"rank {rank}: assigned {dom.end_index - dom.start_index} / with halos "
+                             f"{dom.n_particles_with_halos} exceed the bench buffers ({cap}, {cap_halo})")
         e1.record()
         dom.find_neighbors(NGMAX, nb, nc)
         e2.record()
@@ -266,6 +288,7 @@ def run_ours(args):
     sampler = ClockSampler(local_rank)
     sampler.start()
     launches0 = capi.kernel_launch_count()
+    sent0 = comm.bytes_sent if comm is not None else 0
     e0, e1 = ev(), ev()
     barrier()
     e0.record()
@@ -275,6 +298,7 @@ def run_ours(args):
     barrier()
     clocks = sampler.stop()
     launches = capi.kernel_launch_count() - launches0
+    bytes_per_step = ((comm.bytes_sent if comm is not None else 0) - sent0) / args.steps
     ms_per_step = max_over_ranks(e0.elapsed_time(e1)) / args.steps
     value = world * n / (ms_per_step * 1e-3) / 1e6
     cold_sync = statistics.median(a.elapsed_time(b) for a, b in sync_ms)
@@ -294,9 +318,9 @@ def run_ours(args):
 
     # ---- end to end: pinned host inputs -> C ABI (H2D inside) -> results back in pinned host memory
     hx, hy, hz, hh = (t.cpu().pin_memory() for t in (x, y, z, h))
-    out_host = [torch.empty(n, dtype=torch.float64).pin_memory() for _ in range(4)]
-    keys_host = torch.empty(n, dtype=torch.uint64).pin_memory()
-    nc_host = torch.empty(n, dtype=torch.uint32).pin_memory()
+    out_host = [torch.empty(cap_halo, dtype=torch.float64).pin_memory() for _ in range(4)]
+    keys_host = torch.empty(cap_halo, dtype=torch.uint64).pin_memory()
+    nc_host = torch.empty(cap, dtype=torch.uint32).pin_memory()
 
     def e2e_step():
         dom.reset()
@@ -316,8 +340,19 @@ def run_ours(args):
     e2e_ms = max_over_ranks(e0.elapsed_time(e1)) / e2e_steps
     e2e_value = world * n / (e2e_ms * 1e-3) / 1e6
     h2d = 4 * 8 * n
-    d2h = 4 * 8 * n + 8 * n + 4 * n
+    d2h = (4 * 8 + 8) * dom.n_particles_with_halos + 4 * cap
     mean_nc = float(nc_host[: 1 << 20].to(torch.int64).sum()) / float(min(n, 1 << 20))
+    exchange = None
+    if world > 1:
+        stats = torch.tensor([bytes_per_step, dom.end_index - dom.start_index, dom.n_particles_with_halos,
+                              dom.num_focus_leaves, dom.num_global_leaves], dtype=torch.float64, device=dev)
+        allstats = [torch.zeros_like(stats) for _ in range(world)]
+        dist.all_gather(allstats, stats)
+        exchange = {"bytes_sent_per_gpu_per_step": [int(t[0].item()) for t in allstats],
+                    "assigned_per_gpu": [int(t[1].item()) for t in allstats],
+                    "with_halos_per_gpu": [int(t[2].item()) for t in allstats],
+                    "focus_leaves_per_gpu": [int(t[3].item()) for t in allstats],
+                    "global_leaves": int(allstats[0][4].item())}
 
     if rank != 0:
         return None
@@ -350,12 +385,15 @@ def run_ours(args):
         "metric": METRIC, "value": round(value, 2), "unit": UNIT, "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": round(ms_per_step, 3), "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "u64 keys / f64 coordinates", "data": "synthetic",
-        "config": {"workload": f"{n} uniform-random particles per GPU, 64-bit Hilbert, double, bucketSize="
-                               f"bucketSizeFocus={BUCKET}: first Domain::sync (cold trees, unsorted input) + "
+        "config": {"workload": f"{n} uniform-random particles per GPU, 64-bit Hilbert, double, bucketSize={bucket}, "
+                               f"bucketSizeFocus={BUCKET}, {'open' if world == 1 else 'periodic'} box: first Domain::sync (cold trees, unsorted input) + "
                                f"findNeighbors(ng~{NG0}, ngmax={NGMAX})",
                    "particles_per_gpu": n, "l2_policy": "inputs (>=512 MB per array) exceed the 126 MB L2",
-                   "parallelism": f"independent single-rank domains x{world}", "focus_leaves": num_leaves,
-                   "mean_neighbors": round(mean_nc, 2)},
+                   "parallelism": "single-rank Domain" if world == 1 else
+                   f"one Domain over {world} ranks (SFC ranges): ncclAllReduce of global node counts, "
+                   f"exchangeParticles / LET treelets / exchangeHalos over ncclSend/Recv; periodic box, "
+                   f"bucketSize={bucket}",
+                   "focus_leaves": num_leaves, "mean_neighbors": round(mean_nc, 2), "exchange": exchange},
         "e2e": {"value": round(e2e_value, 2), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "ms_per_step": round(e2e_ms, 3),
                 "note": "neighbour lists stay in HBM for the device-side consumer; keys, x,y,z,h and counts return"},

@@ -15,6 +15,7 @@
  * skipped.  Multi-rank construction is rejected loudly ("what comes next").
  */
 #include <algorithm>
+#include <chrono>
 #include <cmath>
 #include <cstring>
 #include <limits>
@@ -184,7 +185,7 @@ public:
         std::copy(lim0_, lim0_ + 6, lim_);
         const double unitBox[6] = {0, 1, 0, 1, 0, 1};
         std::copy(unitBox, unitBox + 6, focusLim_);
-        fLeavesHost_.clear();
+        fLower_.clear();
         globDispl_.clear();
         geoCenters_.n = geoSizes_.n = 0;
         macs_.n                     = 0;
@@ -262,13 +263,16 @@ public:
         const int P          = comm.size();
         const int me         = comm.rank();
 
+        phase(nullptr, s);
         /* ---- GlobalAssignment::assign (assignment.hpp:92-144) */
         CSB_TRY(updateBox(numPart, s));
+        phase("updateBox", s);
         CSB_TRY(keysDispatch(0, x_.p + start_, y_.p + start_, z_.p + start_, keys_.p + start_, numPart, lim_, bnd_, s));
         // the ordering is indexed by buffer position (primitives_acc.hpp:97-103): ordering[start + i] = start + i
         CSB_TRY(ordering_.resize(std::max<size_t>(bufSize_, 1), s));
         CSB_TRY(cs_sequence_u32(start_, numPart, ordering_.p + start_, s));
         CSB_TRY(sortPairs(keys_.p + start_, ordering_.p + start_, numPart, s));
+        phase("keys+sort", s);
 
         unsigned maxCount = 0;
         CSB_TRY(updateGlobalTree(keys_.p + start_, numPart, &maxCount, s));
@@ -281,6 +285,7 @@ public:
         }
         CSB_TRY(linkTree(gLeaves_, numGlobalLeaves_, gTree_, s));
 
+        phase("globalTree", s);
         // makeSfcAssignment on the host from the replicated leaves and counts (assignment.hpp:125-134)
         if (P == 1)
         {
@@ -316,6 +321,7 @@ public:
         const LocalIndex numPresent  = sendIdx[me + 1] - sendIdx[me];
         const LocalIndex numAssigned = P == 1 ? numPresent : assignment_.counts[me];
 
+        phase("assignment+sendRanges", s);
         /* ---- GlobalAssignment::distribute (assignment.hpp:167-203) */
         LocalIndex envStart = start_, envEnd = end_;
         if (P > 1)
@@ -334,6 +340,7 @@ public:
             BufferDescription o1e{start_, end_, exchangeSize};
             const LocalIndex recvStart = receiveStart(o1e, numRecv);
             CSB_TRY(exchangeParticles(sendIdx, recvStart, numRecv, s));
+            phase("exchangeParticles", s);
             assignedEnvelope(o1e, numRecv, &envStart, &envEnd);
             bufSize_ = exchangeSize;
             if (numRecv)
@@ -347,6 +354,7 @@ public:
         // one rank / nothing received: the envelope is already sorted, the reference's second sort is the identity
         const K* keyView = keys_.p + envStart + numSendDown;
 
+        phase("keys+sort received", s);
         /* ---- gatherArrays(x,y,z,h) to offset 0 (domain.hpp:187) */
         CSB_TRY(sx_.resize(std::max<size_t>(numAssigned, 1), s));
         CSB_TRY(sy_.resize(std::max<size_t>(numAssigned, 1), s));
@@ -359,6 +367,7 @@ public:
                                       int(sizeof(T)), s));
         }
 
+        phase("gatherArrays", s);
         /* ---- focus tree (domain.hpp:189-213) */
         if (P > 1) { return syncFocusMultiRank(keyView, numAssigned, s); }
         if (firstCall_)
@@ -369,6 +378,7 @@ public:
                 CSB_TRY(updateFocusTree(&converged, s));
                 CSB_TRY(updateFocusCounts(keyView, numAssigned, s));
             }
+            phase("focus converge", s);
         }
         {
             int converged = 0;
@@ -382,6 +392,7 @@ public:
                                  fTree_.numLeaves, layout_.p, s));
             CSB_TRY(scanTmp_.resize(scanTempBytes(size_t(fTree_.numLeaves) + 1), s));
             CSB_TRY(exclusiveScanU32(layout_.p, layout_.p, size_t(fTree_.numLeaves) + 1, scanTmp_.p, s));
+            phase("focus update+layout", s);
         }
 
         /* ---- updateLayout (domain.hpp:490-537): new buffer = [0, numAssigned) without halos; keys move to offset 0 */
@@ -429,9 +440,13 @@ public:
             {
                 int converged = 0;
                 CSB_TRY(letUpdateMinMac(invTheta, false, s));
+                phase("  minMac", s);
                 CSB_TRY(updateFocusTree(&converged, s));
+                phase("  updateFocusTree(total)", s);
                 CSB_TRY(letUpdateCounts(keyView, numAssigned, s));
+                phase("  letUpdateCounts", s);
                 CSB_TRY(allreduceSumInt(converged, &numConverged, s));
+                phase("  allreduce converged", s);
             }
         }
 
@@ -440,20 +455,26 @@ public:
         {
             int converged = 0;
             CSB_TRY(letUpdateMinMac(invTheta, true, s));
+            phase("minMac", s);
             CSB_TRY(updateFocusTree(&converged, s));
+            phase("updateFocusTree(total)", s);
             CSB_TRY(letUpdateCounts(keyView, numAssigned, s));
+            phase("letUpdateCounts", s);
             CSB_TRY(letDiscoverHalos(s));
+            phase("discoverHalos", s);
             int localFail = 0;
             CSB_TRY(letComputeLayout(&localFail, s));
             CSB_TRY(allreduceSumInt(localFail, &fail, s));
+            phase("computeLayout", s);
             CSB_TRY(haloExchangeRequests(s));
+            phase("haloExchangeRequests", s);
         } while (fail && maxRep--);
 
         /* ---- updateLayout (domain.hpp:490-537) */
         const int me              = comm.rank();
-        const LocalIndex newStart = layoutHost_[fAssign_[me].first];
-        const LocalIndex newEnd   = layoutHost_[fAssign_[me].second];
-        const LocalIndex newSize  = layoutHost_.back();
+        const LocalIndex newStart = layoutAt_[2 * me];
+        const LocalIndex newEnd   = layoutAt_[2 * me + 1];
+        const LocalIndex newSize  = layoutAt_[2 * P];
         CSB_REQUIRE(newEnd - newStart == numAssigned, "layout of the assigned leaves does not match the particles");
         CSB_TRY(keyBuf_.resize(std::max<size_t>(numAssigned, 1), s));
         CSB_CHECK(cudaMemcpyAsync(keyBuf_.p, keyView, size_t(numAssigned) * sizeof(K), cudaMemcpyDeviceToDevice, s));
@@ -475,12 +496,14 @@ public:
         end_     = newEnd;
         bufSize_ = newSize;
 
+        phase("updateLayout", s);
         /* ---- setupHalos (domain.hpp:479-488) */
         CSB_TRY(exchangeHalos(s));
         CSB_TRY(keysDispatch(0, x_.p, y_.p, z_.p, keys_.p, start_, lim_, bnd_, s));
         CSB_TRY(keysDispatch(0, x_.p + end_, y_.p + end_, z_.p + end_, keys_.p + end_, size_t(bufSize_) - end_, lim_,
                              bnd_, s));
         CSB_CHECK(cudaStreamSynchronize(s));
+        phase("exchangeHalos+halo keys", s);
         firstCall_ = false;
         return 0;
     }
@@ -495,78 +518,68 @@ public:
         return 0;
     }
 
-    //! personalised all-to-all of host byte vectors (sizes exchanged first); the role of the Isend/Probe/Recv idiom
-    //! of focus/exchange_focus.hpp and domain/exchange_keys.hpp
-    int alltoallvHost(const std::vector<std::vector<char>>& send, std::vector<std::vector<char>>& recv, cudaStream_t s)
+    /*! personalised all-to-all of DEVICE buffers (the Isend/Probe/Recv idiom of focus/exchange_focus.hpp and
+     *  domain/exchange_keys.hpp): byte counts go through the host allgather, payloads move device to device.  Message
+     *  from rank r lands at recvBuf + recvOff[r] (16-byte aligned), recvBytes[r] bytes. */
+    int alltoallvDevice(const std::vector<const void*>& sendPtr, const std::vector<size_t>& sendBytes,
+                        DevBuf<char>& recvBuf, std::vector<size_t>& recvOff, std::vector<size_t>& recvBytes,
+                        cudaStream_t s)
     {
         Comm& comm   = *comm_;
         const int P  = comm.size();
         const int me = comm.rank();
         std::vector<uint64_t> sizes(P), all(size_t(P) * P);
         for (int r = 0; r < P; ++r)
-            sizes[r] = send[r].size();
+            sizes[r] = r == me ? 0 : sendBytes[r];
         CSB_TRY(comm.allgatherHost(sizes.data(), P * sizeof(uint64_t), all.data(), s));
         auto pad = [](size_t b) { return (b + 15) & ~size_t(15); };
-        size_t sendTotal = 0, recvTotal = 0;
+        recvOff.assign(P, 0);
+        recvBytes.assign(P, 0);
+        size_t total = 0;
         for (int r = 0; r < P; ++r)
         {
-            sendTotal += pad(send[r].size());
-            recvTotal += pad(all[size_t(r) * P + me]);
+            recvBytes[r] = r == me ? 0 : all[size_t(r) * P + me];
+            recvOff[r]   = total;
+            total += pad(recvBytes[r]);
         }
-        CSB_TRY(hostStage_.resize(std::max<size_t>(sendTotal + recvTotal, 16), s));
+        CSB_TRY(recvBuf.resize(std::max<size_t>(total, 16), s));
         std::vector<CommMessage> sends, recvs;
-        size_t off = 0;
         for (int r = 0; r < P; ++r)
         {
-            if (r == me || send[r].empty()) { continue; }
-            CSB_CHECK(cudaMemcpyAsync(hostStage_.p + off, send[r].data(), send[r].size(), cudaMemcpyHostToDevice, s));
-            sends.push_back({r, hostStage_.p + off, send[r].size()});
-            off += pad(send[r].size());
+            if (sizes[r]) { sends.push_back({r, const_cast<void*>(sendPtr[r]), size_t(sizes[r])}); }
+            if (recvBytes[r]) { recvs.push_back({r, recvBuf.p + recvOff[r], recvBytes[r]}); }
         }
-        std::vector<size_t> recvOff(P, 0);
-        off = sendTotal;
-        for (int r = 0; r < P; ++r)
-        {
-            size_t b = all[size_t(r) * P + me];
-            if (r == me || b == 0) { continue; }
-            recvOff[r] = off;
-            recvs.push_back({r, hostStage_.p + off, b});
-            off += pad(b);
-        }
-        CSB_TRY(comm.exchange(sends, recvs, s));
-        recv.assign(P, {});
-        for (int r = 0; r < P; ++r)
-        {
-            size_t b = all[size_t(r) * P + me];
-            if (r == me || b == 0) { continue; }
-            recv[r].resize(b);
-            CSB_CHECK(cudaMemcpyAsync(recv[r].data(), hostStage_.p + recvOff[r], b, cudaMemcpyDeviceToHost, s));
-        }
-        CSB_CHECK(cudaStreamSynchronize(s));
-        return 0;
+        return comm.exchange(sends, recvs, s);
     }
 
-    static int nodeAbove(const std::vector<K>& leaves, K key)
-    {
-        return int(std::lower_bound(leaves.begin(), leaves.end(), key) - leaves.begin());
-    }
-    static int nodeBelow(const std::vector<K>& leaves, K key)
-    {
-        return int(std::upper_bound(leaves.begin(), leaves.end(), key) - leaves.begin()) - 1;
-    }
-
-    //! domaindecomp.hpp:129-157
-    void translateAssignment()
+    /*! translateAssignment (domaindecomp.hpp:129-157) without moving the leaves: findNodeAbove / findNodeBelow of the
+     *  P + 1 boundary keys are evaluated on the device, 2 (P + 1) integers come back.  fLower_[r] is also the
+     *  findNodeAbove(boundary r) that updateMinMac needs. */
+    int translateAssignment(cudaStream_t s)
     {
         const int P = comm_->size();
+        CSB_TRY(letInts_.resize(LET_INTS + size_t(4) * (P + 1), s, true, true));
+        int* boundsDev = letInts_.p + LET_INTS;
+        CSB_TRY(focusBounds<K>(fLeaves_.p, fTree_.numLeaves + 1, boundaryKeys_.p, P + 1, boundsDev, s));
+        std::vector<int> b(size_t(2) * (P + 1));
+        CSB_CHECK(cudaMemcpyAsync(b.data(), boundsDev, b.size() * sizeof(int), cudaMemcpyDeviceToHost, s));
+        CSB_CHECK(cudaStreamSynchronize(s));
+        fLower_.assign(b.begin(), b.begin() + P + 1);
         fAssign_.assign(P, {0, 0});
+        std::vector<int> flat(size_t(2) * P);
         for (int r = 0; r < P; ++r)
         {
-            int a = nodeAbove(fLeavesHost_, assignment_.boundaries[r]);
-            int b = nodeBelow(fLeavesHost_, assignment_.boundaries[r + 1]);
-            if (b < a) { b = a; }
-            fAssign_[r] = {a, b};
+            int lo = b[r], hi = b[P + 1 + r + 1];
+            if (hi < lo) { hi = lo; }
+            fAssign_[r]     = {lo, hi};
+            flat[2 * r]     = lo;
+            flat[2 * r + 1] = hi;
         }
+        // device copy of the focus assignment for the layout / halo request kernels
+        CSB_TRY(fAssignDev_.resize(flat.size(), s));
+        CSB_CHECK(cudaMemcpyAsync(fAssignDev_.p, flat.data(), flat.size() * sizeof(int), cudaMemcpyHostToDevice, s));
+        CSB_CHECK(cudaStreamSynchronize(s)); // flat is a host temporary
+        return 0;
     }
 
     //! domaindecomp.hpp:159-168
@@ -579,36 +592,30 @@ public:
         std::sort(peerRanges_.begin(), peerRanges_.end());
     }
 
-    int downloadFocusLeaves(cudaStream_t s)
-    {
-        fLeavesHost_.resize(size_t(fTree_.numLeaves) + 1);
-        CSB_CHECK(cudaMemcpyAsync(fLeavesHost_.data(), fLeaves_.p, fLeavesHost_.size() * sizeof(K),
-                                  cudaMemcpyDeviceToHost, s));
-        CSB_CHECK(cudaStreamSynchronize(s));
-        return 0;
-    }
-
     /*! the rank-to-rank part of FocusedOctree::updateTree (octree_focus_mpi.hpp:137-165): focus peers, treelet
-     *  exchange with rejection of keys the owner does not have (focus/exchange_focus.hpp:60-230), treelet indices */
+     *  exchange with rejection of keys the owner does not have (focus/exchange_focus.hpp:60-230), treelet indices.
+     *  Leaves, treelets and prefixes stay in HBM; the host sees O(P) scalars per call. */
     int letSyncWithPeers(cudaStream_t s)
     {
         Comm& comm   = *comm_;
         const int P  = comm.size();
         const int me = comm.rank();
-        CSB_TRY(downloadFocusLeaves(s));
-        translateAssignment();
+        CSB_TRY(translateAssignment(s));
+        int* peerFlagsDev = letInts_.p;            // [P]
+        int* errorDev     = letInts_.p + LET_ERROR; // [1]
 
         // focusPeers (focus/peer_flags.hpp:33-57) with the global offsets of the PREVIOUS call (globDispl_)
         std::vector<int> extFlags(P, 0), allFlags(size_t(P) * P);
         if (globDispl_.empty()) { globDispl_.assign(size_t(P) + 1, 0); }
+        CSB_CHECK(cudaMemsetAsync(letInts_.p, 0, LET_INTS * sizeof(int), s));
         for (int r = 0; r < P; ++r)
         {
             if (r == me) { continue; }
-            auto gs = gLeavesHost_.begin() + globDispl_[r], ge = gLeavesHost_.begin() + globDispl_[r + 1];
-            auto fs = fLeavesHost_.begin() + fAssign_[r].first, fe = fLeavesHost_.begin() + fAssign_[r].second;
-            bool isPeer = (fe - fs > ge - gs) ? true : !std::includes(gs, ge, fs, fe);
-            extFlags[r] = isPeer ? 1 : 0;
+            CSB_TRY(notIncluded<K>(fLeaves_.p + fAssign_[r].first, fAssign_[r].second - fAssign_[r].first,
+                                   gLeaves_.p + globDispl_[r], globDispl_[r + 1] - globDispl_[r], peerFlagsDev + r, s));
         }
+        CSB_CHECK(cudaMemcpyAsync(extFlags.data(), peerFlagsDev, P * sizeof(int), cudaMemcpyDeviceToHost, s));
+        CSB_CHECK(cudaStreamSynchronize(s));
         CSB_TRY(comm.allgatherHost(extFlags.data(), P * sizeof(int), allFlags.data(), s));
         extPeers_.clear();
         intPeers_.clear();
@@ -617,110 +624,109 @@ public:
             if (extFlags[r]) { extPeers_.push_back(r); }
             if (allFlags[size_t(r) * P + me]) { intPeers_.push_back(r); }
         }
-        extractPeerRanges();
 
-        // exchangeTreelets: my view of the peer's domain goes to the peer
-        std::vector<std::vector<char>> send(P), recv;
+        // exchangeTreelets: my view of the peer's domain goes to the peer, straight out of the leaf array
+        std::vector<const void*> sendPtr(P, nullptr);
+        std::vector<size_t> sendBytes(P, 0), recvOff, recvBytes;
         for (int p : extPeers_)
         {
-            const K* b = fLeavesHost_.data() + fAssign_[p].first;
-            size_t cnt = size_t(fAssign_[p].second - fAssign_[p].first) + 1;
-            send[p].assign(reinterpret_cast<const char*>(b), reinterpret_cast<const char*>(b + cnt));
+            sendPtr[p]   = fLeaves_.p + fAssign_[p].first;
+            sendBytes[p] = (size_t(fAssign_[p].second - fAssign_[p].first) + 1) * sizeof(K);
         }
-        CSB_TRY(alltoallvHost(send, recv, s));
-        treelets_.assign(P, {});
-        std::vector<std::vector<char>> rejected(P);
+        CSB_TRY(alltoallvDevice(sendPtr, sendBytes, tlRecv_, recvOff, recvBytes, s));
+
+        // checkTreelets + pruneTreelets: keys that are not leaf boundaries here are reported back and dropped
         const int numLeaves = fTree_.numLeaves;
+        std::vector<int> recvCount(P, 0), keyOff(size_t(P) + 1, 0);
+        for (int r = 0; r < P; ++r)
+        {
+            recvCount[r]  = int(recvBytes[r] / sizeof(K));
+            keyOff[r + 1] = keyOff[r] + recvCount[r];
+        }
+        const int totalRecv = keyOff[P];
+        CSB_TRY(tlValid_.resize(size_t(totalRecv) + 1, s));
+        CSB_TRY(tlKeys_.resize(std::max(totalRecv, 1), s));
+        CSB_TRY(rejKeys_.resize(std::max(totalRecv, 1), s));
+        CSB_CHECK(cudaMemsetAsync(tlValid_.p + totalRecv, 0, sizeof(uint32_t), s));
+        for (int p : intPeers_)
+            CSB_TRY(checkTreelet<K>(reinterpret_cast<const K*>(tlRecv_.p + recvOff[p]), recvCount[p], fLeaves_.p,
+                                    numLeaves, tlValid_.p + keyOff[p], s));
+        CSB_TRY(scanTmp_.resize(scanTempBytes(size_t(totalRecv) + 1), s));
+        CSB_TRY(exclusiveScanU32(tlValid_.p, tlValid_.p, size_t(totalRecv) + 1, scanTmp_.p, s));
+        // the scan runs over the concatenation of all treelets, so accepted / rejected keys of peer p start at
+        // validBefore(p) / keyOff[p] - validBefore(p)
+        std::vector<uint32_t> validAt(size_t(P) + 1, 0);
+        {
+            std::vector<int> idx(keyOff.begin(), keyOff.end());
+            int* idxDev       = letInts_.p + LET_INTS + 2 * (P + 1);
+            uint32_t* pickDev = reinterpret_cast<uint32_t*>(idxDev + (P + 1));
+            CSB_CHECK(cudaMemcpyAsync(idxDev, idx.data(), idx.size() * sizeof(int), cudaMemcpyHostToDevice, s));
+            CSB_TRY(pickU32(tlValid_.p, idxDev, P + 1, pickDev, s));
+            CSB_CHECK(cudaMemcpyAsync(validAt.data(), pickDev, validAt.size() * sizeof(uint32_t),
+                                      cudaMemcpyDeviceToHost, s));
+            CSB_CHECK(cudaStreamSynchronize(s));
+        }
+        for (int p : intPeers_)
+            CSB_TRY(splitTreelet<K>(reinterpret_cast<const K*>(tlRecv_.p + recvOff[p]), recvCount[p],
+                                    tlValid_.p + keyOff[p], tlKeys_.p + validAt[p],
+                                    rejKeys_.p + (keyOff[p] - validAt[p]), s));
+
+        // exchangeRejectedKeys: leaves of mine that the owner does not have are removed (nodeOps = 0)
+        std::vector<const void*> rejPtr(P, nullptr);
+        std::vector<size_t> rejBytes(P, 0), rejOff, rejRecvBytes;
         for (int p : intPeers_)
         {
-            const K* b = reinterpret_cast<const K*>(recv[p].data());
-            size_t cnt = recv[p].size() / sizeof(K);
-            std::vector<K>& tl = treelets_[p];
-            tl.reserve(cnt);
-            // checkTreelets + pruneTreelets: keys that are not leaf boundaries here are reported back and dropped
-            for (size_t i = 0; i < cnt; ++i)
-            {
-                K k        = b[i];
-                bool valid = true;
-                if (i + 1 < cnt && k != 0 && k != nodeRange<K>(0))
-                {
-                    int j = int(std::lower_bound(fLeavesHost_.begin(), fLeavesHost_.begin() + numLeaves, k) -
-                                fLeavesHost_.begin());
-                    valid = (k == fLeavesHost_[j]);
-                }
-                if (valid) { tl.push_back(k); }
-                else
-                {
-                    const char* kb = reinterpret_cast<const char*>(&k);
-                    rejected[p].insert(rejected[p].end(), kb, kb + sizeof(K));
-                }
-            }
+            size_t numRejected = size_t(recvCount[p]) - (validAt[p + 1] - validAt[p]);
+            rejPtr[p]          = rejKeys_.p + (keyOff[p] - validAt[p]);
+            rejBytes[p]        = numRejected * sizeof(K);
         }
-        // exchangeRejectedKeys: leaves of mine that the owner does not have are removed (nodeOps = 0)
-        std::vector<std::vector<char>> rejRecv;
-        CSB_TRY(alltoallvHost(rejected, rejRecv, s));
-        std::vector<int> nodeOps(size_t(numLeaves) + 1, 1);
+        CSB_TRY(alltoallvDevice(rejPtr, rejBytes, rejRecv_, rejOff, rejRecvBytes, s));
         bool changed = false;
         for (int p : extPeers_)
-        {
-            const K* b = reinterpret_cast<const K*>(rejRecv[p].data());
-            size_t cnt = rejRecv[p].size() / sizeof(K);
-            for (size_t i = 0; i < cnt; ++i)
-            {
-                nodeOps[nodeAbove(fLeavesHost_, b[i])] = 0;
-                changed                               = true;
-            }
-        }
+            changed = changed || rejRecvBytes[p] > 0;
         if (changed)
         {
-            std::vector<int> scan(nodeOps.size());
-            int sum = 0;
-            for (size_t i = 0; i < nodeOps.size(); ++i)
-            {
-                scan[i] = sum;
-                sum += nodeOps[i];
-            }
-            int newNumLeaves = scan[numLeaves];
-            CSB_TRY(nodeOps_.resize(scan.size(), s));
-            CSB_CHECK(cudaMemcpyAsync(nodeOps_.p, scan.data(), scan.size() * sizeof(int), cudaMemcpyHostToDevice, s));
+            CSB_TRY(nodeOps_.resize(size_t(numLeaves) + 1, s));
+            CSB_TRY(fillInt(nodeOps_.p, numLeaves + 1, 1, s));
+            for (int p : extPeers_)
+                CSB_TRY(rejectLeaves<K>(reinterpret_cast<const K*>(rejRecv_.p + rejOff[p]),
+                                        int(rejRecvBytes[p] / sizeof(K)), fLeaves_.p, numLeaves + 1, nodeOps_.p, s));
+            CSB_TRY(scanTmp_.resize(scanTempBytes(size_t(numLeaves) + 1), s));
+            CSB_TRY(exclusiveScanU32(reinterpret_cast<uint32_t*>(nodeOps_.p), reinterpret_cast<uint32_t*>(nodeOps_.p),
+                                     size_t(numLeaves) + 1, scanTmp_.p, s));
+            int newNumLeaves = 0;
+            CSB_CHECK(cudaMemcpyAsync(&newNumLeaves, nodeOps_.p + numLeaves, sizeof(int), cudaMemcpyDeviceToHost, s));
+            CSB_CHECK(cudaStreamSynchronize(s));
             CSB_TRY(fLeavesAlt_.resize(size_t(newNumLeaves) + 1, s));
             CSB_TRY(rebalanceTree<K>(fLeaves_.p, numLeaves, newNumLeaves, nodeOps_.p, fLeavesAlt_.p, s));
             CSB_CHECK(cudaStreamSynchronize(s));
             fLeaves_.swap(fLeavesAlt_);
             CSB_TRY(linkTree(fLeaves_, newNumLeaves, fTree_, s));
-            CSB_TRY(downloadFocusLeaves(s));
         }
 
-        // indexTreelets (exchange_focus.hpp:286-308) on the host copy of the prefixes
-        fPrefixesHost_.resize(fTree_.numNodes);
-        CSB_CHECK(cudaMemcpyAsync(fPrefixesHost_.data(), fTree_.prefixes.p, fPrefixesHost_.size() * sizeof(K),
-                                  cudaMemcpyDeviceToHost, s));
-        CSB_CHECK(cudaStreamSynchronize(s));
+        // indexTreelets (exchange_focus.hpp:286-308) against the level-sorted prefixes
         treeletOffsets_.assign(size_t(P) + 1, 0);
-        std::vector<int> tlIdx;
-        const std::vector<int>& lr = fTree_.levelRangeHost;
+        int numTreeletNodes = 0;
         for (int p = 0; p < P; ++p)
         {
-            treeletOffsets_[p] = int(tlIdx.size());
-            const std::vector<K>& tl = treelets_[p];
-            for (size_t i = 0; i + 1 < tl.size(); ++i)
-            {
-                K a = tl[i], b = tl[i + 1];
-                unsigned level = treeLevel<K>(b - a);
-                K prefix       = encodePlaceholderBit(a, int(3 * level));
-                auto first     = fPrefixesHost_.begin() + lr[level];
-                auto last      = fPrefixesHost_.begin() + lr[level + 1];
-                auto it        = std::lower_bound(first, last, prefix);
-                CSB_REQUIRE(it != last && *it == prefix, "treelet node of a peer does not exist in the LET");
-                tlIdx.push_back(int(it - fPrefixesHost_.begin()));
-            }
+            treeletOffsets_[p] = numTreeletNodes;
+            int numKeys        = int(validAt[p + 1] - validAt[p]);
+            if (numKeys > 1) { numTreeletNodes += numKeys - 1; }
         }
-        treeletOffsets_[P] = int(tlIdx.size());
-        CSB_TRY(treeletIdx_.resize(std::max<size_t>(tlIdx.size(), 1), s));
-        CSB_CHECK(cudaMemcpyAsync(treeletIdx_.p, tlIdx.data(), tlIdx.size() * sizeof(int), cudaMemcpyHostToDevice, s));
+        treeletOffsets_[P] = numTreeletNodes;
+        CSB_TRY(treeletIdx_.resize(std::max<size_t>(numTreeletNodes, 1), s));
+        for (int p : intPeers_)
+        {
+            int nn = treeletOffsets_[p + 1] - treeletOffsets_[p];
+            CSB_TRY(indexTreelet<K>(tlKeys_.p + validAt[p], nn, fTree_.prefixes.p, fTree_.levelRange.p,
+                                    treeletIdx_.p + treeletOffsets_[p], errorDev, s));
+        }
+        int error = 0;
+        CSB_CHECK(cudaMemcpyAsync(&error, errorDev, sizeof(int), cudaMemcpyDeviceToHost, s));
         CSB_CHECK(cudaStreamSynchronize(s));
+        CSB_REQUIRE(error == 0, "treelet node of a peer does not exist in the LET");
 
-        translateAssignment();
+        if (changed) { CSB_TRY(translateAssignment(s)); }
         extractPeerRanges();
         globDispl_ = assignment_.treeOffsets;
         return 0;
@@ -733,14 +739,14 @@ public:
         const int me       = comm_->rank();
         const int numNodes = fTree_.numNodes;
         if (geoCenters_.n != size_t(3) * numNodes) { CSB_TRY(updateGeoCenters(s)); } // first call: box (0,1)
-        if (fLeavesHost_.empty()) { CSB_TRY(downloadFocusLeaves(s)); }
+        CSB_TRY(translateAssignment(s)); // the boundaries of THIS sync in the leaves of the previous tree update
         CSB_TRY(centers4_.resize(size_t(4) * numNodes, s));
         CSB_TRY(minMacCenters<T>(geoCenters_.p, geoSizes_.p, numNodes, invTheta, centers4_.p, s));
         if (accumulate) { CSB_REQUIRE(macs_.n == size_t(numNodes), "MAC flags not correctly allocated"); }
         CSB_TRY(macs_.resize(numNodes, s, true));
         if (!accumulate) { CSB_CHECK(cudaMemsetAsync(macs_.p, 0, size_t(numNodes), s)); }
-        int fStart = nodeAbove(fLeavesHost_, assignment_.boundaries[me]);
-        int fEnd   = nodeAbove(fLeavesHost_, assignment_.boundaries[me + 1]);
+        int fStart = fLower_[me];
+        int fEnd   = fLower_[me + 1];
         fStart     = std::min(fStart, fTree_.numLeaves);
         fEnd       = std::min(fEnd, fTree_.numLeaves);
         return markMacs<K, T>(fTree_.prefixes.p, fTree_.childOffsets.p, fTree_.parents.p, centers4_.p, focusLim_, bnd_,
@@ -839,47 +845,62 @@ public:
                                macs_.p, s);
     }
 
-    //! FocusedOctree::computeLayout (octree_focus_mpi.hpp:570-582) + checkLayout (domain/layout.hpp:187-219)
+    /*! FocusedOctree::computeLayout (octree_focus_mpi.hpp:570-582) + checkLayout (domain/layout.hpp:187-219) + the
+     *  first half of Halos::exchangeRequests: the layout is scanned, checked and cut into runs of halo leaves on the
+     *  device; the host reads back 4 P + 3 integers (layout and run numbers at the rank boundaries, status flags) */
     int letComputeLayout(int* fail, cudaStream_t s)
     {
+        const int P         = comm_->size();
         const int me        = comm_->rank();
         const int numLeaves = fTree_.numLeaves;
         CSB_TRY(layoutCounts(fLeafCounts_.p, macs_.p, fTree_.leafToInternalLeaves(), numLeaves, fAssign_[me].first,
                              fAssign_[me].second, layout_.p, s));
         CSB_TRY(scanTmp_.resize(scanTempBytes(size_t(numLeaves) + 1), s));
         CSB_TRY(exclusiveScanU32(layout_.p, layout_.p, size_t(numLeaves) + 1, scanTmp_.p, s));
-        layoutHost_.resize(size_t(numLeaves) + 1);
-        CSB_CHECK(cudaMemcpyAsync(layoutHost_.data(), layout_.p, layoutHost_.size() * sizeof(uint32_t),
+
+        int* statusDev = letInts_.p + LET_STATUS;
+        CSB_CHECK(cudaMemsetAsync(statusDev, 0, 2 * sizeof(int), s));
+        CSB_TRY(runStarts_.resize(size_t(numLeaves) + 1, s));
+        CSB_TRY(haloRunStarts(layout_.p, numLeaves, fAssignDev_.p, P, me, 512u * bucketFocus_, runStarts_.p, statusDev,
+                              s));
+        CSB_TRY(exclusiveScanU32(runStarts_.p, runStarts_.p, size_t(numLeaves) + 1, scanTmp_.p, s));
+
+        // layout and run numbers at every rank's first and last leaf, plus the total
+        std::vector<int> idx(size_t(2) * P + 1);
+        for (int r = 0; r < P; ++r)
+        {
+            idx[2 * r]     = fAssign_[r].first;
+            idx[2 * r + 1] = fAssign_[r].second;
+        }
+        idx[2 * P]        = numLeaves;
+        const int nIdx    = 2 * P + 1;
+        CSB_TRY(pickBuf_.resize(size_t(3) * nIdx, s));
+        int* idxDev = reinterpret_cast<int*>(pickBuf_.p);
+        CSB_CHECK(cudaMemcpyAsync(idxDev, idx.data(), nIdx * sizeof(int), cudaMemcpyHostToDevice, s));
+        CSB_TRY(pickU32(layout_.p, idxDev, nIdx, pickBuf_.p + nIdx, s));
+        CSB_TRY(pickU32(runStarts_.p, idxDev, nIdx, pickBuf_.p + 2 * nIdx, s));
+        std::vector<uint32_t> picked(size_t(2) * nIdx);
+        int status[2];
+        CSB_CHECK(cudaMemcpyAsync(picked.data(), pickBuf_.p + nIdx, picked.size() * sizeof(uint32_t),
                                   cudaMemcpyDeviceToHost, s));
+        CSB_CHECK(cudaMemcpyAsync(status, statusDev, sizeof(status), cudaMemcpyDeviceToHost, s));
         CSB_CHECK(cudaStreamSynchronize(s));
-        int ret                  = 0;
-        const unsigned maxParts  = 512u * bucketFocus_;
-        const int ranges[2][2]   = {{0, fAssign_[me].first}, {fAssign_[me].second, numLeaves}};
-        for (auto& rg : ranges)
-            for (int i = rg[0]; i < rg[1]; ++i)
-            {
-                if (layoutHost_[i + 1] > layoutHost_[i])
-                {
-                    bool peerFound = false;
-                    for (auto pr : fAssign_)
-                        if (pr.first <= i && i < pr.second) { peerFound = true; }
-                    if (!peerFound) { ret = 1; }
-                }
-                if (layoutHost_[i + 1] - layoutHost_[i] > maxParts) { ret = -1; }
-            }
-        *fail = ret;
+        layoutAt_.assign(picked.begin(), picked.begin() + nIdx);
+        runsAt_.assign(picked.begin() + nIdx, picked.end());
+        *fail = status[1] ? -1 : (status[0] ? 1 : 0);
         return 0;
     }
 
     //! Halos::exchangeRequests (halos/halos.hpp:64-80, halos/halo_peers.hpp:20-48, domain/exchange_keys.hpp:45-99)
     int haloExchangeRequests(cudaStream_t s)
     {
-        Comm& comm   = *comm_;
-        const int P  = comm.size();
-        const int me = comm.rank();
+        Comm& comm          = *comm_;
+        const int P         = comm.size();
+        const int me        = comm.rank();
+        const int numLeaves = fTree_.numLeaves;
         std::vector<int> extFlags(P, 0), allFlags(size_t(P) * P);
         for (int r = 0; r < P; ++r)
-            if (r != me) { extFlags[r] = layoutHost_[fAssign_[r].second] > layoutHost_[fAssign_[r].first] ? 1 : 0; }
+            if (r != me) { extFlags[r] = layoutAt_[2 * r + 1] > layoutAt_[2 * r] ? 1 : 0; }
         CSB_TRY(comm.allgatherHost(extFlags.data(), P * sizeof(int), allFlags.data(), s));
         haloExtPeers_.clear();
         haloIntPeers_.clear();
@@ -888,43 +909,53 @@ public:
             if (extFlags[r]) { haloExtPeers_.push_back(r); }
             if (allFlags[size_t(r) * P + me]) { haloIntPeers_.push_back(r); }
         }
-        // request keys: extractMarkedElements (domain/layout.hpp:110-141)
-        std::vector<std::vector<char>> send(P), recv;
+        // request keys: one (first key, end key) pair per run of consecutive halo leaves in a peer's range
+        const uint32_t totalRuns = runsAt_[2 * P];
+        CSB_TRY(reqKeys_.resize(std::max<size_t>(size_t(2) * totalRuns, 1), s));
+        CSB_TRY(haloRequestKeys<K>(layout_.p, numLeaves, fAssignDev_.p, P, me, runStarts_.p, fLeaves_.p, reqKeys_.p, s));
+        std::vector<const void*> sendPtr(P, nullptr);
+        std::vector<size_t> sendBytes(P, 0), recvOff, recvBytes;
         for (int p : haloExtPeers_)
         {
-            std::vector<K> req;
-            int a = fAssign_[p].first, b = fAssign_[p].second;
-            while (a != b)
-            {
-                while (a < b && layoutHost_[a + 1] == layoutHost_[a])
-                    ++a;
-                if (a != b)
-                {
-                    req.push_back(fLeavesHost_[a]);
-                    while (a < b && layoutHost_[a + 1] > layoutHost_[a])
-                        ++a;
-                    req.push_back(fLeavesHost_[a]);
-                }
-            }
-            const char* rb = reinterpret_cast<const char*>(req.data());
-            send[p].assign(rb, rb + req.size() * sizeof(K));
+            sendPtr[p]   = reqKeys_.p + size_t(2) * runsAt_[2 * p];
+            sendBytes[p] = size_t(2) * (runsAt_[2 * p + 1] - runsAt_[2 * p]) * sizeof(K);
         }
-        CSB_TRY(alltoallvHost(send, recv, s));
-        outgoing_.assign(P, {});
+        CSB_TRY(alltoallvDevice(sendPtr, sendBytes, reqRecv_, recvOff, recvBytes, s));
+
+        // requested keys -> outgoing index ranges of my layout, as the [scan | start] tables gatherRanges reads
+        outTableOff_.assign(P, 0);
+        outNumRanges_.assign(P, 0);
+        outTotals_.assign(P, 0);
+        size_t tableSize = 0;
         for (int p : haloIntPeers_)
         {
-            const K* b = reinterpret_cast<const K*>(recv[p].data());
-            size_t cnt = recv[p].size() / sizeof(K);
-            for (size_t i = 0; i + 1 < cnt; i += 2)
-            {
-                uint32_t lo = layoutHost_[nodeAbove(fLeavesHost_, b[i])];
-                uint32_t hi = layoutHost_[nodeAbove(fLeavesHost_, b[i + 1])];
-                if (lo != hi) { outgoing_[p].push_back({lo, hi}); }
-            }
+            outNumRanges_[p] = int(recvBytes[p] / (2 * sizeof(K)));
+            outTableOff_[p]  = tableSize;
+            tableSize += size_t(2) * outNumRanges_[p] + 1;
         }
+        CSB_TRY(rangeTables_.resize(std::max<size_t>(tableSize, 1), s));
+        std::vector<uint32_t> totals(P, 0);
+        CSB_TRY(pickBuf_.resize(std::max<size_t>(size_t(3) * (2 * P + 1), size_t(P)), s, true));
+        for (int p : haloIntPeers_)
+        {
+            const int nr   = outNumRanges_[p];
+            uint32_t* scan = rangeTables_.p + outTableOff_[p]; // nr + 1 entries, then nr starts
+            CSB_TRY(haloRanges<K>(reinterpret_cast<const K*>(reqRecv_.p + recvOff[p]), nr, fLeaves_.p, numLeaves + 1,
+                                  layout_.p, scan, scan + nr + 1, s));
+            CSB_TRY(scanTmp_.resize(scanTempBytes(size_t(nr) + 1), s));
+            CSB_TRY(exclusiveScanU32(scan, scan, size_t(nr) + 1, scanTmp_.p, s));
+            CSB_CHECK(cudaMemcpyAsync(pickBuf_.p + p, scan + nr, sizeof(uint32_t), cudaMemcpyDeviceToDevice, s));
+        }
+        if (!haloIntPeers_.empty())
+        {
+            CSB_CHECK(cudaMemcpyAsync(totals.data(), pickBuf_.p, P * sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
+            CSB_CHECK(cudaStreamSynchronize(s));
+        }
+        for (int p : haloIntPeers_)
+            outTotals_[p] = totals[p];
         incoming_.assign(P, {0, 0});
         for (int p : haloExtPeers_)
-            incoming_[p] = {layoutHost_[fAssign_[p].first], layoutHost_[fAssign_[p].second]};
+            incoming_[p] = {layoutAt_[2 * p], layoutAt_[2 * p + 1]};
         return 0;
     }
 
@@ -935,39 +966,22 @@ public:
         Comm& comm  = *comm_;
         const int P = comm.size();
         auto blockElems = [](size_t c) { return (c + 3) & ~size_t(3); };
-        std::vector<uint32_t> tables; // per peer: scan[numRanges] then start[numRanges]
-        std::vector<size_t> tableOff(P, 0), totals(P, 0);
         size_t sendTotal = 0;
         for (int p = 0; p < P; ++p)
-        {
-            if (outgoing_[p].empty()) { continue; }
-            tableOff[p]   = tables.size();
-            uint32_t scan = 0;
-            for (auto& r : outgoing_[p])
-            {
-                tables.push_back(scan);
-                scan += r.second - r.first;
-            }
-            for (auto& r : outgoing_[p])
-                tables.push_back(r.first);
-            totals[p] = scan;
-            sendTotal += 4 * blockElems(scan);
-        }
-        CSB_TRY(rangeTables_.resize(std::max<size_t>(tables.size(), 1), s));
-        CSB_CHECK(cudaMemcpyAsync(rangeTables_.p, tables.data(), tables.size() * sizeof(uint32_t), cudaMemcpyHostToDevice,
-                                  s));
+            sendTotal += 4 * blockElems(outTotals_[p]);
         CSB_TRY(sendBuf_.resize(std::max<size_t>(sendTotal, 1), s));
         std::vector<CommMessage> sends, recvs;
         size_t off = 0;
         for (int p = 0; p < P; ++p)
         {
-            if (outgoing_[p].empty()) { continue; }
-            int nr    = int(outgoing_[p].size());
-            size_t be = blockElems(totals[p]);
-            CSB_TRY(gatherRanges4<T>(rangeTables_.p + tableOff[p], rangeTables_.p + tableOff[p] + nr, nr,
-                                     uint32_t(totals[p]), x_.p, y_.p, z_.p, h_.p, sendBuf_.p + off, be, s));
+            if (outTotals_[p] == 0) { continue; }
+            const int nr         = outNumRanges_[p];
+            const uint32_t* scan = rangeTables_.p + outTableOff_[p];
+            size_t be            = blockElems(outTotals_[p]);
+            CSB_TRY(gatherRanges4<T>(scan, scan + nr + 1, nr, uint32_t(outTotals_[p]), x_.p, y_.p, z_.p, h_.p,
+                                     sendBuf_.p + off, be, s));
             for (int k = 0; k < 4; ++k)
-                sends.push_back({p, sendBuf_.p + off + k * be, totals[p] * sizeof(T)});
+                sends.push_back({p, sendBuf_.p + off + k * be, outTotals_[p] * sizeof(T)});
             off += 4 * be;
         }
         T* arrays[4] = {x_.p, y_.p, z_.p, h_.p};
@@ -978,9 +992,7 @@ public:
             for (int k = 0; k < 4; ++k)
                 recvs.push_back({p, arrays[k] + incoming_[p].first, c * sizeof(T)});
         }
-        CSB_TRY(comm.exchange(sends, recvs, s));
-        CSB_CHECK(cudaStreamSynchronize(s)); // `tables` is a host temporary
-        return 0;
+        return comm.exchange(sends, recvs, s);
     }
 
     int attachComm(Comm* c) override
@@ -988,6 +1000,7 @@ public:
         CSB_REQUIRE(c != nullptr, "null communicator");
         CSB_REQUIRE(firstCall_, "the communicator must be attached before the first sync");
         CSB_REQUIRE(c->size() == numRanks_ && c->rank() == rank_, "communicator rank/size differ from the domain's");
+        CSB_REQUIRE(c->size() <= LET_ERROR, "at most 120 ranks per domain");
         comm_ = c;
         return 0;
     }
@@ -1057,6 +1070,22 @@ public:
     }
 
 private:
+    //! CSB_TRACE=1: wall time of each phase of sync (stream synchronised at the phase boundaries) on stderr
+    void phase(const char* name, cudaStream_t s)
+    {
+        if (!trace_) { return; }
+        cudaStreamSynchronize(s);
+        auto now = std::chrono::steady_clock::now();
+        if (name)
+        {
+            fprintf(stderr, "[csb rank %d] %-28s %9.3f ms\n", rank_, name,
+                    std::chrono::duration<double, std::milli>(now - lastPhase_).count());
+        }
+        lastPhase_ = now;
+    }
+    bool trace_{std::getenv("CSB_TRACE") != nullptr};
+    std::chrono::steady_clock::time_point lastPhase_;
+
     /* ------------------------------------------------------------ box: makeGlobalBox (sfc/box_mpi.hpp:51-105) +
      *                                                              limitBoxShrinking (sfc/box.hpp:398-415) */
     int updateBox(size_t numPart, cudaStream_t s)
@@ -1298,7 +1327,9 @@ private:
 
         CSB_TRY(linkTree(fLeaves_, numFocusLeaves, fTree_, s));
         *convergedOut = converged ? 1 : 0;
+        phase("    rebalance+link", s);
         if (comm_->size() > 1) { CSB_TRY(letSyncWithPeers(s)); }
+        phase("    letSyncWithPeers", s);
         // FocusedOctree::updateTree stores the box for all property updates until the next call and recomputes the
         // geometric centres (octree_focus_mpi.hpp:166-175)
         std::copy(lim_, lim_ + 6, focusLim_);
@@ -1356,18 +1387,19 @@ private:
 
     // multi-rank LET state (host mirrors are what the reference keeps on the host as well)
     double focusLim_[6]{0, 1, 0, 1, 0, 1};
-    std::vector<K> fLeavesHost_, fPrefixesHost_;
+    static constexpr int LET_INTS = 128, LET_ERROR = 120, LET_STATUS = 121; // header of letInts_: [peer flags | ...]
+    std::vector<int> fLower_;                                                // findNodeAbove of the rank boundaries
     std::vector<std::pair<int, int>> fAssign_, peerRanges_;
-    std::vector<int> extPeers_, intPeers_, haloExtPeers_, haloIntPeers_, globDispl_, treeletOffsets_;
-    std::vector<std::vector<K>> treelets_;
-    std::vector<uint32_t> layoutHost_;
-    std::vector<std::vector<std::pair<uint32_t, uint32_t>>> outgoing_;
+    std::vector<int> extPeers_, intPeers_, haloExtPeers_, haloIntPeers_, globDispl_, treeletOffsets_, outNumRanges_;
+    std::vector<uint32_t> layoutAt_, runsAt_; // layout / halo-run number at {first, last leaf of rank r}..., total
+    std::vector<size_t> outTableOff_, outTotals_;
     std::vector<std::pair<uint32_t, uint32_t>> incoming_;
-    DevBuf<int> treeletIdx_, idxBuf_;
+    DevBuf<int> treeletIdx_, idxBuf_, letInts_, fAssignDev_;
     DevBuf<uint64_t> gCountScan_;
-    DevBuf<uint32_t> peerBuf_, rangeTables_;
+    DevBuf<uint32_t> peerBuf_, rangeTables_, tlValid_, runStarts_, pickBuf_;
+    DevBuf<K> tlKeys_, rejKeys_, reqKeys_;
     DevBuf<T> centers4_, searchCenters_, searchSizes_;
-    DevBuf<char> hostStage_;
+    DevBuf<char> tlRecv_, rejRecv_, reqRecv_;
 
     int rank_, numRanks_;
     SelfComm selfComm_;

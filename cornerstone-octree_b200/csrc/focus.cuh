@@ -56,6 +56,29 @@ int markMacs(const K* prefixes, const int* childOffsets, const int* parents, con
 template<class K>
 int rangeCount(const K* gLeaves, int numGlobalLeaves, const uint64_t* gCountScan, const K* fLeaves, const int* idx,
                int numIdx, uint32_t* leafCounts, cudaStream_t s);
+template<class K>
+int focusBounds(const K* leaves, int numKeys, const K* bounds, int numBounds, int* out, cudaStream_t s);
+template<class K>
+int notIncluded(const K* fLeaves, int count, const K* gLeaves, int gCount, int* flag, cudaStream_t s);
+template<class K>
+int checkTreelet(const K* treelet, int count, const K* leaves, int numLeaves, uint32_t* valid, cudaStream_t s);
+template<class K>
+int splitTreelet(const K* keys, int count, const uint32_t* validScan, K* accepted, K* rejected, cudaStream_t s);
+template<class K>
+int rejectLeaves(const K* rejected, int count, const K* leaves, int numKeys, int* nodeOps, cudaStream_t s);
+int fillInt(int* a, int n, int v, cudaStream_t s);
+template<class K>
+int indexTreelet(const K* treelet, int numNodes, const K* prefixes, const int* levelRange, int* out, int* error,
+                 cudaStream_t s);
+int haloRunStarts(const uint32_t* layout, int numLeaves, const int* fa, int numRanks, int me, uint32_t maxParticles,
+                  uint32_t* flags, int* status, cudaStream_t s);
+template<class K>
+int haloRequestKeys(const uint32_t* layout, int numLeaves, const int* fa, int numRanks, int me,
+                    const uint32_t* startScan, const K* leaves, K* req, cudaStream_t s);
+template<class K>
+int haloRanges(const K* pairs, int numPairs, const K* leaves, int numKeys, const uint32_t* layout, uint32_t* len,
+               uint32_t* start, cudaStream_t s);
+int pickU32(const uint32_t* src, const int* idx, int n, uint32_t* dst, cudaStream_t s);
 int gatherU32(const int* idx, int n, const uint32_t* src, uint32_t* dst, cudaStream_t s);
 int scatterU32(const int* idx, int n, const uint32_t* src, uint32_t* dst, cudaStream_t s);
 template<class E>

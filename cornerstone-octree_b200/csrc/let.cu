@@ -193,7 +193,299 @@ __global__ void gatherRanges4Kernel(const uint32_t* __restrict__ rangeScan, cons
     out[3 * blockElems + k] = d[src];
 }
 
+
+/* ---- device-side pieces of FocusedOctree::updateTree's rank-to-rank part (octree_focus_mpi.hpp:137-165); the leaf and
+ *      prefix arrays never leave HBM, only O(numRanks) scalars are read back by the host ---- */
+
+//! findNodeAbove / findNodeBelow (tree/csarray.hpp:73-95) of a handful of keys: out[t] = lower_bound,
+//! out[numBounds + t] = upper_bound - 1 over the numLeaves + 1 leaf keys
+template<class K>
+__global__ void focusBoundsKernel(const K* __restrict__ leaves, int numKeys, const K* __restrict__ bounds,
+                                  int numBounds, int* __restrict__ out)
+{
+    int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= numBounds) { return; }
+    out[t]             = lowerBound(leaves, numKeys, bounds[t]);
+    out[numBounds + t] = upperBound(leaves, numKeys, bounds[t]) - 1;
+}
+
+//! !std::includes(global leaves of a rank, my focus leaves in that rank's range) (focus/peer_flags.hpp:33-57)
+template<class K>
+__global__ void notIncludedKernel(const K* __restrict__ fLeaves, int count, const K* __restrict__ gLeaves, int gCount,
+                                  int* __restrict__ flag)
+{
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= count) { return; }
+    K k   = fLeaves[i];
+    int j = lowerBound(gLeaves, gCount, k);
+    if (j == gCount || gLeaves[j] != k) { *flag = 1; }
+}
+
+//! checkTreelets (focus/exchange_focus.hpp:60-115): a key of a peer's treelet is valid if it is one of my leaf keys;
+//! the last key of a treelet and the curve ends are always valid
+template<class K>
+__global__ void checkTreeletKernel(const K* __restrict__ treelet, int count, const K* __restrict__ leaves,
+                                   int numLeaves, uint32_t* __restrict__ valid)
+{
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= count) { return; }
+    K k    = treelet[i];
+    bool v = true;
+    if (i + 1 < count && k != 0 && k != nodeRange<K>(0))
+    {
+        int j = lowerBound(leaves, numLeaves, k);
+        v     = (leaves[j] == k); // leaves has numLeaves + 1 entries
+    }
+    valid[i] = v ? 1u : 0u;
+}
+
+//! pruneTreelets: stable split of the received keys into accepted (treelet) and rejected keys
+template<class K>
+__global__ void splitTreeletKernel(const K* __restrict__ keys, int count, const uint32_t* __restrict__ validScan,
+                                   K* __restrict__ accepted, K* __restrict__ rejected)
+{
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= count) { return; }
+    uint32_t pos = validScan[i] - validScan[0]; // accepted keys of this treelet before key i
+    bool v       = validScan[i + 1] != validScan[i];
+    if (v) { accepted[pos] = keys[i]; }
+    else { rejected[uint32_t(i) - pos] = keys[i]; }
+}
+
+//! leaves named by rejected keys are removed: nodeOps[findNodeAbove(key)] = 0
+template<class K>
+__global__ void rejectLeavesKernel(const K* __restrict__ rejected, int count, const K* __restrict__ leaves, int numKeys,
+                                   int* __restrict__ nodeOps)
+{
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= count) { return; }
+    nodeOps[lowerBound(leaves, numKeys, rejected[i])] = 0;
+}
+
+__global__ void fillIntKernel(int* a, int n, int v)
+{
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) { a[i] = v; }
+}
+
+//! indexTreelets (focus/exchange_focus.hpp:286-308): node index of every treelet leaf in the level-sorted prefixes
+template<class K>
+__global__ void indexTreeletKernel(const K* __restrict__ treelet, int numNodes, const K* __restrict__ prefixes,
+                                   const int* __restrict__ levelRange, int* __restrict__ out, int* __restrict__ error)
+{
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= numNodes) { return; }
+    K a = treelet[i], b = treelet[i + 1];
+    unsigned level = treeLevel<K>(b - a);
+    K prefix       = encodePlaceholderBit(a, int(3 * level));
+    int first = levelRange[level], last = levelRange[level + 1];
+    int j     = first + lowerBound(prefixes + first, last - first, prefix);
+    if (j == last || prefixes[j] != prefix) { *error = 1; }
+    out[i] = j;
+}
+
+/* ---- device-side checkLayout (domain/layout.hpp:187-219), halo request keys (extractMarkedElements,
+ *      domain/layout.hpp:110-141, per peer range) and their translation into outgoing index ranges
+ *      (halos/halos.hpp:64-80, domain/exchange_keys.hpp:45-99) ---- */
+
+//! rank r != me whose focus range [fa[2r], fa[2r+1]) holds leaf i, or -1
+__device__ inline int peerOfLeaf(const int* __restrict__ fa, int numRanks, int me, int i)
+{
+    for (int r = 0; r < numRanks; ++r)
+        if (r != me && fa[2 * r] <= i && i < fa[2 * r + 1]) { return r; }
+    return -1;
+}
+
+/*! flags[i] = 1 if leaf i starts a run of consecutive halo leaves (layout count > 0) inside a peer's range;
+ *  status[0] |= a halo leaf lies in no rank's range, status[1] |= a foreign leaf holds more than maxParticles */
+__global__ void haloRunStartKernel(const uint32_t* __restrict__ layout, int numLeaves, const int* __restrict__ fa,
+                                   int numRanks, int me, uint32_t maxParticles, uint32_t* __restrict__ flags,
+                                   int* __restrict__ status)
+{
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i > numLeaves) { return; }
+    uint32_t f = 0;
+    if (i < numLeaves && !(fa[2 * me] <= i && i < fa[2 * me + 1]))
+    {
+        uint32_t cnt = layout[i + 1] - layout[i];
+        if (cnt > 0)
+        {
+            int r = peerOfLeaf(fa, numRanks, me, i);
+            if (r < 0) { status[0] = 1; }
+            else
+            {
+                bool prevMarked = i > fa[2 * r] && layout[i] > layout[i - 1];
+                f               = prevMarked ? 0u : 1u;
+            }
+        }
+        if (cnt > maxParticles) { status[1] = 1; }
+    }
+    flags[i] = f;
+}
+
+//! request key pairs: run k (global numbering from the scan of the run starts) -> req[2k] = first key, req[2k+1] = end key
+template<class K>
+__global__ void haloRequestKeysKernel(const uint32_t* __restrict__ layout, int numLeaves, const int* __restrict__ fa,
+                                      int numRanks, int me, const uint32_t* __restrict__ startScan,
+                                      const K* __restrict__ leaves, K* __restrict__ req)
+{
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= numLeaves) { return; }
+    if (fa[2 * me] <= i && i < fa[2 * me + 1]) { return; }
+    if (layout[i + 1] == layout[i]) { return; }
+    int r = peerOfLeaf(fa, numRanks, me, i);
+    if (r < 0) { return; }
+    bool isStart = startScan[i + 1] != startScan[i];
+    if (isStart) { req[2 * size_t(startScan[i])] = leaves[i]; }
+    bool isEnd = (i + 1 == fa[2 * r + 1]) || layout[i + 2] == layout[i + 1];
+    if (isEnd) { req[2 * size_t(startScan[i + 1] - 1) + 1] = leaves[i + 1]; }
+}
+
+//! requested key pairs -> particle index ranges of my layout: start[q] = layout[nodeAbove(k0)], len[q] = extent
+template<class K>
+__global__ void haloRangesKernel(const K* __restrict__ pairs, int numPairs, const K* __restrict__ leaves, int numKeys,
+                                 const uint32_t* __restrict__ layout, uint32_t* __restrict__ len,
+                                 uint32_t* __restrict__ start)
+{
+    int q = blockIdx.x * blockDim.x + threadIdx.x;
+    if (q > numPairs) { return; }
+    if (q == numPairs)
+    {
+        len[q] = 0;
+        return;
+    }
+    uint32_t lo = layout[lowerBound(leaves, numKeys, pairs[2 * q])];
+    uint32_t hi = layout[lowerBound(leaves, numKeys, pairs[2 * q + 1])];
+    start[q]    = lo;
+    len[q]      = hi - lo;
+}
+
+__global__ void gatherU32PlainKernel(const uint32_t* __restrict__ src, const int* __restrict__ idx, int n,
+                                     uint32_t* __restrict__ dst)
+{
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) { dst[i] = src[idx[i]]; }
+}
+
 } // namespace
+
+int haloRunStarts(const uint32_t* layout, int numLeaves, const int* fa, int numRanks, int me, uint32_t maxParticles,
+                  uint32_t* flags, int* status, cudaStream_t s)
+{
+    haloRunStartKernel<<<iceil(numLeaves + 1, 256), 256, 0, s>>>(layout, numLeaves, fa, numRanks, me, maxParticles,
+                                                                 flags, status);
+    CSB_LAUNCH_CHECK();
+    return 0;
+}
+
+template<class K>
+int haloRequestKeys(const uint32_t* layout, int numLeaves, const int* fa, int numRanks, int me,
+                    const uint32_t* startScan, const K* leaves, K* req, cudaStream_t s)
+{
+    haloRequestKeysKernel<K><<<iceil(numLeaves, 256), 256, 0, s>>>(layout, numLeaves, fa, numRanks, me, startScan,
+                                                                   leaves, req);
+    CSB_LAUNCH_CHECK();
+    return 0;
+}
+
+template<class K>
+int haloRanges(const K* pairs, int numPairs, const K* leaves, int numKeys, const uint32_t* layout, uint32_t* len,
+               uint32_t* start, cudaStream_t s)
+{
+    haloRangesKernel<K><<<iceil(numPairs + 1, 256), 256, 0, s>>>(pairs, numPairs, leaves, numKeys, layout, len, start);
+    CSB_LAUNCH_CHECK();
+    return 0;
+}
+template int haloRequestKeys<uint32_t>(const uint32_t*, int, const int*, int, int, const uint32_t*, const uint32_t*,
+                                       uint32_t*, cudaStream_t);
+template int haloRequestKeys<uint64_t>(const uint32_t*, int, const int*, int, int, const uint32_t*, const uint64_t*,
+                                       uint64_t*, cudaStream_t);
+template int haloRanges<uint32_t>(const uint32_t*, int, const uint32_t*, int, const uint32_t*, uint32_t*, uint32_t*,
+                                  cudaStream_t);
+template int haloRanges<uint64_t>(const uint64_t*, int, const uint64_t*, int, const uint32_t*, uint32_t*, uint32_t*,
+                                  cudaStream_t);
+
+//! dst[i] = src[idx[i]] for a handful of indices (scalars the host needs from a device array)
+int pickU32(const uint32_t* src, const int* idx, int n, uint32_t* dst, cudaStream_t s)
+{
+    if (n <= 0) { return 0; }
+    gatherU32PlainKernel<<<iceil(n, 64), 64, 0, s>>>(src, idx, n, dst);
+    CSB_LAUNCH_CHECK();
+    return 0;
+}
+
+template<class K>
+int focusBounds(const K* leaves, int numKeys, const K* bounds, int numBounds, int* out, cudaStream_t s)
+{
+    focusBoundsKernel<K><<<iceil(numBounds, 64), 64, 0, s>>>(leaves, numKeys, bounds, numBounds, out);
+    CSB_LAUNCH_CHECK();
+    return 0;
+}
+
+template<class K>
+int notIncluded(const K* fLeaves, int count, const K* gLeaves, int gCount, int* flag, cudaStream_t s)
+{
+    if (count <= 0) { return 0; }
+    notIncludedKernel<K><<<iceil(count, 256), 256, 0, s>>>(fLeaves, count, gLeaves, gCount, flag);
+    CSB_LAUNCH_CHECK();
+    return 0;
+}
+
+template<class K>
+int checkTreelet(const K* treelet, int count, const K* leaves, int numLeaves, uint32_t* valid, cudaStream_t s)
+{
+    if (count <= 0) { return 0; }
+    checkTreeletKernel<K><<<iceil(count, 256), 256, 0, s>>>(treelet, count, leaves, numLeaves, valid);
+    CSB_LAUNCH_CHECK();
+    return 0;
+}
+
+template<class K>
+int splitTreelet(const K* keys, int count, const uint32_t* validScan, K* accepted, K* rejected, cudaStream_t s)
+{
+    if (count <= 0) { return 0; }
+    splitTreeletKernel<K><<<iceil(count, 256), 256, 0, s>>>(keys, count, validScan, accepted, rejected);
+    CSB_LAUNCH_CHECK();
+    return 0;
+}
+
+template<class K>
+int rejectLeaves(const K* rejected, int count, const K* leaves, int numKeys, int* nodeOps, cudaStream_t s)
+{
+    if (count <= 0) { return 0; }
+    rejectLeavesKernel<K><<<iceil(count, 256), 256, 0, s>>>(rejected, count, leaves, numKeys, nodeOps);
+    CSB_LAUNCH_CHECK();
+    return 0;
+}
+
+int fillInt(int* a, int n, int v, cudaStream_t s)
+{
+    if (n <= 0) { return 0; }
+    fillIntKernel<<<iceil(n, 256), 256, 0, s>>>(a, n, v);
+    CSB_LAUNCH_CHECK();
+    return 0;
+}
+
+template<class K>
+int indexTreelet(const K* treelet, int numNodes, const K* prefixes, const int* levelRange, int* out, int* error,
+                 cudaStream_t s)
+{
+    if (numNodes <= 0) { return 0; }
+    indexTreeletKernel<K><<<iceil(numNodes, 256), 256, 0, s>>>(treelet, numNodes, prefixes, levelRange, out, error);
+    CSB_LAUNCH_CHECK();
+    return 0;
+}
+
+#define CSB_INST_LET(K)                                                                                                \
+    template int focusBounds<K>(const K*, int, const K*, int, int*, cudaStream_t);                                     \
+    template int notIncluded<K>(const K*, int, const K*, int, int*, cudaStream_t);                                     \
+    template int checkTreelet<K>(const K*, int, const K*, int, uint32_t*, cudaStream_t);                               \
+    template int splitTreelet<K>(const K*, int, const uint32_t*, K*, K*, cudaStream_t);                                \
+    template int rejectLeaves<K>(const K*, int, const K*, int, int*, cudaStream_t);                                    \
+    template int indexTreelet<K>(const K*, int, const K*, const int*, int*, int*, cudaStream_t);
+CSB_INST_LET(uint32_t)
+CSB_INST_LET(uint64_t)
+#undef CSB_INST_LET
 
 template<class T>
 int minMacCenters(const T* geoCenters, const T* geoSizes, int numNodes, float invThetaEff, T* centers4, cudaStream_t s)

@@ -3,9 +3,10 @@
  *
  * Design
  *  - Target groups are LEAF-ALIGNED: every tree leaf is cut into ceil(count/32) equal groups of at most 32 consecutive
- *    particles (the role of the reference's GroupView / computeFixedGroups, traversal/groups.hpp:28-64, but aligned to
- *    leaves).  All targets of a group sit in one leaf cell, so the union of the tree cells their search spheres touch
- *    is close to what a single target touches (27 cells instead of ~85 for arbitrary 32-particle SFC slices).
+ *    particles, and consecutive SIBLING leaves with few particles are packed into one group (the role of the
+ *    reference's GroupView / computeFixedGroups, traversal/groups.hpp:28-64, but aligned to tree cells).  All targets
+ *    of a group sit in one leaf or parent cell, so the union of the tree cells their search spheres touch is close to
+ *    what a single target touches (27 cells instead of ~85 for arbitrary 32-particle SFC slices).
  *  - One warp owns one group (lanes = targets) and walks the octree ONCE for all of them with a warp-uniform, stackless
  *    depth-first traversal (child / next sibling / parent links as in traversal/traversal.hpp:26-69).  Each lane keeps
  *    the exact pruning state of the reference's per-particle walk: a bit per tree depth says whether this lane's own
@@ -38,35 +39,81 @@ __device__ inline void leafTargets(const uint32_t* __restrict__ layout, int leaf
     if (e < s) { e = s; }
 }
 
-__global__ void groupCountKernel(const uint32_t* __restrict__ layout, int numLeaves, uint32_t first, uint32_t last,
-                                 uint32_t* __restrict__ groupCounts)
+/*! Groups are built per internal node from its leaf children: consecutive sibling leaves are packed greedily into one
+ *  group while they hold at most 32 targets together (deep trees have leaves with a handful of particles; a warp per
+ *  such leaf would run mostly empty), a leaf with more than 32 targets is cut into ceil(count/32) balanced groups.
+ *  FILL = false counts the groups that start at each leaf, FILL = true writes them at the scanned offsets. */
+template<bool FILL>
+__global__ void groupBuildKernel(const int* __restrict__ childOffsets, const int* __restrict__ internalToLeaf,
+                                 const uint32_t* __restrict__ layout, int numNodes, uint32_t first, uint32_t last,
+                                 uint32_t* __restrict__ groupCounts, const uint32_t* __restrict__ groupOffsets,
+                                 uint2* __restrict__ groups)
 {
-    int leaf = blockIdx.x * blockDim.x + threadIdx.x;
-    if (leaf > numLeaves) { return; }
-    uint32_t c = 0;
-    if (leaf < numLeaves)
+    int node = blockIdx.x * blockDim.x + threadIdx.x;
+    if (node >= numNodes) { return; }
+
+    auto standalone = [&](int leaf, uint32_t s, uint32_t e)
     {
+        uint32_t c  = e - s;
+        uint32_t ng = (c + 31) / 32;
+        if (!FILL) { groupCounts[leaf] = ng; }
+        else
+        {
+            uint32_t size = (c + ng - 1) / ng; // balanced split, <= 32
+            uint32_t off  = groupOffsets[leaf];
+            for (uint32_t k = 0; k < ng; ++k)
+                groups[off + k] = make_uint2(s + k * size, min(s + (k + 1) * size, e));
+        }
+    };
+
+    const int child0 = childOffsets[node];
+    if (child0 == 0)
+    {
+        if (numNodes == 1) // the root is the only leaf
+        {
+            uint32_t s, e;
+            leafTargets(layout, 0, first, last, s, e);
+            if (e > s) { standalone(0, s, e); }
+        }
+        return;
+    }
+
+    int packLeaf       = -1;
+    uint32_t packStart = 0, packEnd = 0;
+    auto flush = [&]()
+    {
+        if (packLeaf >= 0)
+        {
+            if (!FILL) { groupCounts[packLeaf] = 1; }
+            else { groups[groupOffsets[packLeaf]] = make_uint2(packStart, packEnd); }
+        }
+        packLeaf = -1;
+    };
+    for (int j = 0; j < 8; ++j)
+    {
+        if (childOffsets[child0 + j] != 0)
+        {
+            flush();
+            continue;
+        }
+        const int leaf = internalToLeaf[child0 + j];
         uint32_t s, e;
         leafTargets(layout, leaf, first, last, s, e);
-        c = (e - s + 31) / 32;
+        if (e == s) { continue; }
+        if (packLeaf >= 0 && packEnd == s && e - packStart <= 32) { packEnd = e; }
+        else
+        {
+            flush();
+            if (e - s <= 32)
+            {
+                packLeaf  = leaf;
+                packStart = s;
+                packEnd   = e;
+            }
+            else { standalone(leaf, s, e); }
+        }
     }
-    groupCounts[leaf] = c;
-}
-
-__global__ void groupFillKernel(const uint32_t* __restrict__ layout, int numLeaves, uint32_t first, uint32_t last,
-                                const uint32_t* __restrict__ groupOffsets, uint2* __restrict__ groups)
-{
-    int leaf = blockIdx.x * blockDim.x + threadIdx.x;
-    if (leaf >= numLeaves) { return; }
-    uint32_t s, e;
-    leafTargets(layout, leaf, first, last, s, e);
-    uint32_t c = e - s;
-    if (c == 0) { return; }
-    uint32_t ng   = (c + 31) / 32;
-    uint32_t size = (c + ng - 1) / ng; // balanced split, <= 32
-    uint32_t off  = groupOffsets[leaf];
-    for (uint32_t k = 0; k < ng; ++k)
-        groups[off + k] = make_uint2(s + k * size, min(s + (k + 1) * size, e));
+    flush();
 }
 
 /* ---------------------------------------------------------------- traversal */
@@ -506,10 +553,14 @@ int findNeighbors(const T* x, const T* y, const T* z, const T* h, uint32_t first
     CSB_SCRATCH(groups, uint2*, s, SCRATCH_B, maxGroups * sizeof(uint2));
     CSB_SCRATCH(scanTmp, void*, s, SCRATCH_C, scanTempBytes(size_t(numLeaves) + 1));
 
-    groupCountKernel<<<iceil(numLeaves + 1, 256), 256, 0, s>>>(layout, numLeaves, first, last, groupOffsets);
+    const int numNodes = numLeaves + (numLeaves - 1) / 7;
+    CSB_CHECK(cudaMemsetAsync(groupOffsets, 0, (size_t(numLeaves) + 1) * sizeof(uint32_t), s));
+    groupBuildKernel<false><<<iceil(numNodes, 256), 256, 0, s>>>(childOffsets, internalToLeaf, layout, numNodes, first,
+                                                                  last, groupOffsets, nullptr, nullptr);
     CSB_LAUNCH_CHECK();
     if (int e = exclusiveScanU32(groupOffsets, groupOffsets, size_t(numLeaves) + 1, scanTmp, s)) { return e; }
-    groupFillKernel<<<iceil(numLeaves, 256), 256, 0, s>>>(layout, numLeaves, first, last, groupOffsets, groups);
+    groupBuildKernel<true><<<iceil(numNodes, 256), 256, 0, s>>>(childOffsets, internalToLeaf, layout, numNodes, first,
+                                                                 last, nullptr, groupOffsets, groups);
     CSB_LAUNCH_CHECK();
 
     unsigned grid = iceil(maxGroups * 32, NB_THREADS);

@@ -454,7 +454,7 @@ class Domain:
         with torch.cuda.device(self.device):
             _check(lib().cs_domain_find_neighbors(C.c_void_p(self.handle), C.c_uint32(ngmax), _ptr(neighbors),
                                                   _ptr(counts), _stream()), "cs_domain_find_neighbors")
-        return neighbors.view(nloc, ngmax), counts
+        return neighbors[: nloc * ngmax].view(nloc, ngmax), counts[:nloc]
 
     def download(self, x, y, z, h, keys):
         """asynchronous device -> (pinned) host copy of the synchronised arrays"""
