@@ -416,6 +416,15 @@ def main():
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
 
     rank = int(os.environ.get("RANK", "0"))
+    # stdout carries exactly ONE line (the JSON); everything libraries print (e.g. NCCL's version banner) goes to stderr
+    sys.stdout.flush()
+    json_out = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
+
+    def emit(line):
+        json_out.write(json.dumps(line) + "\n")
+        json_out.flush()
+
     if args.impl == "reference":
         if rank != 0:
             return
@@ -431,7 +440,7 @@ def main():
                 "cpu_baseline": cb,
                 "e2e": {"value": round(cb["value"], 4), "unit": UNIT, "h2d_bytes_per_step": 0,
                         "d2h_bytes_per_step": 0}}
-        print(json.dumps(line), flush=True)
+        emit(line)
         return
 
     line = run_ours(args)
@@ -443,7 +452,7 @@ def main():
         except Exception as e:  # the checker being unavailable must not hide the GPU numbers
             line["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": os.cpu_count(), "kind": "unavailable",
                                     "sample": str(e)[:200]}
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 if __name__ == "__main__":

@@ -33,22 +33,6 @@ __global__ void minMacKernel(const T* __restrict__ geoCenters, const T* __restri
     centers4[4 * i + 3] = mac * mac;
 }
 
-//! containedIn(codeStart, codeEnd, IBox) of traversal/boxoverlap.hpp:96-117 (Hilbert keys)
-template<class K>
-__device__ inline bool iboxContainedIn(K codeStart, K codeEnd, const int* lo, const int* hi)
-{
-    constexpr int pbcRange = 1 << KeyTraits<K>::maxLevel;
-    int mn = min(min(lo[0], lo[1]), lo[2]);
-    int mx = max(max(hi[0], hi[1]), hi[2]);
-    if (mn < 0 || mx > pbcRange) { return codeStart == 0 && codeEnd == nodeRange<K>(0); }
-    K lowCode      = iHilbertLoop<K>(unsigned(lo[0]), unsigned(lo[1]), unsigned(lo[2]));
-    K highCode     = iHilbertLoop<K>(unsigned(hi[0] - 1), unsigned(hi[1] - 1), unsigned(hi[2] - 1));
-    unsigned level = unsigned(commonPrefix(lowCode, highCode)) / 3;
-    K nodeStart    = lowCode & ~(nodeRange<K>(level) - 1);
-    K nodeEnd      = nodeStart + nodeRange<K>(level);
-    return nodeStart >= codeStart && nodeEnd <= codeEnd;
-}
-
 /*! markMacs (traversal/macs.hpp:149-260): one thread per focus leaf whose extended box is not interior to the focus;
  *  marks every LET node outside the focus that fails the MAC against that leaf.  Stores race benignly (all write 1). */
 template<class K, class T>
@@ -77,9 +61,28 @@ __global__ void __launch_bounds__(128) markMacsKernel(const K* __restrict__ pref
     decodeHilbert(a, ix, iy, iz);
     int lo[3] = {int(ix & mask), int(iy & mask), int(iz & mask)};
     int hi[3] = {lo[0] + int(cubeLength), lo[1] + int(cubeLength), lo[2] + int(cubeLength)};
-    int elo[3] = {lo[0] - 1, lo[1] - 1, lo[2] - 1};
-    int ehi[3] = {hi[0] + 1, hi[1] + 1, hi[2] + 1};
-    if (iboxContainedIn<K>(focusStart, focusEnd, elo, ehi)) { return; }
+    /* containedIn(focusStart, focusEnd, leaf box extended by one unit) (traversal/boxoverlap.hpp:96-117) without
+     * encoding the two corner keys: the corners (lo - 1) and (hi) lie in the same cell of side 2^m exactly when no
+     * face of the leaf box is a multiple of 2^m, so the smallest common cell is the leaf's ancestor with
+     * m = 1 + max(ctz(lo), ctz(hi)) over the three dimensions, whose key range is a prefix of the leaf key */
+    {
+        bool contained;
+        int mn = min(min(lo[0], lo[1]), lo[2]);
+        int mx = max(max(hi[0], hi[1]), hi[2]);
+        if (mn == 0 || mx == maxCoord) { contained = focusStart == 0 && focusEnd == nodeRange<K>(0); }
+        else
+        {
+            int m = 0;
+#pragma unroll
+            for (int d = 0; d < 3; ++d)
+                m = max(m, max(__ffs(lo[d]), __ffs(hi[d]))); // __ffs = ctz + 1
+            unsigned ancLevel = unsigned(KeyTraits<K>::maxLevel - m);
+            K nodeStart       = a & ~(nodeRange<K>(ancLevel) - 1);
+            K nodeEnd         = nodeStart + nodeRange<K>(ancLevel);
+            contained         = nodeStart >= focusStart && nodeEnd <= focusEnd;
+        }
+        if (contained) { return; }
+    }
 
     T tc[3], ts[3];
 #pragma unroll

@@ -25,6 +25,7 @@ namespace
 
 constexpr int RADIX_BITS   = 8;
 constexpr int RADIX        = 1 << RADIX_BITS;
+constexpr int LB_WINDOW = 8; // predecessor tiles read per look-back round trip
 constexpr int MIN_TILE = 2048; // smallest tile of any kernel variant (sizes the look-back state)
 
 constexpr uint32_t FLAG_AGG   = 1u << 30;
@@ -45,9 +46,9 @@ constexpr size_t sortSmemBytes(int threads, int ipt)
            RADIX * 4 + 64 * 4;
 }
 
-//! kernel variant used by sortByKey: 0 = 512x12, 1 = 256x12, 2 = 256x15, 3 = 384x12 (default, fastest in
-//! tools/exp_sort.py), 4 = 256x9 (threads x keys/thread for 64-bit keys; 32-bit keys take 4/3 as many)
-int g_sortVariant = 3;
+//! kernel variant used by sortByKey: 0 = 512x12 (default, fastest in tools/exp_sort.py with the windowed look-back),
+//! 1 = 256x12, 2 = 256x15, 3 = 384x12, 4 = 256x9 (threads x keys/thread for 64-bit keys; 32-bit keys take 4/3 as many)
+int g_sortVariant = 0;
 int g_sortDebugNoLookback = 0; // experiments only: wrong results, isolates the cost of the look-back chain
 
 /* ---------------------------------------------------------------- histogram of all digit places */
@@ -55,23 +56,60 @@ int g_sortDebugNoLookback = 0; // experiments only: wrong results, isolates the 
 template<class K>
 __global__ void __launch_bounds__(512) radixHistogramKernel(const K* __restrict__ keys, size_t n, uint32_t* globalHist)
 {
-    constexpr int P = SortCfg<K>::passes;
+    constexpr int P   = SortCfg<K>::passes;
+    constexpr int VEC = 16 / sizeof(K); // keys per 128-bit load
+    constexpr int ILP = 4;              // independent loads in flight per thread
     __shared__ uint32_t hist[P * RADIX];
     for (int i = threadIdx.x; i < P * RADIX; i += blockDim.x)
         hist[i] = 0;
     __syncthreads();
 
-    size_t tid      = size_t(blockIdx.x) * blockDim.x + threadIdx.x;
-    size_t nthreads = size_t(gridDim.x) * blockDim.x;
-    for (size_t i = tid; i < n; i += nthreads)
+    auto add = [&](K key)
     {
-        K key = keys[i];
 #pragma unroll
         for (int p = 0; p < P; ++p)
-        {
             atomicAdd(&hist[p * RADIX + unsigned((key >> (RADIX_BITS * p)) & (RADIX - 1))], 1u);
+    };
+
+    const size_t tid      = size_t(blockIdx.x) * blockDim.x + threadIdx.x;
+    const size_t nthreads = size_t(gridDim.x) * blockDim.x;
+    // head up to the first 16-byte boundary, vector body, tail
+    size_t head = (reinterpret_cast<uintptr_t>(keys) & 15) ? (16 - (reinterpret_cast<uintptr_t>(keys) & 15)) / sizeof(K) : 0;
+    head        = head < n ? head : n;
+    const size_t numVec = (n - head) / VEC;
+    const uint4* vkeys  = reinterpret_cast<const uint4*>(keys + head);
+    for (size_t v = tid; v < numVec; v += nthreads * ILP)
+    {
+        uint4 q[ILP];
+#pragma unroll
+        for (int u = 0; u < ILP; ++u)
+        {
+            size_t idx = v + size_t(u) * nthreads;
+            q[u]       = idx < numVec ? vkeys[idx] : make_uint4(0, 0, 0, 0);
+        }
+#pragma unroll
+        for (int u = 0; u < ILP; ++u)
+        {
+            if (v + size_t(u) * nthreads >= numVec) { break; }
+            if constexpr (sizeof(K) == 8)
+            {
+                add(K(q[u].x) | (K(q[u].y) << 32));
+                add(K(q[u].z) | (K(q[u].w) << 32));
+            }
+            else
+            {
+                add(K(q[u].x));
+                add(K(q[u].y));
+                add(K(q[u].z));
+                add(K(q[u].w));
+            }
         }
     }
+    for (size_t i = tid; i < head; i += nthreads)
+        add(keys[i]);
+    for (size_t i = head + numVec * VEC + tid; i < n; i += nthreads)
+        add(keys[i]);
+
     __syncthreads();
     for (int i = threadIdx.x; i < P * RADIX; i += blockDim.x)
     {
@@ -103,6 +141,24 @@ __global__ void __launch_bounds__(RADIX) scanHistogramKernel(uint32_t* globalHis
 }
 
 /* ---------------------------------------------------------------- one digit pass */
+
+/*! peers &= lanes whose digit agrees with mine in bit B.  Bit set: keep voters; bit clear: keep non-voters.  Spelled in
+ *  PTX so that it stays at 4 instructions per bit (test, vote, select, and-xor); the C++ forms compile to 6. */
+template<int B>
+__device__ __forceinline__ void ballotStep(unsigned d, unsigned& peers)
+{
+    asm volatile("{\n"
+                 " .reg .pred p;\n"
+                 " .reg .b32 t, m;\n"
+                 " and.b32 t, %1, %2;\n"
+                 " setp.ne.b32 p, t, 0;\n"
+                 " vote.sync.ballot.b32 t, p, 0xffffffff;\n"
+                 " selp.b32 m, 0, 0xffffffff, p;\n"
+                 " lop3.b32 %0, %0, t, m, 0x60;\n"
+                 "}"
+                 : "+r"(peers)
+                 : "r"(d), "n"(1u << B));
+}
 
 template<class K, bool HAS_VALUES, int THREADS, int IPT, int MINB>
 __global__ void __launch_bounds__(THREADS, MINB) onesweepKernel(const K* __restrict__ keysIn,
@@ -168,13 +224,15 @@ __global__ void __launch_bounds__(THREADS, MINB) onesweepKernel(const K* __restr
         // lanes holding the same digit, from 8 ballots: MATCH.ANY runs on the ADU pipe at ~1 warp instruction per
         // 64 cycles per SM on sm_100 and was the limiter of this kernel (profiles/r1_first_path_summary.txt)
         unsigned peers = 0xffffffffu;
-#pragma unroll
-        for (int b = 0; b < RADIX_BITS; ++b)
-        {
-            const unsigned bit  = (d >> b) & 1u;
-            const unsigned vote = __ballot_sync(0xffffffffu, bit);
-            peers &= vote ^ (bit - 1u); // bit set: keep voters; bit clear: keep non-voters
-        }
+        ballotStep<0>(d, peers);
+        ballotStep<1>(d, peers);
+        ballotStep<2>(d, peers);
+        ballotStep<3>(d, peers);
+        ballotStep<4>(d, peers);
+        ballotStep<5>(d, peers);
+        ballotStep<6>(d, peers);
+        ballotStep<7>(d, peers);
+        static_assert(RADIX_BITS == 8);
         unsigned leader = __ffs(peers) - 1;
         unsigned below  = __popc(peers & ((1u << lane) - 1u));
         uint32_t pre    = 0;
@@ -212,39 +270,57 @@ __global__ void __launch_bounds__(THREADS, MINB) onesweepKernel(const K* __restr
         if (lane == 31) { scratch[warp] = incl; }
     }
     __syncthreads();
+    uint32_t binOffset = 0;
     if (tid < RADIX)
     {
         uint32_t off = 0;
         for (unsigned w = 0; w < warp; ++w)
             off += scratch[w];
-        uint32_t binOffset = off + incl - binCount; // position of this digit's run in the locally sorted tile
-
-        /* ---- decoupled look-back */
+        binOffset = off + incl - binCount; // position of this digit's run in the locally sorted tile
+        // publish this tile's digit counts (tile-major: one coalesced 1 KiB record per tile)
         volatile uint32_t* myState = tileStates + size_t(tileIdx) * RADIX + tid;
-        uint32_t exclusive         = 0;
-        if (tileIdx == 0) { *myState = FLAG_INCL | binCount; }
-        else
-        {
-            *myState = FLAG_AGG | binCount;
-            for (long long t = (long long)tileIdx - 1; t >= 0 && !debugNoLookback; --t)
-            {
-                volatile uint32_t* p = tileStates + size_t(t) * RADIX + tid;
-                uint32_t s;
-                do
-                {
-                    s = *p;
-                } while ((s & FLAG_MASK) == 0);
-                exclusive += s & VALUE_MASK;
-                if (s & FLAG_INCL) { break; }
-            }
-            *myState = FLAG_INCL | (exclusive + binCount);
-        }
-        binBase[tid] = digitBase[tid] + exclusive - binOffset;
+        *myState                   = (tileIdx == 0 ? FLAG_INCL : FLAG_AGG) | binCount;
 #pragma unroll
         for (int w = 0; w < SORT_WARPS; ++w)
             warpHist[w * RADIX + tid] += binOffset;
     }
-    __syncthreads();
+    __syncthreads(); // warpHist is final: the warps without a bin go on to stage their keys during the look-back
+    if (tid < RADIX)
+    {
+        volatile uint32_t* myState = tileStates + size_t(tileIdx) * RADIX + tid;
+        /* ---- decoupled look-back with a window of LB_WINDOW predecessors per round trip.  Consecutive tiles start
+         *      ~40 ns apart, so a walk that pays one L2 round trip per predecessor keeps finding predecessors that
+         *      have not resolved their own prefix yet (measured: 20 % of the pass); reading a window of states with
+         *      independent loads resolves the same chain in one or two round trips. */
+        uint32_t exclusive = 0;
+        if (tileIdx != 0 && !debugNoLookback)
+        {
+            long long t = (long long)tileIdx - 1;
+            bool done   = false;
+            while (!done)
+            {
+                uint32_t sv[LB_WINDOW];
+#pragma unroll
+                for (int k = 0; k < LB_WINDOW; ++k)
+                    sv[k] = (t - k >= 0) ? uint32_t(tileStates[size_t(t - k) * RADIX + tid]) : uint32_t(FLAG_INCL);
+#pragma unroll
+                for (int k = 0; k < LB_WINDOW; ++k)
+                {
+                    if (done) { break; }
+                    if ((sv[k] & FLAG_MASK) == 0)
+                    {
+                        t -= k; // not published yet: poll again from here
+                        break;
+                    }
+                    exclusive += sv[k] & VALUE_MASK;
+                    if (sv[k] & FLAG_INCL) { done = true; }
+                    else if (k == LB_WINDOW - 1) { t -= LB_WINDOW; }
+                }
+            }
+            *myState = FLAG_INCL | (exclusive + binCount);
+        }
+        binBase[tid] = digitBase[tid] + exclusive - binOffset; // read after the barrier that follows the staging
+    }
 
     /* ---- stage keys in locally sorted order */
 #pragma unroll
@@ -253,6 +329,28 @@ __global__ void __launch_bounds__(THREADS, MINB) onesweepKernel(const K* __restr
         unsigned d = unsigned((key[i] >> shift) & (RADIX - 1));
         rank[i] += wh[d];
         keysS[rank[i]] = key[i];
+    }
+    // the value loads are issued here so that their latency is covered by the key stores below (the registers of
+    // key[] are free from this point on)
+    uint32_t val[HAS_VALUES ? IPT : 1];
+    if constexpr (HAS_VALUES)
+    {
+        const uint32_t* tileVals = valsIn + tileBase;
+        if (tileCount == TILE)
+        {
+#pragma unroll
+            for (int i = 0; i < IPT; ++i)
+                val[i] = tileVals[warpOff + i * 32];
+        }
+        else
+        {
+#pragma unroll
+            for (int i = 0; i < IPT; ++i)
+            {
+                uint32_t off = warpOff + i * 32;
+                val[i]       = off < tileCount ? tileVals[off] : 0u;
+            }
+        }
     }
     __syncthreads();
 
@@ -266,22 +364,10 @@ __global__ void __launch_bounds__(THREADS, MINB) onesweepKernel(const K* __restr
 
     if constexpr (HAS_VALUES)
     {
-        const uint32_t* tileVals = valsIn + tileBase;
-        if (tileCount == TILE)
-        {
+        // padding elements of a partial tile carry the largest key, so their ranks lie beyond tileCount
 #pragma unroll
-            for (int i = 0; i < IPT; ++i)
-                valsS[rank[i]] = tileVals[warpOff + i * 32];
-        }
-        else
-        {
-#pragma unroll
-            for (int i = 0; i < IPT; ++i)
-            {
-                uint32_t off = warpOff + i * 32;
-                if (off < tileCount) { valsS[rank[i]] = tileVals[off]; }
-            }
-        }
+        for (int i = 0; i < IPT; ++i)
+            valsS[rank[i]] = val[i];
         __syncthreads();
         for (uint32_t j = tid; j < tileCount; j += SORT_THREADS)
         {
@@ -361,12 +447,14 @@ int sortByKey(K* keys, uint32_t* values, size_t n, K* keyBuf, uint32_t* valueBuf
             if (values)
             {
                 kv<<<unsigned(numTiles), THREADS, smem, stream>>>(kin, kout, vin, vout, n, p * RADIX_BITS,
-                                                                  hist + p * RADIX, st, counters + p, g_sortDebugNoLookback);
+                                                                  hist + p * RADIX, st, counters + p,
+                                                                  g_sortDebugNoLookback);
             }
             else
             {
                 ko<<<unsigned(numTiles), THREADS, smem, stream>>>(kin, kout, nullptr, nullptr, n, p * RADIX_BITS,
-                                                                  hist + p * RADIX, st, counters + p, g_sortDebugNoLookback);
+                                                                  hist + p * RADIX, st, counters + p,
+                                                                  g_sortDebugNoLookback);
             }
             countLaunch();
             std::swap(kin, kout);
