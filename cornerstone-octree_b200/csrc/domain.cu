@@ -155,6 +155,7 @@ struct DomainBase
     virtual int download(void* x, void* y, void* z, void* h, void* keys, cudaStream_t s)           = 0;
     virtual int reset(cudaStream_t s)                                                              = 0;
     virtual int attachComm(Comm* c)                                                                = 0;
+    virtual int exchangeHaloFields(void* const* arrays, const int* elemBytes, int numArrays, cudaStream_t s) = 0;
     int keyBytes{0}, realBytes{0};
 };
 
@@ -995,6 +996,58 @@ public:
         return comm.exchange(sends, recvs, s);
     }
 
+    /*! Domain::exchangeHalos (domain/domain.hpp:332-337) for client fields: every array holds nParticlesWithHalos
+     *  elements of elemBytes[k] bytes (a multiple of 4); the halo elements are overwritten with the owners' values
+     *  through the send / receive pattern recorded by the last sync (haloExchangeGpu,
+     *  halos/exchange_halos_gpu.cuh:34-119) */
+    int exchangeHaloFields(void* const* arrays, const int* elemBytes, int numArrays, cudaStream_t s) override
+    {
+        CSB_REQUIRE(!firstCall_, "exchangeHalos needs a synchronised domain");
+        Comm& comm  = *comm_;
+        const int P = comm.size();
+        if (P == 1 || numArrays == 0) { return 0; }
+        size_t bytesPerParticle = 0;
+        for (int k = 0; k < numArrays; ++k)
+        {
+            CSB_REQUIRE(arrays[k] != nullptr && elemBytes[k] > 0 && elemBytes[k] % 4 == 0,
+                        "exchangeHalos: element sizes must be positive multiples of 4 bytes");
+            bytesPerParticle += size_t(elemBytes[k]);
+        }
+        auto pad16 = [](size_t b) { return (b + 15) & ~size_t(15); };
+        size_t sendTotal = 0;
+        for (int p = 0; p < P; ++p)
+            for (int k = 0; k < numArrays; ++k)
+                sendTotal += pad16(outTotals_[p] * size_t(elemBytes[k]));
+        CSB_TRY(fieldSendBuf_.resize(std::max<size_t>(sendTotal, 16), s));
+        std::vector<CommMessage> sends, recvs;
+        size_t off = 0;
+        for (int p = 0; p < P; ++p)
+        {
+            if (outTotals_[p] == 0) { continue; }
+            const int nr         = outNumRanges_[p];
+            const uint32_t* scan = rangeTables_.p + outTableOff_[p];
+            for (int k = 0; k < numArrays; ++k)
+            {
+                size_t bytes = outTotals_[p] * size_t(elemBytes[k]);
+                CSB_TRY(gatherRangesWords(scan, scan + nr + 1, nr, uint32_t(outTotals_[p]), elemBytes[k] / 4, arrays[k],
+                                          fieldSendBuf_.p + off, s));
+                sends.push_back({p, fieldSendBuf_.p + off, bytes});
+                off += pad16(bytes);
+            }
+        }
+        for (int p = 0; p < P; ++p)
+        {
+            size_t c = size_t(incoming_[p].second - incoming_[p].first);
+            if (c == 0) { continue; }
+            for (int k = 0; k < numArrays; ++k)
+                recvs.push_back({p, static_cast<char*>(arrays[k]) + size_t(incoming_[p].first) * elemBytes[k],
+                                 c * size_t(elemBytes[k])});
+        }
+        CSB_TRY(comm.exchange(sends, recvs, s));
+        CSB_CHECK(cudaStreamSynchronize(s));
+        return 0;
+    }
+
     int attachComm(Comm* c) override
     {
         CSB_REQUIRE(c != nullptr, "null communicator");
@@ -1399,7 +1452,7 @@ private:
     DevBuf<uint32_t> peerBuf_, rangeTables_, tlValid_, runStarts_, pickBuf_;
     DevBuf<K> tlKeys_, rejKeys_, reqKeys_;
     DevBuf<T> centers4_, searchCenters_, searchSizes_;
-    DevBuf<char> tlRecv_, rejRecv_, reqRecv_;
+    DevBuf<char> tlRecv_, rejRecv_, reqRecv_, fieldSendBuf_;
 
     int rank_, numRanks_;
     SelfComm selfComm_;
@@ -1511,6 +1564,12 @@ int cs_domain_attach_comm(cs_domain_t* d, cs_comm_t* comm)
 {
     CSB_REQUIRE(d != nullptr, "null domain");
     return csb::impl(d)->attachComm(reinterpret_cast<csb::Comm*>(comm));
+}
+
+int cs_domain_exchange_halos(cs_domain_t* d, void* const* arrays, const int* elemBytes, int numArrays, void* stream)
+{
+    CSB_REQUIRE(d != nullptr, "null domain");
+    return csb::impl(d)->exchangeHaloFields(arrays, elemBytes, numArrays, cudaStream_t(stream));
 }
 
 int cs_domain_reset(cs_domain_t* d, void* stream)

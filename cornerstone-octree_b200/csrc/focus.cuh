@@ -81,6 +81,8 @@ int haloRanges(const K* pairs, int numPairs, const K* leaves, int numKeys, const
 int pickU32(const uint32_t* src, const int* idx, int n, uint32_t* dst, cudaStream_t s);
 int gatherU32(const int* idx, int n, const uint32_t* src, uint32_t* dst, cudaStream_t s);
 int scatterU32(const int* idx, int n, const uint32_t* src, uint32_t* dst, cudaStream_t s);
+int gatherRangesWords(const uint32_t* rangeScan, const uint32_t* rangeStart, int numRanges, uint32_t total, int words,
+                      const void* src, void* out, cudaStream_t s);
 template<class E>
 int gatherRanges4(const uint32_t* rangeScan, const uint32_t* rangeStart, int numRanges, uint32_t total, const E* a,
                   const E* b, const E* c, const E* d, E* out, size_t blockElems, cudaStream_t s);

@@ -287,6 +287,21 @@ __global__ void indexTreeletKernel(const K* __restrict__ treelet, int numNodes, 
     out[i] = j;
 }
 
+//! gatherRanges for one array of elements made of `words` 32-bit words (any field type of the client, as the
+//! reference reinterprets its payloads to int / util::array<float, 1..4>, halos/pack_buffers.hpp:50-54)
+__global__ void gatherRangesWordsKernel(const uint32_t* __restrict__ rangeScan, const uint32_t* __restrict__ rangeStart,
+                                        int numRanges, uint32_t total, int words, const uint32_t* __restrict__ src,
+                                        uint32_t* __restrict__ out)
+{
+    size_t t = size_t(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (t >= size_t(total) * words) { return; }
+    uint32_t k = uint32_t(t / words);
+    int w      = int(t - size_t(k) * words);
+    int r      = int(upperBound(rangeScan, numRanges, k)) - 1;
+    size_t e   = size_t(rangeStart[r]) + (k - rangeScan[r]);
+    out[t]     = src[e * words + w];
+}
+
 /* ---- device-side checkLayout (domain/layout.hpp:187-219), halo request keys (extractMarkedElements,
  *      domain/layout.hpp:110-141, per peer range) and their translation into outgoing index ranges
  *      (halos/halos.hpp:64-80, domain/exchange_keys.hpp:45-99) ---- */
@@ -534,6 +549,16 @@ int scatterU32(const int* idx, int n, const uint32_t* src, uint32_t* dst, cudaSt
 {
     if (n == 0) { return 0; }
     scatterU32Kernel<<<iceil(n, 256), 256, 0, s>>>(idx, n, src, dst);
+    CSB_LAUNCH_CHECK();
+    return 0;
+}
+
+int gatherRangesWords(const uint32_t* rangeScan, const uint32_t* rangeStart, int numRanges, uint32_t total, int words,
+                      const void* src, void* out, cudaStream_t s)
+{
+    if (total == 0) { return 0; }
+    gatherRangesWordsKernel<<<iceil(size_t(total) * words, 256), 256, 0, s>>>(
+        rangeScan, rangeStart, numRanges, total, words, static_cast<const uint32_t*>(src), static_cast<uint32_t*>(out));
     CSB_LAUNCH_CHECK();
     return 0;
 }

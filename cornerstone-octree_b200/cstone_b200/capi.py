@@ -456,6 +456,17 @@ class Domain:
                                                   _ptr(counts), _stream()), "cs_domain_find_neighbors")
         return neighbors[: nloc * ngmax].view(nloc, ngmax), counts[:nloc]
 
+    def exchange_halos(self, *fields):
+        """Domain::exchangeHalos: fields are device tensors with n_particles_with_halos rows; halo rows are filled in"""
+        n = len(fields)
+        for f in fields:
+            assert f.is_cuda and f.is_contiguous() and f.shape[0] == self.n_particles_with_halos
+        ptrs = (C.c_void_p * n)(*[f.data_ptr() for f in fields])
+        sizes = (C.c_int * n)(*[f.element_size() * (f.numel() // max(f.shape[0], 1)) for f in fields])
+        with torch.cuda.device(self.device):
+            _check(lib().cs_domain_exchange_halos(C.c_void_p(self.handle), ptrs, sizes, C.c_int(n), _stream()),
+                   "cs_domain_exchange_halos")
+
     def download(self, x, y, z, h, keys):
         """asynchronous device -> (pinned) host copy of the synchronised arrays"""
         ptrs = [C.c_void_p(t.data_ptr()) if t is not None else C.c_void_p(0) for t in (x, y, z, h, keys)]

@@ -214,7 +214,7 @@ uint64_t cs_comm_bytes_sent(const cs_comm_t* comm);
  * (hostInput = 1) memory; passing x == NULL re-synchronises the domain-owned arrays in place after the caller has
  * updated them through cs_domain_ptr.  After the call the arrays hold nParticlesWithHalos elements, SFC-sorted
  * assigned particles in [startIndex, endIndex).  Synchronises the stream.
- * Round 1: numRanks must be 1. */
+ * Multi-rank domains (numRanks > 1) need cs_domain_attach_comm before the first sync. */
 typedef struct cs_domain cs_domain_t;
 
 enum cs_domain_field
@@ -261,6 +261,11 @@ int cs_domain_find_neighbors(cs_domain_t* d, uint32_t ngmax, uint32_t* neighbors
 /* multi-rank domains (numRanks > 1): attach the communicator (same rank/size) before the first cs_domain_sync; the
  * communicator must outlive the domain */
 int cs_domain_attach_comm(cs_domain_t* d, cs_comm_t* comm);
+/* Domain::exchangeHalos(std::tie(fields...), sendBuf, recvBuf) (domain/domain.hpp:332-337): numArrays device arrays of
+ * nParticlesWithHalos elements, elemBytes[k] bytes per element (multiples of 4); the halo elements of every array are
+ * replaced by the owning ranks' values with the pattern recorded by the last cs_domain_sync.  No-op on one rank.
+ * Synchronises the stream. */
+int cs_domain_exchange_halos(cs_domain_t* d, void* const* arrays, const int* elemBytes, int numArrays, void* stream);
 /* forget all tree state so that the next cs_domain_sync behaves like the first call on a new Domain (device buffers
  * are kept; used by bench.py to time cold syncs without re-allocating) */
 int cs_domain_reset(cs_domain_t* d, void* stream);

@@ -37,8 +37,10 @@ def drift(dom, d):
     keys = dom.field("keys").view(torch.int64 if dom.kt == "u64" else torch.int32)
     box = dom.box
     d = torch.tensor(d, dtype=T, device=DEV)
+    sl = slice(dom.start_index, dom.end_index)  # only the assigned particles move, halos are refreshed by the sync
+    keys = keys[sl]
     for name, shift, lo, hi in (("x", 3, box[0], box[1]), ("y", 6, box[2], box[3]), ("z", 9, box[4], box[5])):
-        a = dom.field(name)
+        a = dom.field(name)[sl]
         digit = ((keys >> shift) & 7).to(T)
         a += d * (torch.tensor(0.5, dtype=T, device=DEV) - digit / torch.tensor(7, dtype=T, device=DEV))
         lo_t = torch.tensor(lo, dtype=T, device=DEV)

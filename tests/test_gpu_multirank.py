@@ -172,3 +172,103 @@ def test_full_domain_with_halos_matches_reference(combo, P, dist, pbc, bucket, b
             assert np.array_equal(g["nc"], w["neighbors_count"]), (r, "neighbour counts")
             m = np.arange(64)[None, :] < np.minimum(w["neighbors_count"], 64)[:, None]
             assert np.array_equal(g["nb"][m], w["neighbors"].reshape(-1, 64)[m]), (r, "neighbour lists")
+
+
+@pytest.mark.skipif(ref() is None, reason="needs oracle/_ref (built where /root/reference exists)")
+@pytest.mark.parametrize("combo,P,dist,pbc,bucket,bucket_focus", [
+    ("u64d", 2, "uniform", 1, 64, 8),
+    ("u64d", 4, "gaussian", 0, 128, 16),
+    ("u64f", 3, "uniform", 0, 64, 16),
+])
+def test_drifting_particles_match_reference(combo, P, dist, pbc, bucket, bucket_focus):
+    """particles move between syncs (the deterministic drift of oracle/ref_api.cpp), so later syncs re-assign and
+    exchange particles, the LET changes under the peers' feet (treelet keys get rejected) and halos are re-discovered;
+    after four syncs every rank still holds the reference's arrays bit for bit"""
+    from test_gpu_domain import drift
+
+    n_per = 4000
+    n = n_per * P
+    x, y, z, lim = make_particles(combo, n, dist, 11)
+    T = real_of(combo)
+    h = const_h(n, 40, T, 8.0 if dist == "gaussian" else 1.0)
+    bnd = (pbc, pbc, pbc)
+    offsets = [n_per * r for r in range(P + 1)]
+    moves = np.array([0.02, 0.05, 0.01], dtype=T)
+    num_syncs = moves.size + 1
+    want = ref_domain_run(combo, P, bucket, bucket_focus, 0.5, lim, bnd, x, y, z, h, offsets, num_syncs=num_syncs,
+                          moves=moves)
+    world = capi().LocalWorld(P)
+
+    def rank_body(r):
+        c = capi()
+        comm = world.comm(r)
+        dom = c.Domain(r, P, bucket, bucket_focus, 0.5, lim, bnd, key=key_of(combo), real=combo[-1], device=DEV,
+                       comm=comm)
+        sl = slice(offsets[r], offsets[r + 1])
+        to = lambda a: torch.from_numpy(np.ascontiguousarray(a[sl])).to(DEV)  # noqa: E731
+        dom.sync(to(x), to(y), to(z), to(h))
+        for s in range(1, num_syncs):
+            drift(dom, float(moves[s - 1]))
+            dom.sync()
+        out = {k: dom.field(k).cpu().numpy() for k in ("keys", "x", "y", "z", "h", "focus_leaves", "layout")}
+        out["start"], out["end"] = dom.start_index, dom.end_index
+        dom.close()
+        comm.close()
+        return out
+
+    got = run_ranks(P, rank_body)
+    for r in range(P):
+        w, g = want[r], got[r]
+        assert (g["start"], g["end"]) == (w["start"], w["end"]), r
+        for k in ("focus_leaves", "layout", "keys", "x", "y", "z", "h"):
+            assert np.array_equal(g[k], w[k]), (r, k)
+
+
+@pytest.mark.parametrize("combo,P,pbc", [("u64d", 2, 0), ("u64d", 4, 1), ("u32f", 3, 0)])
+def test_exchange_halos_of_client_fields(combo, P, pbc):
+    """Domain::exchangeHalos (domain.hpp:332-337): fields the client computed for its assigned particles arrive in the
+    halo rows of the ranks that need them.  The fields are functions of the coordinates, and the halo coordinates were
+    already proven identical with the reference, so the expected halo values follow from them exactly."""
+    n_per = 5000
+    n = n_per * P
+    x, y, z, lim = make_particles(combo, n, "uniform", 9)
+    T = real_of(combo)
+    tT = torch.float32 if T == np.float32 else torch.float64
+    h = const_h(n, 40, T, 1.0)
+    bnd = (pbc, pbc, pbc)
+    offsets = [n_per * r for r in range(P + 1)]
+    world = capi().LocalWorld(P)
+
+    def make_fields(dom):
+        fx, fy, fz = dom.field("x"), dom.field("y"), dom.field("z")
+        rho = fx * 2 + fy                                        # one real per particle
+        vel = torch.stack([fz, fx - fy, fy * fz], dim=1).contiguous()   # three reals per particle
+        tag = (fx * 1000).to(torch.int32)                        # one 32-bit integer per particle
+        return rho, vel, tag
+
+    def rank_body(r):
+        c = capi()
+        comm = world.comm(r)
+        dom = c.Domain(r, P, 64, 8, 0.5, lim, bnd, key=key_of(combo), real=combo[-1], device=DEV, comm=comm)
+        sl = slice(offsets[r], offsets[r + 1])
+        to = lambda a: torch.from_numpy(np.ascontiguousarray(a[sl])).to(DEV)  # noqa: E731
+        dom.sync(to(x), to(y), to(z), to(h))
+        want = make_fields(dom)
+        s, e, nh = dom.start_index, dom.end_index, dom.n_particles_with_halos
+        fields = []
+        for w in want:
+            f = torch.full_like(w, -7)
+            f[s:e] = w[s:e]
+            fields.append(f)
+        dom.exchange_halos(*fields)
+        torch.cuda.current_stream().synchronize()
+        ok = all(torch.equal(f, w) for f, w in zip(fields, want))
+        num_halos = nh - (e - s)
+        assert tT == want[0].dtype
+        dom.close()
+        comm.close()
+        return ok, num_halos
+
+    res = run_ranks(P, rank_body)
+    assert all(ok for ok, _ in res)
+    assert all(nh > 0 for _, nh in res), "the test needs halos to be meaningful"
