@@ -62,7 +62,8 @@ enum ScratchSlot : int
     SCRATCH_A = 0,
     SCRATCH_B = 1,
     SCRATCH_C = 2,
-    SCRATCH_D = 3
+    SCRATCH_D = 3,
+    SCRATCH_E = 4
 };
 #define CSB_SCRATCH(ptr, type, stream, slot, bytes)                                                                    \
     type ptr = static_cast<type>(::csb::scratch(stream, slot, bytes));                                                 \

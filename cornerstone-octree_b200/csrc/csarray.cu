@@ -17,42 +17,88 @@ namespace
 
 /* ---------------------------------------------------------------- node counts */
 
-//! lower bound of v in a[0,n) starting with a galloping probe from index 0 (counts are small, so the answer is near)
+/* counts[i] = lower_bound(keys, leaves[i+1]) - lower_bound(keys, leaves[i]) (calculateNodeCount, tree/csarray.hpp:68-79).
+ * Leaves and keys are both sorted, so a block of NC_LEAVES consecutive leaves needs one contiguous window of keys:
+ *   1. coarseBoundsKernel: lower bound of every NC_LEAVES-th leaf key by binary search over all keys (few searches,
+ *      all in flight at once);
+ *   2. nodeCountsKernel: each block streams its key window through shared memory with coalesced loads - every key is
+ *      read from HBM once - and the threads search their leaf keys there.  Very long windows (coarse trees with few
+ *      leaves) are searched in global memory instead, bounded by the window.
+ */
+constexpr int NC_LEAVES  = 128;  // leaves per block
+constexpr int NC_THREADS = 256;  // threads per block: all of them stream keys, the first NC_LEAVES search
+constexpr int NC_WINDOW  = 6144; // keys staged in shared memory per tile (48 KiB of 64-bit keys: 4 blocks per SM)
+constexpr int NC_MAX_TILES = 8; // longer windows (coarse trees) are searched in global memory
+
 template<class K>
-__device__ inline size_t gallopLowerBound(const K* __restrict__ a, size_t n, K v)
+__global__ void coarseBoundsKernel(const K* __restrict__ leaves, int numLeaves, const K* __restrict__ keys, size_t n,
+                                   int numChunks, uint64_t* __restrict__ coarse)
 {
-    size_t step = 32, lo = 0, hi = 0;
-    while (true)
-    {
-        hi = lo + step;
-        if (hi >= n)
-        {
-            hi = n;
-            break;
-        }
-        if (!(a[hi - 1] < v)) { break; }
-        lo = hi;
-        step *= 2;
-    }
-    return lo + lowerBound(a + lo, hi - lo, v);
+    int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j > numChunks) { return; }
+    int leaf  = min(j * NC_LEAVES, numLeaves);
+    coarse[j] = lowerBound(keys, n, leaves[leaf]);
 }
 
 template<class K>
-__global__ void nodeCountsKernel(const K* __restrict__ leaves,
-                                 uint32_t* __restrict__ counts,
-                                 int numLeaves,
-                                 const K* __restrict__ keys,
-                                 size_t n,
-                                 uint32_t maxCount)
+__global__ void __launch_bounds__(NC_THREADS) nodeCountsKernel(const K* __restrict__ leaves,
+                                                              uint32_t* __restrict__ counts,
+                                                              int numLeaves,
+                                                              const K* __restrict__ keys,
+                                                              const uint64_t* __restrict__ coarse,
+                                                              uint32_t maxCount)
 {
-    int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= numLeaves) { return; }
-    K start   = leaves[i];
-    K end     = leaves[i + 1];
-    size_t a  = lowerBound(keys, n, start);
-    size_t b  = a + gallopLowerBound(keys + a, n - a, end);
-    size_t c  = b - a;
-    counts[i] = uint32_t(c < size_t(maxCount) ? c : size_t(maxCount));
+    extern __shared__ __align__(16) unsigned char ncSmem[];
+    K* window = reinterpret_cast<K*>(ncSmem);
+    __shared__ uint32_t bound[NC_LEAVES + 1];
+
+    const int c0   = blockIdx.x * NC_LEAVES;
+    const int nl   = min(NC_LEAVES, numLeaves - c0);
+    const size_t A = coarse[blockIdx.x], B = coarse[blockIdx.x + 1];
+    const size_t W = B - A;
+    const int t    = threadIdx.x;
+    const K mine   = leaves[c0 + min(t, nl)]; // thread nl would look for leaves[c0 + nl], whose bound is B
+
+    if (W <= size_t(NC_WINDOW) * NC_MAX_TILES)
+    {
+        // stream the window through shared memory tile by tile; a thread's bound is the number of window keys smaller
+        // than its leaf key: whole tiles below it count fully, the tile that straddles it is searched
+        uint32_t below = 0;
+        bool open      = t < nl;
+        for (size_t base = 0; base < W; base += NC_WINDOW)
+        {
+            const uint32_t tw = uint32_t(min(size_t(NC_WINDOW), W - base));
+            const K* src      = keys + A + base;
+            if (base) { __syncthreads(); }
+            // fixed trip count, fully unrolled: all 24 loads of a thread are in flight together (a `for (i < tw)`
+            // loop issues them a few at a time and the block waits on one DRAM round trip after the other)
+#pragma unroll
+            for (int u = 0; u < NC_WINDOW / NC_THREADS; ++u)
+            {
+                uint32_t i = uint32_t(u) * NC_THREADS + t;
+                if (i < tw) { window[i] = src[i]; }
+            }
+            __syncthreads();
+            if (open)
+            {
+                if (window[tw - 1] < mine) { below += tw; }
+                else
+                {
+                    below += lowerBound(window, tw, mine);
+                    open = false;
+                }
+            }
+        }
+        if (t < nl) { bound[t] = below; }
+    }
+    else if (t < nl) { bound[t] = uint32_t(lowerBound(keys + A, W, mine)); } // W < 2^32: fewer than 2^32 keys per call
+    if (t == 0) { bound[nl] = uint32_t(W); }
+    __syncthreads();
+    if (t < nl)
+    {
+        uint32_t c     = bound[t + 1] - bound[t];
+        counts[c0 + t] = c < maxCount ? c : maxCount;
+    }
 }
 
 /* ---------------------------------------------------------------- rebalance decision */
@@ -149,7 +195,14 @@ int computeNodeCounts(const K* leaves, uint32_t* counts, int numLeaves, const K*
                       cudaStream_t s)
 {
     if (numLeaves <= 0) { return 0; }
-    nodeCountsKernel<K><<<iceil(numLeaves, 256), 256, 0, s>>>(leaves, counts, numLeaves, keys, n, maxCount);
+    CSB_REQUIRE(n < (size_t(1) << 32), "computeNodeCounts supports fewer than 2^32 keys");
+    const int numChunks = int(iceil(numLeaves, NC_LEAVES));
+    CSB_SCRATCH(coarse, uint64_t*, s, SCRATCH_E, (size_t(numChunks) + 1) * sizeof(uint64_t));
+    coarseBoundsKernel<K><<<iceil(numChunks + 1, 128), 128, 0, s>>>(leaves, numLeaves, keys, n, numChunks, coarse);
+    CSB_LAUNCH_CHECK();
+    constexpr size_t smem = size_t(NC_WINDOW) * sizeof(K);
+    CSB_CHECK(cudaFuncSetAttribute(nodeCountsKernel<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
+    nodeCountsKernel<K><<<numChunks, NC_THREADS, smem, s>>>(leaves, counts, numLeaves, keys, coarse, maxCount);
     CSB_LAUNCH_CHECK();
     return 0;
 }
