@@ -33,8 +33,12 @@ __global__ void minMacKernel(const T* __restrict__ geoCenters, const T* __restri
     centers4[4 * i + 3] = mac * mac;
 }
 
-/*! markMacs (traversal/macs.hpp:149-260): one thread per focus leaf whose extended box is not interior to the focus;
- *  marks every LET node outside the focus that fails the MAC against that leaf.  Stores race benignly (all write 1). */
+/*! markMacs (traversal/macs.hpp:149-260): marks every LET node outside the focus that fails the MAC against a focus
+ *  leaf whose extended box is not interior to the focus.  The reference walks the tree once per leaf; here a warp
+ *  owns 32 SFC-consecutive focus leaves and walks the UNION of their traversals once, warp-uniformly: bit d of a
+ *  lane's `path` says that this lane's own walk descended at depth d on the current root path, so every lane
+ *  evaluates the MAC for exactly the nodes its own traversal (traversal/traversal.hpp:26-69) visits and the marks
+ *  are the same set.  Stores race benignly (all write 1). */
 template<class K, class T>
 __global__ void __launch_bounds__(128) markMacsKernel(const K* __restrict__ prefixes,
                                                       const int* __restrict__ childOffsets,
@@ -45,14 +49,16 @@ __global__ void __launch_bounds__(128) markMacsKernel(const K* __restrict__ pref
                                                       int numFocusNodes,
                                                       uint8_t* markings)
 {
-    int tid = blockIdx.x * blockDim.x + threadIdx.x;
-    if (tid >= numFocusNodes) { return; }
+    const int tid          = blockIdx.x * blockDim.x + threadIdx.x;
     constexpr int maxCoord = 1 << KeyTraits<K>::maxLevel;
     constexpr T uL         = T(1) / maxCoord;
+    constexpr unsigned FULL = 0xffffffffu;
 
-    K focusStart = focusNodes[0];
-    K focusEnd   = focusNodes[numFocusNodes];
-    K a = focusNodes[tid], b = focusNodes[tid + 1];
+    const K focusStart = focusNodes[0];
+    const K focusEnd   = focusNodes[numFocusNodes];
+    bool active        = tid < numFocusNodes;
+    const int leaf     = active ? tid : numFocusNodes - 1;
+    const K a = focusNodes[leaf], b = focusNodes[leaf + 1];
 
     unsigned level      = treeLevel<K>(b - a);
     unsigned cubeLength = unsigned(maxCoord) >> level;
@@ -81,8 +87,9 @@ __global__ void __launch_bounds__(128) markMacsKernel(const K* __restrict__ pref
             K nodeEnd         = nodeStart + nodeRange<K>(ancLevel);
             contained         = nodeStart >= focusStart && nodeEnd <= focusEnd;
         }
-        if (contained) { return; }
+        active = active && !contained;
     }
+    if (!__any_sync(FULL, active)) { return; }
 
     T tc[3], ts[3];
 #pragma unroll
@@ -93,56 +100,124 @@ __global__ void __launch_bounds__(128) markMacsKernel(const K* __restrict__ pref
         ts[d]      = T(hi[d] - lo[d]) * halfUnit;
     }
 
-    auto check = [&](int idx)
+    /* singleTraversal (traversal/traversal.hpp:26-69) for 32 leaves at once, one SIBLING GROUP per step: lanes 0-7 fetch
+     * the 8 children of the node being expanded (one round trip to L2 instead of one per node - the walk of a leaf at
+     * the focus boundary visits thousands of nodes and its latency chain is what this kernel's run time consists of),
+     * then every lane evaluates the MAC of the children its own walk reaches from shared memory. */
+    struct Group
     {
-        K nodePrefix         = prefixes[idx];
-        unsigned sourceLevel = decodePrefixLength(nodePrefix) / 3;
-        K nodeStart          = decodePlaceholderBit(nodePrefix);
-        K nodeEnd            = nodeStart + nodeRange<K>(sourceLevel);
-        if (!(nodeStart < focusStart || nodeEnd > focusEnd)) { return false; } // fully inside the focus
-        // evaluateMacPbc (macs.hpp:118-130)
+        T cx[8], cy[8], cz[8], mac2[8];
+        int child[8];
+        uint8_t outside[8]; // node not fully inside the focus
+    };
+    __shared__ Group groups[128 / 32];
+    __shared__ uint8_t laneMask[128 / 32][KeyTraits<K>::maxLevel + 2][32];
+    const unsigned lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    Group& g            = groups[warp];
+
+    //! evaluateMacPbc (macs.hpp:118-130) of this lane's leaf box against a source centre
+    auto violates = [&](T cx, T cy, T cz, T mac2)
+    {
+        T c[3] = {cx, cy, cz};
         T dx[3];
 #pragma unroll
         for (int d = 0; d < 3; ++d)
         {
-            T v   = tc[d] - centers4[4 * idx + d];
-            v     = rabs(pbcFold(v, d, box));
+            T v = tc[d] - c[d];
+            v   = rabs(pbcFold(v, d, box));
             v -= ts[d];
             v += rabs(v);
             v *= T(0.5);
             dx[d] = v;
         }
-        T R2        = dx[0] * dx[0] + (dx[1] * dx[1] + dx[2] * dx[2]);
-        bool violates = R2 < rabs(centers4[4 * idx + 3]);
-        if (violates && !markings[idx]) { markings[idx] = 1; }
-        return violates;
+        T R2 = dx[0] * dx[0] + (dx[1] * dx[1] + dx[2] * dx[2]);
+        return R2 < rabs(mac2);
+    };
+    auto outsideFocus = [&](int idx)
+    {
+        K nodePrefix         = prefixes[idx];
+        unsigned sourceLevel = decodePrefixLength(nodePrefix) / 3;
+        K nodeStart          = decodePlaceholderBit(nodePrefix);
+        K nodeEnd            = nodeStart + nodeRange<K>(sourceLevel);
+        return nodeStart < focusStart || nodeEnd > focusEnd;
     };
 
-    // singleTraversal (traversal/traversal.hpp:26-69)
-    if (!check(0)) { return; }
-    int node = childOffsets[0];
-    if (node == 0) { return; }
-    bool backtrack = false;
-    while (node != 0)
+    //! this lane's decisions for the 8 children starting at child0 (bit c: the lane's walk marks and enters child c)
+    auto testChildren = [&](int child0, bool mine) -> unsigned
     {
-        int child    = childOffsets[node];
-        bool isLeaf  = child == 0;
-        bool descend = !backtrack && check(node);
-        if (!isLeaf && descend)
+        __syncwarp();
+        if (lane < 8)
         {
-            node      = child;
-            backtrack = false;
+            int idx         = child0 + int(lane);
+            g.cx[lane]      = centers4[4 * idx];
+            g.cy[lane]      = centers4[4 * idx + 1];
+            g.cz[lane]      = centers4[4 * idx + 2];
+            g.mac2[lane]    = centers4[4 * idx + 3];
+            g.child[lane]   = childOffsets[idx];
+            g.outside[lane] = outsideFocus(idx) ? 1 : 0;
         }
-        else if (((node - 1) & 7) < 7)
+        __syncwarp();
+        unsigned bits = 0;
+        if (mine)
         {
-            ++node;
-            backtrack = false;
+#pragma unroll
+            for (int c = 0; c < 8; ++c)
+                if (g.outside[c] && violates(g.cx[c], g.cy[c], g.cz[c], g.mac2[c])) { bits |= 1u << c; }
         }
-        else
+        return bits;
+    };
+
+    bool viol = active && outsideFocus(0) &&
+                violates(centers4[0], centers4[1], centers4[2], centers4[3]);
+    if (!__any_sync(FULL, viol)) { return; }
+    if (lane == 0 && !markings[0]) { markings[0] = 1; }
+    int base = childOffsets[0];
+    if (base == 0) { return; }
+
+    int depth     = 1;
+    unsigned lm   = testChildren(base, viol);
+    unsigned wm   = __reduce_or_sync(FULL, lm);
+    laneMask[warp][1][lane] = uint8_t(lm);
+    if (lane < 8 && ((wm >> lane) & 1u) && !markings[base + lane]) { markings[base + lane] = 1; }
+    unsigned enter = 0; // children of the current group that are internal nodes and entered by some lane
+#pragma unroll
+    for (int c = 0; c < 8; ++c)
+        if (((wm >> c) & 1u) && g.child[c] != 0) { enter |= 1u << c; }
+    while (true)
+    {
+        if (enter == 0)
         {
-            node      = parents[(node - 1) >> 3];
-            backtrack = true;
+            if (depth == 1) { return; }
+            // back to the parent's sibling group: its per-lane decisions are in shared memory, the children still
+            // to expand are recomputed from the group data (re-fetched: the walk is depth-first)
+            const int up = parents[(base - 1) >> 3];
+            --depth;
+            base = ((up - 1) & ~7) + 1;
+            lm   = laneMask[warp][depth][lane];
+            wm   = __reduce_or_sync(FULL, lm);
+            __syncwarp();
+            if (lane < 8) { g.child[lane] = childOffsets[base + int(lane)]; }
+            __syncwarp();
+            enter = 0;
+#pragma unroll
+            for (int c = 0; c < 8; ++c)
+                if (((wm >> c) & 1u) && g.child[c] != 0 && c > ((up - 1) & 7)) { enter |= 1u << c; }
+            continue;
         }
+        const int c = __ffs(int(enter)) - 1;
+        enter &= enter - 1;
+        const bool mine = (lm >> c) & 1u;
+        const int child = g.child[c];
+        ++depth;
+        base = child;
+        lm   = testChildren(child, mine);
+        wm   = __reduce_or_sync(FULL, lm);
+        laneMask[warp][depth][lane] = uint8_t(lm);
+        if (lane < 8 && ((wm >> lane) & 1u) && !markings[base + lane]) { markings[base + lane] = 1; }
+        enter = 0;
+#pragma unroll
+        for (int cc = 0; cc < 8; ++cc)
+            if (((wm >> cc) & 1u) && g.child[cc] != 0) { enter |= 1u << cc; }
     }
 }
 
