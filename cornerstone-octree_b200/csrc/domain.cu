@@ -131,6 +131,16 @@ inline int sortDispatch(uint32_t* k, uint32_t* v, size_t n, uint32_t* kb, uint32
 {
     return sortByKeyU32(k, v, n, kb, vb, t, tb, s);
 }
+inline int sortIotaDispatch(uint64_t* k, uint32_t* v, uint32_t first, size_t n, uint64_t* kb, uint32_t* vb, void* t,
+                            size_t tb, cudaStream_t s)
+{
+    return sortByKeyIotaU64(k, v, first, n, kb, vb, t, tb, s);
+}
+inline int sortIotaDispatch(uint32_t* k, uint32_t* v, uint32_t first, size_t n, uint32_t* kb, uint32_t* vb, void* t,
+                            size_t tb, cudaStream_t s)
+{
+    return sortByKeyIotaU32(k, v, first, n, kb, vb, t, tb, s);
+}
 template<class K>
 size_t sortTempBytesT(size_t n)
 {
@@ -271,8 +281,7 @@ public:
         CSB_TRY(keysDispatch(0, x_.p + start_, y_.p + start_, z_.p + start_, keys_.p + start_, numPart, lim_, bnd_, s));
         // the ordering is indexed by buffer position (primitives_acc.hpp:97-103): ordering[start + i] = start + i
         CSB_TRY(ordering_.resize(std::max<size_t>(bufSize_, 1), s));
-        CSB_TRY(cs_sequence_u32(start_, numPart, ordering_.p + start_, s));
-        CSB_TRY(sortPairs(keys_.p + start_, ordering_.p + start_, numPart, s));
+        CSB_TRY(sortPairs(keys_.p + start_, ordering_.p + start_, numPart, s, (long long)start_));
         phase("keys+sort", s);
 
         unsigned maxCount = 0;
@@ -1264,12 +1273,17 @@ private:
         return 0;
     }
 
-    int sortPairs(K* keys, uint32_t* values, size_t n, cudaStream_t s)
+    //! iotaStart >= 0: values are produced as the sorting permutation of iotaStart, iotaStart + 1, ... (sequence + sort)
+    int sortPairs(K* keys, uint32_t* values, size_t n, cudaStream_t s, long long iotaStart = -1)
     {
         CSB_TRY(keyBuf_.resize(std::max<size_t>(n, 1), s));
         CSB_TRY(valueBuf_.resize(std::max<size_t>(n, 1), s));
         size_t tb = sortTempBytesT<K>(n);
         CSB_TRY(sortTmp_.resize(tb, s));
+        if (iotaStart >= 0 && n > 0)
+        {
+            return sortIotaDispatch(keys, values, uint32_t(iotaStart), n, keyBuf_.p, valueBuf_.p, sortTmp_.p, tb, s);
+        }
         return sortDispatch(keys, values, n, keyBuf_.p, valueBuf_.p, sortTmp_.p, tb, s);
     }
 

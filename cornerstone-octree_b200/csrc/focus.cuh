@@ -112,6 +112,8 @@ size_t buildOctreeTempBytesU64(int numLeaves);
 /* sort.cu */
 int sortByKeyU64(uint64_t*, uint32_t*, size_t, uint64_t*, uint32_t*, void*, size_t, cudaStream_t);
 int sortByKeyU32(uint32_t*, uint32_t*, size_t, uint32_t*, uint32_t*, void*, size_t, cudaStream_t);
+int sortByKeyIotaU64(uint64_t*, uint32_t*, uint32_t, size_t, uint64_t*, uint32_t*, void*, size_t, cudaStream_t);
+int sortByKeyIotaU32(uint32_t*, uint32_t*, uint32_t, size_t, uint32_t*, uint32_t*, void*, size_t, cudaStream_t);
 size_t sortTempBytesU64(size_t n);
 size_t sortTempBytesU32(size_t n);
 

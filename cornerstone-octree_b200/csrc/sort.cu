@@ -170,7 +170,8 @@ __global__ void __launch_bounds__(THREADS, MINB) onesweepKernel(const K* __restr
                                                                   const uint32_t* __restrict__ digitBase,
                                                                   volatile uint32_t* tileStates,
                                                                   uint32_t* tileCounter,
-                                                                  int debugNoLookback)
+                                                                  int debugNoLookback,
+                                                                  long long iotaStart)
 {
     constexpr int TILE         = THREADS * IPT;
     constexpr int SORT_THREADS = THREADS;
@@ -336,7 +337,15 @@ __global__ void __launch_bounds__(THREADS, MINB) onesweepKernel(const K* __restr
     if constexpr (HAS_VALUES)
     {
         const uint32_t* tileVals = valsIn + tileBase;
-        if (tileCount == TILE)
+        if (iotaStart >= 0)
+        {
+            // first pass of an index sort: the values are the sequence iotaStart, iotaStart + 1, ... (the reference
+            // fills them with sequence() first, primitives_gpu.cu:56-63); generated here instead of read
+#pragma unroll
+            for (int i = 0; i < IPT; ++i)
+                val[i] = uint32_t(iotaStart) + uint32_t(tileBase) + warpOff + i * 32;
+        }
+        else if (tileCount == TILE)
         {
 #pragma unroll
             for (int i = 0; i < IPT; ++i)
@@ -390,7 +399,7 @@ size_t sortTempBytes(size_t n)
 
 template<class K>
 int sortByKey(K* keys, uint32_t* values, size_t n, K* keyBuf, uint32_t* valueBuf, void* tmp, size_t tmpBytes,
-              cudaStream_t stream)
+              cudaStream_t stream, long long iotaStart = -1)
 {
     using Cfg = SortCfg<K>;
     if (n < 2) { return 0; }
@@ -448,13 +457,13 @@ int sortByKey(K* keys, uint32_t* values, size_t n, K* keyBuf, uint32_t* valueBuf
             {
                 kv<<<unsigned(numTiles), THREADS, smem, stream>>>(kin, kout, vin, vout, n, p * RADIX_BITS,
                                                                   hist + p * RADIX, st, counters + p,
-                                                                  g_sortDebugNoLookback);
+                                                                  g_sortDebugNoLookback, p == 0 ? iotaStart : -1LL);
             }
             else
             {
                 ko<<<unsigned(numTiles), THREADS, smem, stream>>>(kin, kout, nullptr, nullptr, n, p * RADIX_BITS,
                                                                   hist + p * RADIX, st, counters + p,
-                                                                  g_sortDebugNoLookback);
+                                                                  g_sortDebugNoLookback, -1LL);
             }
             countLaunch();
             std::swap(kin, kout);
@@ -584,6 +593,21 @@ int sortByKeyU32(uint32_t* keys, uint32_t* values, size_t n, uint32_t* keyBuf, u
                  size_t tmpBytes, cudaStream_t stream)
 {
     return sortByKey<uint32_t>(keys, values, n, keyBuf, valueBuf, tmp, tmpBytes, stream);
+}
+
+//! sort keys and produce the sorting permutation of the sequence first, first + 1, ... (values need no initialisation)
+int sortByKeyIotaU64(uint64_t* keys, uint32_t* values, uint32_t first, size_t n, uint64_t* keyBuf, uint32_t* valueBuf,
+                     void* tmp, size_t tmpBytes, cudaStream_t stream)
+{
+    if (n == 1) { return cs_sequence_u32(first, 1, values, stream); }
+    return sortByKey<uint64_t>(keys, values, n, keyBuf, valueBuf, tmp, tmpBytes, stream, (long long)first);
+}
+
+int sortByKeyIotaU32(uint32_t* keys, uint32_t* values, uint32_t first, size_t n, uint32_t* keyBuf, uint32_t* valueBuf,
+                     void* tmp, size_t tmpBytes, cudaStream_t stream)
+{
+    if (n == 1) { return cs_sequence_u32(first, 1, values, stream); }
+    return sortByKey<uint32_t>(keys, values, n, keyBuf, valueBuf, tmp, tmpBytes, stream, (long long)first);
 }
 
 void setSortVariant(int v)

@@ -227,6 +227,16 @@ public:
         else { d_ = cs_domain_create_u64d(rank, nRanks, bucketSize, bucketSizeFocus, theta, b.lim, b.bnd); }
         if (!d_) { throw std::runtime_error(cs_last_error()); }
     }
+    /*! multi-rank domain: the communicator takes the place of the reference's MPI_Comm argument (domain.hpp:63-86).
+     *  Create it with cs_comm_create_nccl (one process per GPU; rank 0 distributes cs_nccl_unique_id) or
+     *  cs_comm_create_local (ranks as threads); it must outlive the domain. */
+    template<class BoxT>
+    Domain(int rank, int nRanks, unsigned bucketSize, unsigned bucketSizeFocus, float theta, cs_comm_t* comm,
+           const BoxT& box)
+        : Domain(rank, nRanks, bucketSize, bucketSizeFocus, theta, box)
+    {
+        if (comm) { csCheck(cs_domain_attach_comm(d_, comm), "Domain: attach communicator"); }
+    }
     Domain(const Domain&)            = delete;
     Domain& operator=(const Domain&) = delete;
     ~Domain() { cs_domain_destroy(d_); }
@@ -253,6 +263,16 @@ public:
     void findNeighbors(unsigned ngmax, uint32_t* neighbors, unsigned* neighborsCount, void* stream = nullptr)
     {
         csCheck(cs_domain_find_neighbors(d_, ngmax, neighbors, neighborsCount, stream), "findNeighbors");
+    }
+
+    /*! exchangeHalos(std::tie(fields...), ...) domain.hpp:332-337: device arrays with nParticlesWithHalos() elements;
+     *  the halo elements are overwritten with the owners' values.  Element sizes must be multiples of 4 bytes. */
+    template<class... Arrays>
+    void exchangeHalos(void* stream, Arrays*... arrays)
+    {
+        void* ptrs[]  = {static_cast<void*>(arrays)...};
+        int sizes[]   = {int(sizeof(Arrays))...};
+        csCheck(cs_domain_exchange_halos(d_, ptrs, sizes, int(sizeof...(Arrays)), stream), "Domain::exchangeHalos");
     }
 
     cs_domain_t* handle() { return d_; }

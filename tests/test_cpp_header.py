@@ -24,6 +24,13 @@ int main()
     try { cstone_b200::computeSfcKeys(Gpu{}, x, x, x, keys, 4, Box{}); }
     catch (std::exception& e) { std::printf("threw: %s\n", e.what()); return 3; }
     std::printf("computed\n");
+    // the Domain forwarder (single rank here) with the client-field halo exchange instantiated
+    if (false)
+    {
+        cstone_b200::Domain<uint64_t, double> dom(0, 1, 64, 8, 0.5f, nullptr, Box{});
+        float* rho = nullptr; double* vel = nullptr;
+        dom.exchangeHalos(nullptr, rho, vel);
+    }
     return 0;
 }
 '''
