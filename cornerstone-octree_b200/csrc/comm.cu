@@ -7,8 +7,11 @@
 #include <nccl.h>
 
 #include <condition_variable>
+#include <cstdlib>
 #include <cstring>
+#include <map>
 #include <mutex>
+#include <string>
 
 #include "comm.cuh"
 #include "cstone_b200.h"
@@ -44,9 +47,11 @@ struct LocalWorld
     std::vector<const void*> slot;
     std::vector<const std::vector<CommMessage>*> sendLists;
 
-    void barrier()
+    //! false when a rank has given up (cs_local_world_abort): the waiting ranks return an error instead of hanging
+    bool barrier()
     {
         std::unique_lock<std::mutex> lk(mtx);
+        if (aborted) { return false; }
         long long g = gen;
         if (++count == size)
         {
@@ -54,9 +59,24 @@ struct LocalWorld
             ++gen;
             cv.notify_all();
         }
-        else { cv.wait(lk, [&] { return gen != g; }); }
+        else { cv.wait(lk, [&] { return gen != g || aborted; }); }
+        return !aborted;
     }
+
+    void abort()
+    {
+        std::unique_lock<std::mutex> lk(mtx);
+        aborted = true;
+        cv.notify_all();
+    }
+    bool aborted{false};
 };
+
+#define CSB_LOCAL_BARRIER()                                                                                            \
+    do                                                                                                                 \
+    {                                                                                                                  \
+        if (!w_->barrier()) { return setLastError("local communicator: another rank failed"), 3; }                    \
+    } while (0)
 
 class LocalComm final : public Comm
 {
@@ -78,10 +98,10 @@ public:
     int allgatherHost(const void* in, size_t bytes, void* out, cudaStream_t) override
     {
         w_->slot[rank_] = in;
-        w_->barrier();
+        CSB_LOCAL_BARRIER();
         for (int r = 0; r < w_->size; ++r)
             std::memcpy(static_cast<char*>(out) + size_t(r) * bytes, w_->slot[r], bytes);
-        w_->barrier();
+        CSB_LOCAL_BARRIER();
         return 0;
     }
 
@@ -98,7 +118,7 @@ public:
         }
         CSB_CHECK(cudaStreamSynchronize(s)); // my contribution is complete
         w_->slot[rank_] = data;
-        w_->barrier();
+        CSB_LOCAL_BARRIER();
         for (int r = 0; r < w_->size; ++r)
         {
             uint32_t* dst = r == 0 ? acc_ : tmp_;
@@ -110,7 +130,7 @@ public:
             }
         }
         CSB_CHECK(cudaStreamSynchronize(s));
-        w_->barrier(); // every rank has read every contribution
+        CSB_LOCAL_BARRIER(); // every rank has read every contribution
         CSB_CHECK(cudaMemcpyAsync(data, acc_, n * sizeof(uint32_t), cudaMemcpyDeviceToDevice, s));
         bytesSent += n * sizeof(uint32_t);
         return 0;
@@ -120,7 +140,7 @@ public:
     {
         CSB_CHECK(cudaStreamSynchronize(s)); // send buffers are complete
         w_->sendLists[rank_] = &sends;
-        w_->barrier();
+        CSB_LOCAL_BARRIER();
         int status = 0;
         std::vector<int> taken(w_->size, 0);
         for (const CommMessage& r : recvs)
@@ -149,16 +169,43 @@ public:
             }
         }
         cudaStreamSynchronize(s);
-        w_->barrier(); // all copies out of my send buffers are done
+        CSB_LOCAL_BARRIER(); // all copies out of my send buffers are done
         for (const CommMessage& m : sends)
             bytesSent += m.bytes;
         return status;
     }
 
+    int sharePointers(void* const* mine, int count, uint64_t extraMine, std::vector<void*>& peers,
+                      std::vector<uint64_t>& extras, cudaStream_t s) override
+    {
+        // same process: the pointers themselves are valid on every rank's thread
+        struct Rec
+        {
+            void* p[MAX_SHARED];
+            uint64_t extra;
+        } rec{};
+        if (count > MAX_SHARED) { return setLastError("sharePointers: too many allocations"), 1; }
+        for (int k = 0; k < count; ++k)
+            rec.p[k] = mine[k];
+        rec.extra = extraMine;
+        CSB_CHECK(cudaStreamSynchronize(s)); // earlier work on my stream (resizes) is complete before peers write
+        std::vector<Rec> all(w_->size);
+        if (int e = allgatherHost(&rec, sizeof(Rec), all.data(), s)) { return e; }
+        peers.resize(size_t(w_->size) * count);
+        extras.resize(w_->size);
+        for (int r = 0; r < w_->size; ++r)
+        {
+            for (int k = 0; k < count; ++k)
+                peers[size_t(r) * count + k] = all[r].p[k];
+            extras[r] = all[r].extra;
+        }
+        return 0;
+    }
+
     int barrier(cudaStream_t s) override
     {
         CSB_CHECK(cudaStreamSynchronize(s));
-        w_->barrier();
+        CSB_LOCAL_BARRIER();
         return 0;
     }
 
@@ -243,6 +290,8 @@ public:
     }
     ~NcclComm() override
     {
+        for (auto& kv : ipcCache_)
+            cudaIpcCloseMemHandle(kv.second);
         if (comm_) { api_->CommDestroy(comm_); }
         cudaFree(stage_);
     }
@@ -294,6 +343,79 @@ public:
         return 0;
     }
 
+    /*! CUDA IPC: every rank publishes the memory handles of its allocations, peers map them once (cached by handle)
+     *  and then address the memory with ordinary loads/stores over NVLink */
+    int sharePointers(void* const* mine, int count, uint64_t extraMine, std::vector<void*>& peers,
+                      std::vector<uint64_t>& extras, cudaStream_t s) override
+    {
+        struct Rec
+        {
+            cudaIpcMemHandle_t h[MAX_SHARED];
+            uint64_t extra;
+            int ok;
+        } rec{};
+        if (count > MAX_SHARED) { return setLastError("sharePointers: too many allocations"), 1; }
+        rec.extra = extraMine;
+        rec.ok    = ipcDisabled_ ? 0 : 1;
+        for (int k = 0; k < count && rec.ok; ++k)
+            if (cudaIpcGetMemHandle(&rec.h[k], mine[k]) != cudaSuccess)
+            {
+                cudaGetLastError();
+                rec.ok = 0;
+            }
+        std::vector<Rec> all(size_);
+        if (int e = allgatherHost(&rec, sizeof(Rec), all.data(), s)) { return e; }
+        int ok = 1;
+        for (int r = 0; r < size_; ++r)
+            ok = ok && all[r].ok;
+        peers.assign(size_t(size_) * count, nullptr);
+        extras.resize(size_);
+        for (int r = 0; r < size_ && ok; ++r)
+        {
+            extras[r] = all[r].extra;
+            for (int k = 0; k < count && ok; ++k)
+            {
+                if (r == rank_)
+                {
+                    peers[size_t(r) * count + k] = mine[k];
+                    continue;
+                }
+                std::string key(reinterpret_cast<const char*>(&all[r].h[k]), sizeof(cudaIpcMemHandle_t));
+                auto it = ipcCache_.find(key);
+                if (it == ipcCache_.end())
+                {
+                    void* p = nullptr;
+                    if (cudaIpcOpenMemHandle(&p, all[r].h[k], cudaIpcMemLazyEnablePeerAccess) != cudaSuccess)
+                    {
+                        cudaGetLastError();
+                        ok = 0;
+                        break;
+                    }
+                    if (ipcOrder_.size() >= 64) // peers reallocate rarely; unmap the oldest mapping
+                    {
+                        cudaIpcCloseMemHandle(ipcCache_[ipcOrder_.front()]);
+                        ipcCache_.erase(ipcOrder_.front());
+                        ipcOrder_.erase(ipcOrder_.begin());
+                    }
+                    it = ipcCache_.emplace(key, p).first;
+                    ipcOrder_.push_back(key);
+                }
+                peers[size_t(r) * count + k] = it->second;
+            }
+        }
+        // every rank must take the same path
+        std::vector<int> oks(size_);
+        if (int e = allgatherHost(&ok, sizeof(int), oks.data(), s)) { return e; }
+        for (int v : oks)
+            ok = ok && v;
+        if (!ok)
+        {
+            ipcDisabled_ = true;
+            return 2;
+        }
+        return 0;
+    }
+
     int barrier(cudaStream_t s) override
     {
         int token = 0;
@@ -305,6 +427,9 @@ private:
     NcclApi* api_;
     ncclComm_t comm_;
     int rank_, size_;
+    bool ipcDisabled_{std::getenv("CSB_NO_PEER_PUSH") != nullptr};
+    std::map<std::string, void*> ipcCache_;
+    std::vector<std::string> ipcOrder_;
     char* stage_{nullptr};
     size_t stageCap_{0};
 };
@@ -327,6 +452,11 @@ void* cs_local_world_create(int size)
 }
 
 void cs_local_world_destroy(void* world) { delete static_cast<csb::LocalWorld*>(world); }
+
+void cs_local_world_abort(void* world)
+{
+    if (world) { static_cast<csb::LocalWorld*>(world)->abort(); }
+}
 
 cs_comm_t* cs_comm_create_local(void* world, int rank)
 {

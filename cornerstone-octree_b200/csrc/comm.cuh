@@ -48,6 +48,16 @@ public:
 
     virtual int barrier(cudaStream_t s) = 0;
 
+    /*! make `count` (<= MAX_SHARED) device allocations of this rank addressable by every other rank:
+     *  peers[r * count + k] is a pointer through which the caller can store into allocation k of rank r (its own
+     *  pointers for r == rank()); extras[r] carries one 64-bit word of rank r along.  `mine` must be allocation base
+     *  pointers (cudaMalloc).  Collective; it is ordered after all earlier work on every rank's stream, so a rank may
+     *  write into a peer's allocation as soon as the call returns.  Returns 2 (on every rank) when the transport cannot
+     *  map peer memory - the caller then uses exchange(). */
+    static constexpr int MAX_SHARED = 4;
+    virtual int sharePointers(void* const* mine, int count, uint64_t extraMine, std::vector<void*>& peers,
+                              std::vector<uint64_t>& extras, cudaStream_t s) = 0;
+
     //! statistics: bytes sent by this rank through exchange() and allreduce payload since creation
     uint64_t bytesSent{0};
 };
@@ -70,6 +80,13 @@ public:
         return 0;
     }
     int barrier(cudaStream_t) override { return 0; }
+    int sharePointers(void* const* mine, int count, uint64_t extraMine, std::vector<void*>& peers,
+                      std::vector<uint64_t>& extras, cudaStream_t) override
+    {
+        peers.assign(mine, mine + count);
+        extras.assign(1, extraMine);
+        return 0;
+    }
 };
 
 } // namespace csb

@@ -334,6 +334,10 @@ public:
         phase("assignment+sendRanges", s);
         /* ---- GlobalAssignment::distribute (assignment.hpp:167-203) */
         LocalIndex envStart = start_, envEnd = end_;
+        // one rank / nothing received: the present particles are already sorted, the reference's second sort is the
+        // identity
+        const K* keyView          = keys_.p + start_ + numSendDown;
+        const uint32_t* orderView = ordering_.p + start_ + numSendDown;
         if (P > 1)
         {
             CSB_REQUIRE(numAssigned >= numPresent, "global node counts are inconsistent with the local particles");
@@ -355,14 +359,30 @@ public:
             bufSize_ = exchangeSize;
             if (numRecv)
             {
-                CSB_TRY(keysDispatch(0, x_.p + recvStart, y_.p + recvStart, z_.p + recvStart, keys_.p + recvStart,
-                                     numRecv, lim_, bnd_, s));
-                CSB_TRY(cs_sequence_u32(recvStart, numRecv, ordering_.p + recvStart, s));
-                CSB_TRY(sortPairs(keys_.p + envStart, ordering_.p + envStart, envEnd - envStart, s));
+                /* The reference sorts the whole envelope - the present particles including those that were just sent
+                 * away, plus the received ones (assignment.hpp:197-201) - and then looks at the assigned sub-range.
+                 * Only the assigned particles matter afterwards, so the sort runs on them alone: the present-assigned
+                 * keys (a sorted, contiguous piece of the first sort) and the received keys, in envelope order so that
+                 * the stable sort breaks ties between equal keys exactly as the envelope sort does. */
+                const bool recvFirst        = recvStart < start_;
+                const LocalIndex offPresent = recvFirst ? numRecv : 0;
+                const LocalIndex offRecv    = recvFirst ? 0 : numPresent;
+                CSB_TRY(assignedKeys_.resize(numAssigned, s));
+                CSB_TRY(assignedOrder_.resize(numAssigned, s));
+                CSB_CHECK(cudaMemcpyAsync(assignedKeys_.p + offPresent, keys_.p + start_ + numSendDown,
+                                          size_t(numPresent) * sizeof(K), cudaMemcpyDeviceToDevice, s));
+                CSB_CHECK(cudaMemcpyAsync(assignedOrder_.p + offPresent, ordering_.p + start_ + numSendDown,
+                                          size_t(numPresent) * sizeof(uint32_t), cudaMemcpyDeviceToDevice, s));
+                // the key kernel keeps entries that are marked with removeKey: the output starts out as zeros
+                CSB_CHECK(cudaMemsetAsync(assignedKeys_.p + offRecv, 0, size_t(numRecv) * sizeof(K), s));
+                CSB_TRY(keysDispatch(0, x_.p + recvStart, y_.p + recvStart, z_.p + recvStart,
+                                     assignedKeys_.p + offRecv, numRecv, lim_, bnd_, s));
+                CSB_TRY(cs_sequence_u32(recvStart, numRecv, assignedOrder_.p + offRecv, s));
+                CSB_TRY(sortPairs(assignedKeys_.p, assignedOrder_.p, numAssigned, s));
+                keyView   = assignedKeys_.p;
+                orderView = assignedOrder_.p;
             }
         }
-        // one rank / nothing received: the envelope is already sorted, the reference's second sort is the identity
-        const K* keyView = keys_.p + envStart + numSendDown;
 
         phase("keys+sort received", s);
         /* ---- gatherArrays(x,y,z,h) to offset 0 (domain.hpp:187) */
@@ -373,8 +393,7 @@ public:
         {
             const void* src[4] = {x_.p, y_.p, z_.p, h_.p};
             void* dst[4]       = {sx_.p, sy_.p, sz_.p, sh_.p};
-            CSB_TRY(cs_gather_arrays4(ordering_.p + envStart + numSendDown, numAssigned, bufSize_, src, dst,
-                                      int(sizeof(T)), s));
+            CSB_TRY(cs_gather_arrays4(orderView, numAssigned, bufSize_, src, dst, int(sizeof(T)), s));
         }
 
         phase("gatherArrays", s);
@@ -1237,6 +1256,44 @@ private:
             sendCounts[r] = r == me ? 0 : sendIdx[r + 1] - sendIdx[r];
         CSB_TRY(comm.allgatherHost(sendCounts.data(), P * sizeof(uint32_t), allCounts.data(), s));
 
+        /* Peer-memory path: the pack kernel of every destination gathers through the ordering and stores straight into
+         * the destination rank's particle arrays over NVLink (CUDA IPC mappings, cached) - pack and transfer are one
+         * kernel and nothing is staged.  Source r's block lands behind the blocks of the lower ranks, exactly where
+         * the send/recv path below puts it. */
+        if (peerPush_)
+        {
+            void* mine[4] = {x_.p, y_.p, z_.p, h_.p};
+            std::vector<void*> peers;
+            std::vector<uint64_t> recvStarts;
+            int st = comm.sharePointers(mine, 4, uint64_t(recvStart), peers, recvStarts, s);
+            if (st == 2) { peerPush_ = false; }
+            else if (st != 0) { return st; }
+            else
+            {
+                size_t received = 0;
+                for (int r = 0; r < P; ++r)
+                    if (r != me) { received += allCounts[size_t(r) * P + me]; }
+                CSB_REQUIRE(received == numRecv,
+                            "exchangeParticles: incoming particle count does not match the assignment");
+                for (int r = 0; r < P; ++r)
+                {
+                    size_t c = sendCounts[r];
+                    if (c == 0) { continue; }
+                    size_t dstOffset = size_t(recvStarts[r]);
+                    for (int src = 0; src < me; ++src)
+                        if (src != r) { dstOffset += allCounts[size_t(src) * P + r]; }
+                    const void* src4[4] = {x_.p, y_.p, z_.p, h_.p};
+                    void* dst4[4];
+                    for (int k = 0; k < 4; ++k)
+                        dst4[k] = static_cast<T*>(peers[size_t(r) * 4 + k]) + dstOffset;
+                    CSB_TRY(cs_gather4(ordering_.p + start_ + sendIdx[r], c, src4, dst4, int(sizeof(T)), s));
+                    comm.bytesSent += 4 * c * sizeof(T);
+                }
+                CSB_CHECK(cudaStreamSynchronize(s)); // my stores have landed ...
+                return comm.barrier(s);              // ... and so have everybody else's
+            }
+        }
+
         auto blockElems = [](size_t c) { return (c + 3) & ~size_t(3); }; // 16-byte multiples for 4- and 8-byte reals
         size_t totalSend = 0;
         for (int r = 0; r < P; ++r)
@@ -1469,6 +1526,7 @@ private:
     DevBuf<char> tlRecv_, rejRecv_, reqRecv_, fieldSendBuf_;
 
     int rank_, numRanks_;
+    bool peerPush_{true}; // exchangeParticles through peer memory; cleared when the transport cannot map it
     SelfComm selfComm_;
     Comm* comm_{&selfComm_};
     SfcAssignment<K> assignment_;
@@ -1483,8 +1541,8 @@ private:
     LocalIndex start_{0}, end_{0}, bufSize_{0};
 
     DevBuf<T> x_, y_, z_, h_, sx_, sy_, sz_, sh_, partials_, geoCenters_, geoSizes_, sendBuf_;
-    DevBuf<K> keys_, keyBuf_, boundaryKeys_;
-    DevBuf<uint32_t> ordering_, valueBuf_, scalars_, gapCounts_, layout_;
+    DevBuf<K> keys_, keyBuf_, boundaryKeys_, assignedKeys_;
+    DevBuf<uint32_t> ordering_, valueBuf_, scalars_, gapCounts_, layout_, assignedOrder_;
     DevBuf<unsigned char> sortTmp_, linkTmp_, opsTmp_, scanTmp_;
     DevBuf<int> nodeOps_, nodeOpsAll_;
 

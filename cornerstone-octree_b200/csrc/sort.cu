@@ -549,18 +549,46 @@ __global__ void packRec4Kernel(size_t n, const E* __restrict__ a, const E* __res
     }
 }
 
+//! record load with the L2 fetch-size hint 64 B: a missing sector then costs 64 B of DRAM traffic instead of the whole
+//! 128-byte line that the default policy brings in (LDG.LTC64B; measured on the random gather: see profiles/)
 template<class E>
+__device__ __forceinline__ Rec4<E> loadRecord64B(const Rec4<E>* p)
+{
+    Rec4<E> r;
+    if constexpr (sizeof(E) == 8)
+    {
+        uint64_t a, b, c, d;
+        asm volatile("ld.global.nc.L2::64B.v2.u64 {%0,%1}, [%2];" : "=l"(a), "=l"(b) : "l"(p));
+        asm volatile("ld.global.nc.L2::64B.v2.u64 {%0,%1}, [%2+16];" : "=l"(c), "=l"(d) : "l"(p));
+        uint64_t w[4] = {a, b, c, d};
+        memcpy(&r, w, sizeof(r)); // E is whatever 8-byte type the caller moves; keep the bits
+    }
+    else
+    {
+        uint32_t a, b, c, d;
+        asm volatile("ld.global.nc.L2::64B.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(a), "=r"(b), "=r"(c), "=r"(d) : "l"(p));
+        uint32_t w[4] = {a, b, c, d};
+        memcpy(&r, w, sizeof(r));
+    }
+    return r;
+}
+
+int g_gatherVariant = 1; // 0: plain 256-bit record loads, 1: L2::64B fetch hint
+
+template<class E, int VARIANT>
 __global__ void gatherRec4Kernel(const uint32_t* __restrict__ ord, size_t n, const Rec4<E>* __restrict__ rec, E* __restrict__ a,
                                  E* __restrict__ b, E* __restrict__ c, E* __restrict__ d)
 {
     size_t i = size_t(blockIdx.x) * blockDim.x + threadIdx.x;
     if (i < n)
     {
-        Rec4<E> r = rec[ord[i]];
-        a[i]      = r.v[0];
-        b[i]      = r.v[1];
-        c[i]      = r.v[2];
-        d[i]      = r.v[3];
+        Rec4<E> r;
+        if constexpr (VARIANT == 1) { r = loadRecord64B(rec + ord[i]); }
+        else { r = rec[ord[i]]; }
+        a[i] = r.v[0];
+        b[i] = r.v[1];
+        c[i] = r.v[2];
+        d[i] = r.v[3];
     }
 }
 
@@ -574,9 +602,9 @@ int gatherArrays4(const uint32_t* ordering, size_t n, size_t srcCount, const voi
                                                            static_cast<const E*>(src4[2]),
                                                            static_cast<const E*>(src4[3]), rec);
     CSB_LAUNCH_CHECK();
-    gatherRec4Kernel<E><<<iceil(n, 256), 256, 0, s>>>(ordering, n, rec, static_cast<E*>(dst4[0]),
-                                                      static_cast<E*>(dst4[1]), static_cast<E*>(dst4[2]),
-                                                      static_cast<E*>(dst4[3]));
+    auto kernel = g_gatherVariant == 1 ? gatherRec4Kernel<E, 1> : gatherRec4Kernel<E, 0>;
+    kernel<<<iceil(n, 256), 256, 0, s>>>(ordering, n, rec, static_cast<E*>(dst4[0]), static_cast<E*>(dst4[1]),
+                                         static_cast<E*>(dst4[2]), static_cast<E*>(dst4[3]));
     CSB_LAUNCH_CHECK();
     return 0;
 }
@@ -623,10 +651,12 @@ size_t sortTempBytesU32(size_t n) { return sortTempBytes<uint32_t>(n); }
 extern "C"
 {
 
-/* tuning hook (not part of the drop-in surface): select the onesweep kernel variant */
+/* tuning hook (not part of the drop-in surface): select the onesweep kernel variant; 1000 + v selects the record
+ * load of gatherArrays (0: plain, 1: L2 64-byte fetch hint) */
 int cs_sort_set_variant(int variant)
 {
-    csb::setSortVariant(variant);
+    if (variant >= 1000) { csb::g_gatherVariant = variant - 1000; }
+    else { csb::setSortVariant(variant); }
     return 0;
 }
 

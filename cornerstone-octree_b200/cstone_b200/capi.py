@@ -314,6 +314,11 @@ class LocalWorld:
         if not self.handle:
             raise CstoneError(lib().cs_last_error().decode())
 
+    def abort(self):
+        """wake the ranks that wait for a rank that has failed (they return an error)"""
+        if getattr(self, "handle", None):
+            lib().cs_local_world_abort(C.c_void_p(self.handle))
+
     def comm(self, rank):
         lib().cs_comm_create_local.restype = C.c_void_p
         h = lib().cs_comm_create_local(C.c_void_p(self.handle), C.c_int(rank))

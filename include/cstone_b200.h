@@ -193,6 +193,8 @@ int cs_exchange_buffer_layout(uint32_t start, uint32_t end, uint32_t size, uint3
 typedef struct cs_comm cs_comm_t;
 void* cs_local_world_create(int size);
 void cs_local_world_destroy(void* world);
+/* a rank that fails calls this so that the ranks waiting for it return an error instead of blocking forever */
+void cs_local_world_abort(void* world);
 cs_comm_t* cs_comm_create_local(void* world, int rank);
 int cs_nccl_unique_id(void* out128);
 cs_comm_t* cs_comm_create_nccl(int rank, int size, const void* id128);

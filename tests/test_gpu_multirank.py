@@ -21,8 +21,9 @@ def capi():
     return c
 
 
-def run_ranks(P, fn):
-    """run fn(rank) on P threads (each with its own CUDA stream); re-raise the first failure"""
+def run_ranks(P, fn, world=None):
+    """run fn(rank) on P threads (each with its own CUDA stream); re-raise the first failure.  A failing rank aborts
+    the local world so that the ranks waiting for it at a collective return an error instead of blocking forever."""
     errors = [None] * P
     results = [None] * P
 
@@ -33,17 +34,26 @@ def run_ranks(P, fn):
                 torch.cuda.current_stream().synchronize()
         except BaseException as e:  # noqa: BLE001
             errors[r] = e
+            if world is not None:
+                world.abort()
 
-    threads = [threading.Thread(target=body, args=(r,)) for r in range(P)]
+    threads = [threading.Thread(target=body, args=(r,), daemon=True) for r in range(P)]
     for t in threads:
         t.start()
     for t in threads:
         t.join(timeout=120)
-    for t in threads:
-        assert not t.is_alive(), "rank thread hung"
+    if any(t.is_alive() for t in threads) and world is not None:
+        world.abort()
+        for t in threads:
+            t.join(timeout=10)
+    first = [e for e in errors if e is not None and "another rank failed" not in str(e)]
+    if first:
+        raise first[0]
     for e in errors:
         if e is not None:
             raise e
+    for t in threads:
+        assert not t.is_alive(), "rank thread hung"
     return results
 
 
@@ -99,7 +109,7 @@ def test_assigned_particles_match_reference(combo, P, dist, pbc, bucket, bucket_
             comm.close()
             return out
 
-        got = run_ranks(P, rank_body)
+        got = run_ranks(P, rank_body, world)
         for r in range(P):
             w = want[r]
             s, e = w["start"], w["end"]
@@ -158,7 +168,7 @@ def test_full_domain_with_halos_matches_reference(combo, P, dist, pbc, bucket, b
             comm.close()
             return out
 
-        got = run_ranks(P, rank_body)
+        got = run_ranks(P, rank_body, world)
         for r in range(P):
             w, g = want[r], got[r]
             assert (g["start"], g["end"], g["size"]) == (w["start"], w["end"], w["keys"].size), (r, num_syncs)
@@ -216,7 +226,7 @@ def test_drifting_particles_match_reference(combo, P, dist, pbc, bucket, bucket_
         comm.close()
         return out
 
-    got = run_ranks(P, rank_body)
+    got = run_ranks(P, rank_body, world)
     for r in range(P):
         w, g = want[r], got[r]
         assert (g["start"], g["end"]) == (w["start"], w["end"]), r
@@ -269,6 +279,6 @@ def test_exchange_halos_of_client_fields(combo, P, pbc):
         comm.close()
         return ok, num_halos
 
-    res = run_ranks(P, rank_body)
+    res = run_ranks(P, rank_body, world)
     assert all(ok for ok, _ in res)
     assert all(nh > 0 for _, nh in res), "the test needs halos to be meaningful"
