@@ -477,6 +477,8 @@ int sortByKey(K* keys, uint32_t* values, size_t n, K* keyBuf, uint32_t* valueBuf
         case 2: run(integral_constant<int, 256>{}, integral_constant<int, 15>{}, integral_constant<int, 3>{}); break;
         case 3: run(integral_constant<int, 384>{}, integral_constant<int, 12>{}, integral_constant<int, 3>{}); break;
         case 4: run(integral_constant<int, 256>{}, integral_constant<int, 9>{}, integral_constant<int, 5>{}); break;
+        case 5: run(integral_constant<int, 512>{}, integral_constant<int, 15>{}, integral_constant<int, 2>{}); break;
+        case 6: run(integral_constant<int, 384>{}, integral_constant<int, 18>{}, integral_constant<int, 2>{}); break;
         default: run(integral_constant<int, 512>{}, integral_constant<int, 12>{}, integral_constant<int, 2>{}); break;
     }
     if (status) { return status; }

@@ -26,7 +26,7 @@ keys = torch.empty_like(keys0)
 vals = torch.empty(n, dtype=torch.uint32, device=dev)
 seq = capi.sequence(0, n, dev)
 
-for variant, name in [(0, "512x12"), (1, "256x12"), (2, "256x15"), (3, "384x12"), (4, "256x9"), (103, "384x12 NO LOOKBACK (wrong result, timing only)"), (100, "512x12 NO LOOKBACK")]:
+for variant, name in [(5, "512x15"), (6, "384x18"), (0, "512x12"), (1, "256x12"), (2, "256x15"), (3, "384x12"), (4, "256x9"), (103, "384x12 NO LOOKBACK (wrong result, timing only)"), (100, "512x12 NO LOOKBACK")]:
     capi.lib().cs_sort_set_variant(C.c_int(variant))
     ms = []
     for _ in range(4):
