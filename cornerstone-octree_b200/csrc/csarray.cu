@@ -25,9 +25,9 @@ namespace
  *      read from HBM once - and the threads search their leaf keys there.  Very long windows (coarse trees with few
  *      leaves) are searched in global memory instead, bounded by the window.
  */
-constexpr int NC_LEAVES  = 128;  // leaves per block
+constexpr int NC_LEAVES  = 64;   // leaves per block
 constexpr int NC_THREADS = 256;  // threads per block: all of them stream keys, the first NC_LEAVES search
-constexpr int NC_WINDOW  = 6144; // keys staged in shared memory per tile (48 KiB of 64-bit keys: 4 blocks per SM)
+constexpr int NC_WINDOW  = 3072; // keys staged in shared memory per tile (24 KiB of 64-bit keys: 8 blocks per SM)
 constexpr int NC_MAX_TILES = 8; // longer windows (coarse trees) are searched in global memory
 
 template<class K>
@@ -70,7 +70,7 @@ __global__ void __launch_bounds__(NC_THREADS) nodeCountsKernel(const K* __restri
             const uint32_t tw = uint32_t(min(size_t(NC_WINDOW), W - base));
             const K* src      = keys + A + base;
             if (base) { __syncthreads(); }
-            // fixed trip count, fully unrolled: all 24 loads of a thread are in flight together (a `for (i < tw)`
+            // fixed trip count, fully unrolled: all 12 loads of a thread are in flight together (a `for (i < tw)`
             // loop issues them a few at a time and the block waits on one DRAM round trip after the other)
 #pragma unroll
             for (int u = 0; u < NC_WINDOW / NC_THREADS; ++u)

@@ -1275,9 +1275,12 @@ private:
                     if (r != me) { received += allCounts[size_t(r) * P + me]; }
                 CSB_REQUIRE(received == numRecv,
                             "exchangeParticles: incoming particle count does not match the assignment");
-                for (int r = 0; r < P; ++r)
+                // destinations in the order me+1, me+2, ...: at any time every rank is the target of one sender
+                // instead of all ranks storing into rank 0 first
+                for (int k = 1; k < P; ++k)
                 {
-                    size_t c = sendCounts[r];
+                    const int r = (me + k) % P;
+                    size_t c    = sendCounts[r];
                     if (c == 0) { continue; }
                     size_t dstOffset = size_t(recvStarts[r]);
                     for (int src = 0; src < me; ++src)
