@@ -305,6 +305,32 @@ def run_ours(args):
     nb_time = statistics.median(a.elapsed_time(b) for a, b in nb_ms)
     num_leaves = dom.num_focus_leaves
 
+    # ---- invariants of the synchronised state (outside the timed region; size independent): every particle arrived
+    # exactly once (wrapping integer sums of the coordinate bit patterns are order independent and exact), keys are
+    # sorted on every rank and the ranks' key ranges are ordered along the curve
+    def bits_sum(t):
+        return t.view(torch.int64).sum(dtype=torch.int64)
+
+    s_, e_ = dom.start_index, dom.end_index
+    keys_assigned = dom.field("keys")[s_:e_].view(torch.int64)
+    chk = torch.stack([bits_sum(x) + bits_sum(y) + bits_sum(z),
+                       bits_sum(dom.field("x")[s_:e_]) + bits_sum(dom.field("y")[s_:e_]) + bits_sum(dom.field("z")[s_:e_]),
+                       torch.tensor(e_ - s_, dtype=torch.int64, device=dev)])
+    ends = torch.stack([keys_assigned[0], keys_assigned[-1]]) if e_ > s_ else torch.zeros(2, dtype=torch.int64, device=dev)
+    sorted_ok = torch.tensor([int(bool((keys_assigned[1:] >= keys_assigned[:-1]).all()))], dtype=torch.int64, device=dev)
+    if world > 1:
+        dist.all_reduce(chk)  # sums wrap consistently on every rank
+        all_ends = [torch.zeros_like(ends) for _ in range(world)]
+        dist.all_gather(all_ends, ends)
+        dist.all_reduce(sorted_ok, op=dist.ReduceOp.MIN)
+        flat = torch.cat(all_ends)
+        ranges_ordered = bool((flat[1:] >= flat[:-1]).all())
+    else:
+        ranges_ordered = True
+    checks = {"every_particle_arrived_once": bool(chk[0] == chk[1]) and int(chk[2]) == world * n,
+              "keys_sorted_on_every_rank": bool(sorted_ok.item()), "rank_key_ranges_ordered": ranges_ordered}
+    del keys_assigned
+
     # ---- steady state: re-sync the (already SFC-ordered) domain arrays in place, one tree update per call
     steady = []
     for _ in range(4):
@@ -404,7 +430,8 @@ def run_ours(args):
                    f"one Domain over {world} ranks (SFC ranges): ncclAllReduce of global node counts, "
                    f"exchangeParticles / LET treelets / exchangeHalos over ncclSend/Recv; periodic box, "
                    f"bucketSize={bucket}",
-                   "focus_leaves": num_leaves, "mean_neighbors": round(mean_nc, 2), "exchange": exchange},
+                   "focus_leaves": num_leaves, "mean_neighbors": round(mean_nc, 2), "exchange": exchange,
+                   "checks": checks},
         "e2e": {"value": round(e2e_value, 2), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "ms_per_step": round(e2e_ms, 3),
                 "note": "neighbour lists stay in HBM for the device-side consumer; keys, x,y,z,h (copied on a second "

@@ -17,6 +17,7 @@
 #include <algorithm>
 #include <chrono>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <limits>
 #include <vector>
@@ -1529,7 +1530,9 @@ private:
     DevBuf<char> tlRecv_, rejRecv_, reqRecv_, fieldSendBuf_;
 
     int rank_, numRanks_;
-    bool peerPush_{true}; // exchangeParticles through peer memory; cleared when the transport cannot map it
+    // exchangeParticles through peer memory; cleared when the transport cannot map it (CSB_NO_PEER_PUSH forces the
+    // send/recv path)
+    bool peerPush_{std::getenv("CSB_NO_PEER_PUSH") == nullptr};
     SelfComm selfComm_;
     Comm* comm_{&selfComm_};
     SfcAssignment<K> assignment_;
