@@ -112,6 +112,9 @@ def run_reference(args):
     """the reference's own CPU path (Domain::sync x2 + findNeighbors) on a bounded sample of the workload"""
     import numpy as np
 
+    # torch.distributed.run exports OMP_NUM_THREADS=1 to its workers; the reference arm uses every host core
+    os.environ["OMP_NUM_THREADS"] = str(os.cpu_count())
+    os.environ.setdefault("OMP_PROC_BIND", "spread")
     import _libs
 
     n = args.ref_n
@@ -119,9 +122,21 @@ def run_reference(args):
     x, y, z = (rng.random(n) for _ in range(3))
     h = np.full(n, h_for(n, NG0))
     lim, bnd = (0, 1, 0, 1, 0, 1), (0, 0, 0)
-    cores = os.cpu_count()
     values = []
     kind = "reference" if _libs.ref_lib() is not None else "port"
+    cores = os.cpu_count()
+    if kind == "reference":
+        try:
+            # the OpenMP runtime may have been initialised (by torch) before the variable was set: ask it, and raise the
+            # thread count through the runtime if it came up short
+            import ctypes as C
+            omp = C.CDLL("libgomp.so.1")
+            omp.omp_set_num_threads(C.c_int(os.cpu_count()))
+            cores = int(_libs.ref_lib().ref_num_threads())
+        except Exception:
+            pass
+    else:
+        cores = 1  # the C port of the oracle is scalar
     for it in range(args.warmup_ref + args.steps_ref):
         t0 = time.perf_counter()
         if kind == "reference":
