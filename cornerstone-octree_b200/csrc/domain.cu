@@ -189,6 +189,17 @@ public:
         realBytes = sizeof(T);
     }
 
+    ~DomainImpl() override
+    {
+        if (copyStream_)
+        {
+            cudaStreamSynchronize(copyStream_);
+            cudaEventDestroy(copyReady_);
+            cudaEventDestroy(copyDone_);
+            cudaStreamDestroy(copyStream_);
+        }
+    }
+
     //! back to the freshly constructed state (next sync is a "first call"); device buffers are kept
     int reset(cudaStream_t s) override
     {
@@ -255,7 +266,23 @@ public:
             CSB_CHECK(cudaMemcpyAsync(x_.p, xin, nIn * sizeof(T), kindOfCopy, s));
             CSB_CHECK(cudaMemcpyAsync(y_.p, yin, nIn * sizeof(T), kindOfCopy, s));
             CSB_CHECK(cudaMemcpyAsync(z_.p, zin, nIn * sizeof(T), kindOfCopy, s));
-            CSB_CHECK(cudaMemcpyAsync(h_.p, hin, nIn * sizeof(T), kindOfCopy, s));
+            if (hostInput)
+            {
+                // h is not needed before the particle exchange / gatherArrays: its upload runs on a second stream and
+                // overlaps the key generation, the sort and the global tree update
+                if (!copyStream_)
+                {
+                    CSB_CHECK(cudaStreamCreateWithFlags(&copyStream_, cudaStreamNonBlocking));
+                    CSB_CHECK(cudaEventCreateWithFlags(&copyReady_, cudaEventDisableTiming));
+                    CSB_CHECK(cudaEventCreateWithFlags(&copyDone_, cudaEventDisableTiming));
+                }
+                CSB_CHECK(cudaEventRecord(copyReady_, s)); // h_ is allocated and no longer in use on s
+                CSB_CHECK(cudaStreamWaitEvent(copyStream_, copyReady_, 0));
+                CSB_CHECK(cudaMemcpyAsync(h_.p, hin, nIn * sizeof(T), kindOfCopy, copyStream_));
+                CSB_CHECK(cudaEventRecord(copyDone_, copyStream_));
+                hUploadPending_ = true;
+            }
+            else { CSB_CHECK(cudaMemcpyAsync(h_.p, hin, nIn * sizeof(T), kindOfCopy, s)); }
             CSB_TRY(keys_.resize(nIn, s));
             if (keysIn) { CSB_CHECK(cudaMemcpyAsync(keys_.p, keysIn, nIn * sizeof(K), kindOfCopy, s)); }
             else { CSB_CHECK(cudaMemsetAsync(keys_.p, 0, nIn * sizeof(K), s)); }
@@ -333,6 +360,11 @@ public:
         const LocalIndex numAssigned = P == 1 ? numPresent : assignment_.counts[me];
 
         phase("assignment+sendRanges", s);
+        if (hUploadPending_)
+        {
+            CSB_CHECK(cudaStreamWaitEvent(s, copyDone_, 0)); // everything below may read h
+            hUploadPending_ = false;
+        }
         /* ---- GlobalAssignment::distribute (assignment.hpp:167-203) */
         LocalIndex envStart = start_, envEnd = end_;
         // one rank / nothing received: the present particles are already sorted, the reference's second sort is the
@@ -440,6 +472,7 @@ public:
         end_       = numAssigned;
         bufSize_   = numAssigned;
         firstCall_ = false;
+        CSB_CHECK(cudaStreamSynchronize(s)); // the caller's input buffers are free again, the results are in place
         return 0;
     }
 
@@ -1545,6 +1578,9 @@ private:
     int bnd_[3];
     bool firstCall_{true};
     LocalIndex start_{0}, end_{0}, bufSize_{0};
+    cudaStream_t copyStream_{nullptr}; // upload of h from host memory, concurrent with the first stages of sync
+    cudaEvent_t copyReady_{nullptr}, copyDone_{nullptr};
+    bool hUploadPending_{false};
 
     DevBuf<T> x_, y_, z_, h_, sx_, sy_, sz_, sh_, partials_, geoCenters_, geoSizes_, sendBuf_;
     DevBuf<K> keys_, keyBuf_, boundaryKeys_, assignedKeys_;
