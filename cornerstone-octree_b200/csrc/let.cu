@@ -108,7 +108,6 @@ __global__ void __launch_bounds__(128) markMacsKernel(const K* __restrict__ pref
     {
         T cx[8], cy[8], cz[8], mac2[8];
         int child[8];
-        uint8_t outside[8]; // node not fully inside the focus
     };
     __shared__ Group groups[128 / 32];
     __shared__ uint8_t laneMask[128 / 32][KeyTraits<K>::maxLevel + 2][32];
@@ -142,27 +141,72 @@ __global__ void __launch_bounds__(128) markMacsKernel(const K* __restrict__ pref
         return nodeStart < focusStart || nodeEnd > focusEnd;
     };
 
+    /* Bounding box of the active leaves of the warp.  The expression the MAC compares, sum over d of
+     * max(p(tc_d - c_d) - ts_d, 0)^2 with p = distance to the nearest multiple of the period (or |.| for open
+     * dimensions), can only grow when the target box shrinks inside its bounding box: p(a + b) <= p(a) + |b| and
+     * |bc_d - tc_d| <= bs_d - ts_d.  A source whose expression against the bounding box already exceeds mac^2 (with a
+     * margin far above the rounding errors of either evaluation) therefore passes the MAC of every lane, and the
+     * per-lane tests of that child are skipped - the marks stay exactly those of the per-leaf walks. */
+    T bc[3], bs[3];
+    {
+        constexpr T big = sizeof(T) == 8 ? T(1e300) : T(1e30);
+#pragma unroll
+        for (int d = 0; d < 3; ++d)
+        {
+            T mn = active ? tc[d] - ts[d] : big;
+            T mx = active ? tc[d] + ts[d] : -big;
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1)
+            {
+                T a = __shfl_xor_sync(FULL, mn, o), b = __shfl_xor_sync(FULL, mx, o);
+                mn  = a < mn ? a : mn;
+                mx  = b > mx ? b : mx;
+            }
+            bc[d] = T(0.5) * (mx + mn);
+            // inflated beyond the rounding of bc and bs themselves, so that the bounding-box expression is a lower
+            // bound of every lane's also in floating point
+            bs[d] = T(0.5) * (mx - mn) * (T(1) + (sizeof(T) == 8 ? T(1e-12) : T(1e-5))) +
+                    (sizeof(T) == 8 ? T(1e-13) : T(1e-6)) * (rabs(mx) + rabs(mn));
+        }
+    }
+    constexpr T cullMargin = sizeof(T) == 8 ? T(1e-9) : T(1e-3);
+
     //! this lane's decisions for the 8 children starting at child0 (bit c: the lane's walk marks and enters child c)
     auto testChildren = [&](int child0, bool mine) -> unsigned
     {
         __syncwarp();
+        bool test = false;
         if (lane < 8)
         {
             int idx         = child0 + int(lane);
-            g.cx[lane]      = centers4[4 * idx];
-            g.cy[lane]      = centers4[4 * idx + 1];
-            g.cz[lane]      = centers4[4 * idx + 2];
-            g.mac2[lane]    = centers4[4 * idx + 3];
+            const T cx = centers4[4 * idx], cy = centers4[4 * idx + 1], cz = centers4[4 * idx + 2];
+            const T mac2    = centers4[4 * idx + 3];
+            g.cx[lane]      = cx;
+            g.cy[lane]      = cy;
+            g.cz[lane]      = cz;
+            g.mac2[lane]    = mac2;
             g.child[lane]   = childOffsets[idx];
-            g.outside[lane] = outsideFocus(idx) ? 1 : 0;
+            if (outsideFocus(idx))
+            {
+                const T c[3] = {cx, cy, cz};
+                T r2         = 0;
+#pragma unroll
+                for (int d = 0; d < 3; ++d)
+                {
+                    T v = rabs(pbcFold(bc[d] - c[d], d, box)) - bs[d];
+                    v   = v > T(0) ? v : T(0);
+                    r2 += v * v;
+                }
+                test = !(r2 * (T(1) - cullMargin) > rabs(mac2)); // not certainly far for every lane
+            }
         }
-        __syncwarp();
-        unsigned bits = 0;
+        const unsigned testMask = __ballot_sync(FULL, test);
+        unsigned bits           = 0;
         if (mine)
         {
 #pragma unroll
             for (int c = 0; c < 8; ++c)
-                if (g.outside[c] && violates(g.cx[c], g.cy[c], g.cz[c], g.mac2[c])) { bits |= 1u << c; }
+                if (((testMask >> c) & 1u) && violates(g.cx[c], g.cy[c], g.cz[c], g.mac2[c])) { bits |= 1u << c; }
         }
         return bits;
     };
