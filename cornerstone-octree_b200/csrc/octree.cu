@@ -13,8 +13,8 @@
 namespace csb
 {
 
-int sortByKeyU64(uint64_t*, uint32_t*, size_t, uint64_t*, uint32_t*, void*, size_t, cudaStream_t);
-int sortByKeyU32(uint32_t*, uint32_t*, size_t, uint32_t*, uint32_t*, void*, size_t, cudaStream_t);
+int sortByKeySkipU64(uint64_t*, uint32_t*, size_t, uint64_t*, uint32_t*, void*, size_t, cudaStream_t);
+int sortByKeySkipU32(uint32_t*, uint32_t*, size_t, uint32_t*, uint32_t*, void*, size_t, cudaStream_t);
 size_t sortTempBytesU64(size_t n);
 size_t sortTempBytesU32(size_t n);
 
@@ -23,11 +23,11 @@ namespace
 
 inline int sortByKeyK(uint64_t* k, uint32_t* v, size_t n, uint64_t* kb, uint32_t* vb, void* t, size_t tb, cudaStream_t s)
 {
-    return sortByKeyU64(k, v, n, kb, vb, t, tb, s);
+    return sortByKeySkipU64(k, v, n, kb, vb, t, tb, s);
 }
 inline int sortByKeyK(uint32_t* k, uint32_t* v, size_t n, uint32_t* kb, uint32_t* vb, void* t, size_t tb, cudaStream_t s)
 {
-    return sortByKeyU32(k, v, n, kb, vb, t, tb, s);
+    return sortByKeySkipU32(k, v, n, kb, vb, t, tb, s);
 }
 template<class K>
 size_t sortTempBytesK(size_t n)

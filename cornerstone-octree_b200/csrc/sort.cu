@@ -399,7 +399,7 @@ size_t sortTempBytes(size_t n)
 
 template<class K>
 int sortByKey(K* keys, uint32_t* values, size_t n, K* keyBuf, uint32_t* valueBuf, void* tmp, size_t tmpBytes,
-              cudaStream_t stream, long long iotaStart = -1)
+              cudaStream_t stream, long long iotaStart = -1, bool skipTrivialPasses = false)
 {
     using Cfg = SortCfg<K>;
     if (n < 2) { return 0; }
@@ -446,18 +446,44 @@ int sortByKey(K* keys, uint32_t* values, size_t n, K* keyBuf, uint32_t* valueBuf
         scanHistogramKernel<<<Cfg::passes, RADIX, 0, stream>>>(hist);
         countLaunch();
 
+        // a digit place in which all keys agree is an identity pass.  Keys with a small range (octree prefixes) have
+        // several; finding them costs one read-back of the scanned histograms, so only callers that synchronise anyway
+        // ask for it
+        bool trivial[Cfg::passes] = {};
+        if (skipTrivialPasses)
+        {
+            uint32_t base[Cfg::passes * RADIX];
+            if (cudaMemcpyAsync(base, hist, sizeof(base), cudaMemcpyDeviceToHost, stream) != cudaSuccess ||
+                cudaStreamSynchronize(stream) != cudaSuccess)
+            {
+                setLastError("sort_by_key: histogram read-back failed");
+                status = 1;
+                return;
+            }
+            for (int p = 0; p < Cfg::passes; ++p)
+                for (int b = 0; b < RADIX; ++b)
+                {
+                    uint64_t next = b + 1 < RADIX ? base[p * RADIX + b + 1] : n;
+                    if (next - base[p * RADIX + b] == n) { trivial[p] = true; }
+                }
+        }
+
         K* kin         = keys;
         K* kout        = keyBuf;
         uint32_t* vin  = values;
         uint32_t* vout = valueBuf;
+        bool iotaDone  = iotaStart < 0;
         for (int p = 0; p < Cfg::passes; ++p)
         {
+            if (trivial[p]) { continue; }
+            const long long iota = iotaDone ? -1LL : iotaStart;
+            iotaDone             = true;
             uint32_t* st = states + size_t(p) * numTiles * RADIX;
             if (values)
             {
                 kv<<<unsigned(numTiles), THREADS, smem, stream>>>(kin, kout, vin, vout, n, p * RADIX_BITS,
                                                                   hist + p * RADIX, st, counters + p,
-                                                                  g_sortDebugNoLookback, p == 0 ? iotaStart : -1LL);
+                                                                  g_sortDebugNoLookback, iota);
             }
             else
             {
@@ -468,6 +494,24 @@ int sortByKey(K* keys, uint32_t* values, size_t n, K* keyBuf, uint32_t* valueBuf
             countLaunch();
             std::swap(kin, kout);
             std::swap(vin, vout);
+        }
+        if (!iotaDone && values) // every pass was trivial: the keys are constant, the permutation is the identity
+        {
+            if (cs_sequence_u32(uint32_t(iotaStart), n, values, stream) != 0) { status = 1; }
+        }
+        if (kin != keys) // an odd number of passes ran: the result sits in the double buffers
+        {
+            bool ok = cudaMemcpyAsync(keys, kin, n * sizeof(K), cudaMemcpyDeviceToDevice, stream) == cudaSuccess;
+            if (values)
+            {
+                ok = ok && cudaMemcpyAsync(values, vin, n * sizeof(uint32_t), cudaMemcpyDeviceToDevice, stream) ==
+                               cudaSuccess;
+            }
+            if (!ok)
+            {
+                setLastError("sort_by_key: copy back failed");
+                status = 1;
+            }
         }
     };
     using std::integral_constant;
@@ -483,7 +527,7 @@ int sortByKey(K* keys, uint32_t* values, size_t n, K* keyBuf, uint32_t* valueBuf
     }
     if (status) { return status; }
     CSB_CHECK(cudaGetLastError());
-    // passes is even for both key widths, so the sorted data is back in keys/values
+    // passes is even for both key widths, so the sorted data is back in keys/values (skipped passes: copied back)
     static_assert(Cfg::passes % 2 == 0);
     return 0;
 }
@@ -638,6 +682,19 @@ int sortByKeyIotaU32(uint32_t* keys, uint32_t* values, uint32_t first, size_t n,
 {
     if (n == 1) { return cs_sequence_u32(first, 1, values, stream); }
     return sortByKey<uint32_t>(keys, values, n, keyBuf, valueBuf, tmp, tmpBytes, stream, (long long)first);
+}
+
+//! sort for callers that synchronise the stream anyway: identity passes (a digit place shared by all keys) are skipped
+int sortByKeySkipU64(uint64_t* keys, uint32_t* values, size_t n, uint64_t* keyBuf, uint32_t* valueBuf, void* tmp,
+                     size_t tmpBytes, cudaStream_t stream)
+{
+    return sortByKey<uint64_t>(keys, values, n, keyBuf, valueBuf, tmp, tmpBytes, stream, -1, true);
+}
+
+int sortByKeySkipU32(uint32_t* keys, uint32_t* values, size_t n, uint32_t* keyBuf, uint32_t* valueBuf, void* tmp,
+                     size_t tmpBytes, cudaStream_t stream)
+{
+    return sortByKey<uint32_t>(keys, values, n, keyBuf, valueBuf, tmp, tmpBytes, stream, -1, true);
 }
 
 void setSortVariant(int v)
