@@ -45,13 +45,25 @@ struct DevBuf
     DevBuf() = default;
     DevBuf(const DevBuf&)            = delete;
     DevBuf& operator=(const DevBuf&) = delete;
-    ~DevBuf() { cudaFree(p); }
+    ~DevBuf()
+    {
+        cudaFree(p);
+        for (void* q : retired)
+            cudaFree(q);
+    }
+
+    /*! set once the allocation has been mapped by peer ranks (Comm::sharePointers): a later reallocation must not free
+     *  memory that peers may still have mapped, so the old allocation is parked until the buffer is destroyed (and the
+     *  buffer grows geometrically from then on, which bounds what can be parked) */
+    bool sharedWithPeers{false};
+    std::vector<void*> retired;
 
     //! grow to m elements; keeps the first min(n, m) elements when keep is set; new elements are zeroed when zeroNew
     int resize(size_t m, cudaStream_t s, bool keep = false, bool zeroNew = false, double growth = 1.05)
     {
         if (m > cap)
         {
+            if (sharedWithPeers) { growth = std::max(growth, 1.5); }
             size_t newCap = std::max<size_t>(size_t(double(m) * growth), 64);
             E* q          = nullptr;
             CSB_CHECK(cudaMalloc(&q, newCap * sizeof(E)));
@@ -59,7 +71,8 @@ struct DevBuf
             if (p)
             {
                 CSB_CHECK(cudaStreamSynchronize(s));
-                CSB_CHECK(cudaFree(p));
+                if (sharedWithPeers) { retired.push_back(p); }
+                else { CSB_CHECK(cudaFree(p)); }
             }
             p   = q;
             cap = newCap;
@@ -73,6 +86,8 @@ struct DevBuf
         std::swap(p, o.p);
         std::swap(cap, o.cap);
         std::swap(n, o.n);
+        std::swap(sharedWithPeers, o.sharedWithPeers);
+        retired.swap(o.retired);
     }
 };
 
@@ -1299,6 +1314,7 @@ private:
             void* mine[4] = {x_.p, y_.p, z_.p, h_.p};
             std::vector<void*> peers;
             std::vector<uint64_t> recvStarts;
+            x_.sharedWithPeers = y_.sharedWithPeers = z_.sharedWithPeers = h_.sharedWithPeers = true;
             int st = comm.sharePointers(mine, 4, uint64_t(recvStart), peers, recvStarts, s);
             if (st == 2) { peerPush_ = false; }
             else if (st != 0) { return st; }

@@ -5,6 +5,7 @@
  * Integer-only: bit-exact.
  */
 #include "common.cuh"
+#include "cstone_b200.h"
 #include "focus.cuh"
 
 namespace csb
@@ -499,3 +500,47 @@ template int minMaxPartials<float>(const float*, size_t, float*, int, cudaStream
 template int minMaxPartials<double>(const double*, size_t, double*, int, cudaStream_t);
 
 } // namespace csb
+
+extern "C"
+{
+
+/* rebalanceDecisionEssentialGpu / protectAncestorsGpu / enforceKeysGpu (focus/rebalance_gpu.h:27-79); the host-value
+ * results the reference returns (converged flag, ResolutionStatus) come back through the last pointer argument, which
+ * synchronises the stream exactly as the reference functions do */
+#define CSB_FOCUS_ABI(SFX, K)                                                                                          \
+    int cs_rebalance_decision_essential_##SFX(const K* prefixes, const int* childOffsets, const int* parents,         \
+                                              const uint32_t* counts, const uint8_t* macs, K focusStart, K focusEnd,  \
+                                              uint32_t bucketSize, int* nodeOps, int numNodes, void* stream)          \
+    {                                                                                                                  \
+        return csb::essentialOps<K>(prefixes, childOffsets, parents, counts, macs, focusStart, focusEnd, bucketSize,  \
+                                    nodeOps, numNodes, cudaStream_t(stream));                                          \
+    }                                                                                                                  \
+    int cs_protect_ancestors_##SFX(const K* prefixes, const int* parents, int* nodeOps, int numNodes, int* converged, \
+                                   void* stream)                                                                       \
+    {                                                                                                                  \
+        cudaStream_t s = cudaStream_t(stream);                                                                         \
+        CSB_SCRATCH(flag, int*, s, csb::SCRATCH_A, sizeof(int));                                                       \
+        CSB_CHECK(cudaMemsetAsync(flag, 0, sizeof(int), s));                                                           \
+        if (int e = csb::protectAncestors<K>(prefixes, parents, nodeOps, numNodes, flag, s)) { return e; }            \
+        int changes = 0;                                                                                               \
+        CSB_CHECK(cudaMemcpyAsync(&changes, flag, sizeof(int), cudaMemcpyDeviceToHost, s));                            \
+        CSB_CHECK(cudaStreamSynchronize(s));                                                                           \
+        *converged = changes == 0;                                                                                     \
+        return 0;                                                                                                      \
+    }                                                                                                                  \
+    int cs_enforce_keys_##SFX(const K* keys, int numKeys, const K* prefixes, const int* childOffsets,                 \
+                              const int* parents, int* nodeOps, int* status, void* stream)                            \
+    {                                                                                                                  \
+        cudaStream_t s = cudaStream_t(stream);                                                                         \
+        CSB_SCRATCH(flag, int*, s, csb::SCRATCH_A, sizeof(int));                                                       \
+        CSB_CHECK(cudaMemsetAsync(flag, 0, sizeof(int), s));                                                           \
+        if (int e = csb::enforceKeys<K>(keys, numKeys, prefixes, childOffsets, parents, nodeOps, flag, s)) { return e; } \
+        CSB_CHECK(cudaMemcpyAsync(status, flag, sizeof(int), cudaMemcpyDeviceToHost, s));                              \
+        CSB_CHECK(cudaStreamSynchronize(s));                                                                           \
+        return 0;                                                                                                      \
+    }
+CSB_FOCUS_ABI(u32, uint32_t)
+CSB_FOCUS_ABI(u64, uint64_t)
+#undef CSB_FOCUS_ABI
+
+} // extern "C"

@@ -173,6 +173,26 @@ int cs_find_neighbors_d(const double* x, const double* y, const double* z, const
                         const double* sizes, uint32_t ngmax, uint32_t* neighbors, uint32_t* neighborsCount,
                         void* stream);
 
+/* ---- focus-tree (LET) rebalance decisions: focus/rebalance_gpu.h:27-79 ----
+ * rebalanceDecisionEssentialGpu: nodeOps[numNodes] from node counts and MAC flags of the fully linked tree, for the focus
+ *   [focusStart, focusEnd); protectAncestorsGpu: nodes whose ancestors change are reset, *converged as the reference
+ *   returns it; enforceKeysGpu: makes the mandatory keys resolvable, *status = ResolutionStatus (0 converged,
+ *   1 cancelMerge, 2 rebalance, 3 failed; focus/rebalance.hpp:171-178) */
+int cs_rebalance_decision_essential_u32(const uint32_t* prefixes, const int* childOffsets, const int* parents,
+                                        const uint32_t* counts, const uint8_t* macs, uint32_t focusStart,
+                                        uint32_t focusEnd, uint32_t bucketSize, int* nodeOps, int numNodes, void* stream);
+int cs_rebalance_decision_essential_u64(const uint64_t* prefixes, const int* childOffsets, const int* parents,
+                                        const uint32_t* counts, const uint8_t* macs, uint64_t focusStart,
+                                        uint64_t focusEnd, uint32_t bucketSize, int* nodeOps, int numNodes, void* stream);
+int cs_protect_ancestors_u32(const uint32_t* prefixes, const int* parents, int* nodeOps, int numNodes, int* converged,
+                             void* stream);
+int cs_protect_ancestors_u64(const uint64_t* prefixes, const int* parents, int* nodeOps, int numNodes, int* converged,
+                             void* stream);
+int cs_enforce_keys_u32(const uint32_t* keys, int numKeys, const uint32_t* prefixes, const int* childOffsets,
+                        const int* parents, int* nodeOps, int* status, void* stream);
+int cs_enforce_keys_u64(const uint64_t* keys, int numKeys, const uint64_t* prefixes, const int* childOffsets,
+                        const int* parents, int* nodeOps, int* status, void* stream);
+
 /* ---- host-side SFC domain decomposition (no device work; identical on every rank) ----
  * uniformBins (domain/domaindecomp.hpp:33-55): bins[numBins+1] leaf indices with ~equal particle sums, binCounts[numBins] */
 int cs_uniform_bins(const uint32_t* counts, size_t numCounts, int numBins, int* bins, uint32_t* binCounts);
