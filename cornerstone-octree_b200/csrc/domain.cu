@@ -401,7 +401,8 @@ public:
             CSB_TRY(ordering_.resize(exchangeSize, s, true));
             BufferDescription o1e{start_, end_, exchangeSize};
             const LocalIndex recvStart = receiveStart(o1e, numRecv);
-            CSB_TRY(exchangeParticles(sendIdx, recvStart, numRecv, s));
+            std::vector<uint32_t> recvCounts;
+            CSB_TRY(exchangeParticles(sendIdx, recvStart, numRecv, recvCounts, s));
             phase("exchangeParticles", s);
             assignedEnvelope(o1e, numRecv, &envStart, &envEnd);
             bufSize_ = exchangeSize;
@@ -426,7 +427,27 @@ public:
                 CSB_TRY(keysDispatch(0, x_.p + recvStart, y_.p + recvStart, z_.p + recvStart,
                                      assignedKeys_.p + offRecv, numRecv, lim_, bnd_, s));
                 CSB_TRY(cs_sequence_u32(recvStart, numRecv, assignedOrder_.p + offRecv, s));
-                CSB_TRY(sortPairs(assignedKeys_.p, assignedOrder_.p, numAssigned, s));
+                // the present particles and the block of every source rank are sorted runs: a stable merge in buffer
+                // order equals the stable sort (merge.cu)
+                {
+                    std::vector<size_t> runs{0};
+                    if (!recvFirst) { runs.push_back(numPresent); }
+                    for (int r = 0; r < P; ++r)
+                        runs.push_back(runs.back() + recvCounts[r]);
+                    if (recvFirst) { runs.push_back(runs.back() + numPresent); }
+                    CSB_REQUIRE(runs.back() == size_t(numAssigned), "merge runs do not cover the assigned particles");
+                    CSB_TRY(keyBuf_.resize(std::max<size_t>(numAssigned, 1), s));
+                    CSB_TRY(valueBuf_.resize(std::max<size_t>(numAssigned, 1), s));
+                    if (std::getenv("CSB_SORT_RECEIVED"))
+                    {
+                        CSB_TRY(sortPairs(assignedKeys_.p, assignedOrder_.p, numAssigned, s));
+                    }
+                    else
+                    {
+                        CSB_TRY(mergeSortedRuns<K>(assignedKeys_.p, assignedOrder_.p, runs.data(), int(runs.size()) - 1,
+                                                   keyBuf_.p, valueBuf_.p, s));
+                    }
+                }
                 keyView   = assignedKeys_.p;
                 orderView = assignedOrder_.p;
             }
@@ -1294,7 +1315,8 @@ private:
      *  particle arrays at [recvStart, recvStart + numRecv), sources in ascending rank order (the reference takes
      *  them in arrival order, domaindecomp_mpi.hpp:116-140; the stable key sort that follows makes the final order
      *  independent of it for distinct keys).  Keys are not sent, the receiver recomputes them (assignment.hpp:197). */
-    int exchangeParticles(const std::vector<uint32_t>& sendIdx, LocalIndex recvStart, LocalIndex numRecv, cudaStream_t s)
+    int exchangeParticles(const std::vector<uint32_t>& sendIdx, LocalIndex recvStart, LocalIndex numRecv,
+                          std::vector<uint32_t>& recvCounts, cudaStream_t s)
     {
         Comm& comm   = *comm_;
         const int P  = comm.size();
@@ -1304,6 +1326,9 @@ private:
         for (int r = 0; r < P; ++r)
             sendCounts[r] = r == me ? 0 : sendIdx[r + 1] - sendIdx[r];
         CSB_TRY(comm.allgatherHost(sendCounts.data(), P * sizeof(uint32_t), allCounts.data(), s));
+        recvCounts.assign(P, 0);
+        for (int r = 0; r < P; ++r)
+            if (r != me) { recvCounts[r] = allCounts[size_t(r) * P + me]; }
 
         /* Peer-memory path: the pack kernel of every destination gathers through the ordering and stores straight into
          * the destination rank's particle arrays over NVLink (CUDA IPC mappings, cached) - pack and transfer are one

@@ -109,6 +109,11 @@ int upsweepSum(int maxLevel, const int* levelRangeHost, const int* childOffsets,
 size_t buildOctreeTempBytesU32(int numLeaves);
 size_t buildOctreeTempBytesU64(int numLeaves);
 
+/* merge.cu */
+template<class K>
+int mergeSortedRuns(K* keys, uint32_t* vals, const size_t* runOffsets, int numRuns, K* keyBuf, uint32_t* valBuf,
+                    cudaStream_t s);
+
 /* sort.cu */
 int sortByKeyU64(uint64_t*, uint32_t*, size_t, uint64_t*, uint32_t*, void*, size_t, cudaStream_t);
 int sortByKeyU32(uint32_t*, uint32_t*, size_t, uint32_t*, uint32_t*, void*, size_t, cudaStream_t);

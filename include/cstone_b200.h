@@ -193,6 +193,15 @@ int cs_enforce_keys_u32(const uint32_t* keys, int numKeys, const uint32_t* prefi
 int cs_enforce_keys_u64(const uint64_t* keys, int numKeys, const uint64_t* prefixes, const int* childOffsets,
                         const int* parents, int* nodeOps, int* status, void* stream);
 
+/* ---- stable merge of sorted runs: what the second sortByKey of GlobalAssignment::distribute (domain/assignment.hpp:197-201)
+ *      amounts to when the present particles and the block of every source rank are already sorted.  runOffsets is a
+ *      HOST array of numRuns + 1 element offsets; keyBuf / valueBuf are double buffers of runOffsets[numRuns] elements.
+ *      Equal keys keep run order, then their order inside the run (= std::stable_sort of the concatenation). */
+int cs_merge_sorted_runs_u32(uint32_t* keys, uint32_t* values, const size_t* runOffsets, int numRuns, uint32_t* keyBuf,
+                             uint32_t* valueBuf, void* stream);
+int cs_merge_sorted_runs_u64(uint64_t* keys, uint32_t* values, const size_t* runOffsets, int numRuns, uint64_t* keyBuf,
+                             uint32_t* valueBuf, void* stream);
+
 /* ---- host-side SFC domain decomposition (no device work; identical on every rank) ----
  * uniformBins (domain/domaindecomp.hpp:33-55): bins[numBins+1] leaf indices with ~equal particle sums, binCounts[numBins] */
 int cs_uniform_bins(const uint32_t* counts, size_t numCounts, int numBins, int* bins, uint32_t* binCounts);

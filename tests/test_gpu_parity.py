@@ -410,3 +410,31 @@ def test_full_size_keys_and_sort_properties():
     assert bool((o64[1:][eq] > o64[:-1][eq]).all())
     xs = capi().gather(order, x)
     assert bool((xs == x[o64]).all())
+
+
+@pytest.mark.parametrize("kt", ["u32", "u64"])
+@pytest.mark.parametrize("run_sizes", [[5, 0, 7], [4096, 4096], [1, 100000, 3, 0, 77777], [50000] * 8, [12345, 1],
+                                       [300000, 200000, 100000]])
+def test_merge_sorted_runs_equals_stable_sort(kt, run_sizes):
+    """cs_merge_sorted_runs_*: the stable merge of sorted runs is the stable sort of their concatenation (what the
+    reference's second sortByKey computes, domain/assignment.hpp:197-201); few distinct keys force ties across runs"""
+    import ctypes as C
+    from cstone_b200 import capi
+    np_t = np.uint32 if kt == "u32" else np.uint64
+    torch_t = torch.uint32 if kt == "u32" else torch.uint64
+    rng = np.random.default_rng(5)
+    runs = [np.sort(rng.integers(0, 1000 if i % 2 else 1 << 28, size=n).astype(np_t)) for i, n in enumerate(run_sizes)]
+    keys = np.concatenate(runs) if runs else np.zeros(0, np_t)
+    n = keys.size
+    vals = rng.permutation(n).astype(np.uint32)
+    order = np.argsort(keys, kind="stable")
+    offsets = (C.c_size_t * (len(run_sizes) + 1))(*np.concatenate([[0], np.cumsum(run_sizes)]).tolist())
+    dk = torch.from_numpy(keys.view(np.int32 if kt == "u32" else np.int64)).to(DEV).view(torch_t)
+    dv = torch.from_numpy(vals.view(np.int32)).to(DEV).view(torch.uint32)
+    kb, vb = torch.empty_like(dk), torch.empty_like(dv)
+    f = getattr(capi.lib(), "cs_merge_sorted_runs_" + kt)
+    capi._check(f(capi._ptr(dk), capi._ptr(dv), offsets, C.c_int(len(run_sizes)), capi._ptr(kb), capi._ptr(vb),
+                  capi._stream()), "merge")
+    torch.cuda.synchronize()
+    assert np.array_equal(dk.cpu().view(torch.int32 if kt == "u32" else torch.int64).numpy().view(np_t), keys[order])
+    assert np.array_equal(dv.cpu().view(torch.int32).numpy().view(np.uint32), vals[order])
