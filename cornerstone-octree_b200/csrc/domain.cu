@@ -442,6 +442,16 @@ public:
                     {
                         CSB_TRY(sortPairs(assignedKeys_.p, assignedOrder_.p, numAssigned, s));
                     }
+                    else if (numPresent > numRecv)
+                    {
+                        // steady state, few particles migrate: merge the small received runs among themselves first,
+                        // the large present run then takes part in a single round instead of log2(P)
+                        const size_t firstRecv = recvFirst ? 0 : 1;
+                        CSB_TRY(mergeSortedRuns<K>(assignedKeys_.p, assignedOrder_.p, runs.data() + firstRecv, P,
+                                                   keyBuf_.p, valueBuf_.p, s));
+                        const size_t two[3] = {0, recvFirst ? size_t(numRecv) : size_t(numPresent), size_t(numAssigned)};
+                        CSB_TRY(mergeSortedRuns<K>(assignedKeys_.p, assignedOrder_.p, two, 2, keyBuf_.p, valueBuf_.p, s));
+                    }
                     else
                     {
                         CSB_TRY(mergeSortedRuns<K>(assignedKeys_.p, assignedOrder_.p, runs.data(), int(runs.size()) - 1,
