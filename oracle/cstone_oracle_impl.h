@@ -485,6 +485,144 @@ static void KS(orc_single_traversal)(
     }
 }
 
+
+/* ---------------------------------------------------------------- focus-tree (LET) rebalance decisions */
+
+/* sfc/common.hpp:369-386 lastNzPlace, makePrefix */
+static inline int KS(orc_last_nz_place)(KEY x)
+{
+    if (!x) return MAXLEVEL;
+    int ctz = 0;
+    while (((x >> ctz) & 1u) == 0)
+        ++ctz;
+    return MAXLEVEL - ctz / 3;
+}
+
+static inline KEY KS(orc_make_prefix)(KEY a)
+{
+    if (a == 0) return 1;
+    return KS(orc_encode_placeholder)(a, 3 * KS(orc_last_nz_place)(a));
+}
+
+/* tree/octree.hpp:198-216 containingNode */
+static int KS(orc_containing_node)(KEY nodeKey, const KEY* prefixes, const int* childOffsets)
+{
+    int nodeLevel = (int)(KS(orc_decode_prefix_length)(nodeKey) / 3);
+    KEY key       = KS(orc_decode_placeholder)(nodeKey);
+    int ret       = 0;
+    for (int i = 1; i <= nodeLevel; ++i)
+    {
+        if (childOffsets[ret] == 0 || nodeKey == prefixes[ret]) break;
+        ret = childOffsets[ret] + (int)KS(orc_octal_digit)(key, (unsigned)i);
+    }
+    return ret;
+}
+
+/* focus/rebalance.hpp:31-74 mergeCountAndMacOp (overlapTwoRanges: traversal/boxoverlap.hpp:26-30) */
+static int KS(orc_merge_count_and_mac_op)(int nodeIdx, const KEY* nodeKeys, const int* childOffsets, const int* parents,
+                                          const unsigned* counts, const uint8_t* macs, KEY focusStart, KEY focusEnd,
+                                          unsigned bucketSize)
+{
+    int siblingGroup = (nodeIdx - 1) / 8;
+    int parent       = nodeIdx ? parents[siblingGroup] : 0;
+    KEY nodeKey      = nodeKeys[nodeIdx];
+    unsigned level   = KS(orc_decode_prefix_length)(nodeKey) / 3;
+    if (nodeIdx)
+    {
+        int countMerge    = counts[parent] <= bucketSize;
+        int macMerge      = macs[parent] == 0;
+        KEY firstGroupKey = KS(orc_decode_placeholder)(nodeKeys[parent]);
+        KEY lastGroupKey  = firstGroupKey + 8 * KS(orc_node_range)(level);
+        int inFringe      = lastGroupKey > focusStart && focusEnd > firstGroupKey;
+        if (countMerge || (macMerge && !inFringe)) return 0;
+    }
+    KEY nodeStart = KS(orc_decode_placeholder)(nodeKey);
+    int isLeaf    = childOffsets[nodeIdx] == 0;
+    int inFocus   = nodeStart >= focusStart && nodeStart < focusEnd;
+    if (isLeaf && (macs[nodeIdx] || inFocus))
+    {
+        if (level + 3 < MAXLEVEL && counts[nodeIdx] > 4096 * bucketSize) return 4096;
+        if (level + 2 < MAXLEVEL && counts[nodeIdx] > 512 * bucketSize) return 512;
+        if (level + 1 < MAXLEVEL && counts[nodeIdx] > 64 * bucketSize) return 64;
+        if (level < MAXLEVEL && counts[nodeIdx] > bucketSize) return 8;
+    }
+    return 1;
+}
+
+/* focus/rebalance.hpp:138-156 rebalanceDecisionEssential */
+void KS(orc_rebalance_decision_essential)(const KEY* nodeKeys, int numNodes, const int* childOffsets, const int* parents,
+                                          const unsigned* counts, const uint8_t* macs, KEY focusStart, KEY focusEnd,
+                                          unsigned bucketSize, int* nodeOps)
+{
+    for (int i = 0; i < numNodes; ++i)
+        nodeOps[i] = KS(orc_merge_count_and_mac_op)(i, nodeKeys, childOffsets, parents, counts, macs, focusStart,
+                                                    focusEnd, bucketSize);
+}
+
+/* focus/rebalance.hpp:91-116 nzAncestorOp, :158-172 protectAncestors (in place, ascending node index - parents have
+ * smaller indices than their children, so the serial order is one of the orders the reference's parallel loop allows) */
+int KS(orc_protect_ancestors)(const KEY* nodeKeys, int numNodes, const int* parents, int* nodeOps)
+{
+    int numChanges = 0;
+    for (int i = 0; i < numNodes; ++i)
+    {
+        int decision;
+        if (i == 0) decision = nodeOps[0];
+        else
+        {
+            int a = i;
+            while (nodeOps[a] == 0)
+                a = parents[(a - 1) / 8];
+            decision = KS(orc_decode_placeholder)(nodeKeys[i]) == KS(orc_decode_placeholder)(nodeKeys[a]) ? nodeOps[a] : 0;
+        }
+        if (decision != 1) numChanges++;
+        nodeOps[i] = decision;
+    }
+    return numChanges == 0;
+}
+
+/* focus/rebalance.hpp:174-252 enforceKeySingle + enforceKeys; returns the ResolutionStatus
+ * (0 converged, 1 cancelMerge, 2 rebalance, 3 failed) */
+int KS(orc_enforce_keys)(const KEY* mandatoryKeys, int numKeys, const KEY* nodeKeys, const int* childOffsets,
+                         const int* parents, int* nodeOps)
+{
+    int status = 0;
+    for (int k = 0; k < numKeys; ++k)
+    {
+        KEY key = mandatoryKeys[k];
+        if (key == 0 || key == NODE_RANGE0) continue;
+        int st            = 0;
+        KEY nodeKeyWant   = KS(orc_make_prefix)(key);
+        int nodeIdx       = KS(orc_containing_node)(nodeKeyWant, nodeKeys, childOffsets);
+        KEY nodeKeyHave   = nodeKeys[nodeIdx];
+        int nodeLevelHave = (int)(KS(orc_decode_prefix_length)(nodeKeyHave) / 3);
+        int trySplit      = nodeKeyHave != nodeKeyWant && nodeLevelHave < MAXLEVEL;
+        int undoMerges    = nodeOps[nodeIdx] == 0 || trySplit;
+        if (undoMerges && nodeIdx > 0)
+        {
+            st         = 1;
+            int parent = nodeIdx;
+            do
+            {
+                parent           = parents[(parent - 1) / 8];
+                int firstSibling = childOffsets[parent];
+                for (int i = firstSibling; i < firstSibling + 8; ++i)
+                    if (nodeOps[i] == 0) nodeOps[i] = 1;
+            } while (parent != 0);
+        }
+        if (trySplit)
+        {
+            int levelDiff = KS(orc_last_nz_place)(key) - nodeLevelHave;
+            st            = levelDiff > 1 ? 3 : 2;
+            if (levelDiff > 1) levelDiff = 1;
+            int op = 1 << (3 * levelDiff);
+            if (op > nodeOps[nodeIdx]) nodeOps[nodeIdx] = op;
+        }
+        if (st > status) status = st;
+    }
+    return status;
+}
+
 #endif /* ORC_EMIT_KEY */
 
 /* ====================================================================================================== */

@@ -8,6 +8,8 @@ import numpy as np
 import pytest
 import torch
 
+from _focus_vectors import ENFORCE_CASES, ESSENTIAL_CASES, decode_placeholder, octree_maker
+
 pytestmark = pytest.mark.gpu
 DEV = "cuda:0"
 KEYS = {"u32": (np.uint32, torch.uint32, 10), "u64": (np.uint64, torch.uint64, 21)}
@@ -16,22 +18,6 @@ KEYS = {"u32": (np.uint32, torch.uint32, 10), "u64": (np.uint64, torch.uint64, 2
 def capi():
     from cstone_b200 import capi as c
     return c
-
-
-def octree_maker(kt, *paths):
-    """OctreeMaker (test/coord_samples... tree/cs_util.hpp:65-140): divide the node addressed by a path of octants"""
-    np_t, _, max_level = KEYS[kt]
-    leaves = [0, 1 << (3 * max_level)]
-    for path in paths:
-        key, level = 0, 0
-        for digit in path:
-            level += 1
-            key += digit << (3 * (max_level - level))
-        i = leaves.index(key)
-        size = 1 << (3 * (max_level - level))
-        assert leaves[i + 1] - key == size, "node to divide is not a leaf"
-        leaves[i + 1:i + 1] = [key + s * (size // 8) for s in range(1, 8)]
-    return np.array(leaves, dtype=np_t)
 
 
 def linked(kt, cstree):
@@ -69,36 +55,6 @@ def node_ops_essential(kt, tree, cstree, leaf_counts, leaf_macs, focus, bucket, 
     return ops[l2i].cpu().tolist(), bool(conv.value)
 
 
-# (divisions, leaf counts, leaf macs, internal macs {prefix: mac}, focus leaf indices, expected leaf ops, converged)
-ESSENTIAL_CASES = [
-    (((), (0,), (7,)),
-     [1, 1, 1, 2, 1, 1, 1, 1, 1, 1, 2, 1, 1, 1, 0, 0, 0, 0, 0, 0, 0, 0],
-     [0, 0, 1, 0, 1, 1, 1, 1, 1, 0, 1, 1, 1, 1, 1, 0, 0, 0, 0, 0, 0, 0],
-     [(1, 1), (0o10, 1), (0o17, 1)], (0, 8),
-     [1, 1, 1, 8, 1, 1, 1, 1, 1, 1, 8, 1, 1, 1, 1, 0, 0, 0, 0, 0, 0, 0], False),
-    (((), (0,), (7,)),
-     [1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 0, 0, 2, 1, 0, 0, 0, 0],
-     [0, 0, 1, 1, 1, 1, 1, 1, 1, 0, 1, 1, 1, 1, 0, 0, 0, 0, 0, 0, 0, 0],
-     [(1, 1), (0o10, 1), (0o17, 1)], (0, 8),
-     [1] * 22, True),
-    (((), (0,), (7,)),
-     [1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 0, 0, 2, 1, 0, 0, 0, 0],
-     [0, 0, 1, 1, 1, 1, 1, 1, 1, 0, 1, 1, 1, 1, 0, 0, 0, 0, 0, 0, 0, 0],
-     [(1, 1), (0o10, 1), (0o17, 0)], (0, 8),
-     [1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 0, 0, 0, 0, 0, 0, 0], False),
-    (((), (0,), (1,)),
-     [1, 2, 1, 1, 1, 1, 1, 1, 1, 1, 0, 0, 1, 1, 2, 1, 2, 1, 1, 2, 1, 1],
-     [0, 1, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 1, 0, 0, 0, 0, 0],
-     [(1, 1), (0o10, 1), (0o11, 0)], (2, 10),
-     [1, 8, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 8, 1, 1, 1, 1, 1], False),
-    (((), (6,), (7,)),
-     [1] * 22,
-     [1, 1, 1, 1, 1, 1, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0],
-     [(1, 1), (0o16, 0), (0o17, 0)], (14, 22),
-     [1, 1, 1, 1, 1, 1, 1, 0, 0, 0, 0, 0, 0, 0, 1, 1, 1, 1, 1, 1, 1, 1], False),
-]
-
-
 @pytest.mark.parametrize("kt", ["u32", "u64"])
 @pytest.mark.parametrize("case", range(len(ESSENTIAL_CASES)))
 def test_rebalance_decision_essential_vectors(kt, case):
@@ -109,11 +65,6 @@ def test_rebalance_decision_essential_vectors(kt, case):
     got, conv = node_ops_essential(kt, tree, cstree, counts, macs, focus, 1, imacs)
     assert got == want
     assert conv == want_conv
-
-
-def decode_placeholder(code, max_level):
-    length = code.bit_length() - 1
-    return (code ^ (1 << length)) << (3 * max_level - length)
 
 
 def enforce(kt, tree, ops, code):
@@ -128,34 +79,87 @@ def enforce(kt, tree, ops, code):
     return status.value
 
 
-CANCEL_MERGE, REBALANCE, FAILED = 1, 2, 3
+@pytest.mark.parametrize("kt", ["u32", "u64"])
+@pytest.mark.parametrize("case", range(len(ENFORCE_CASES)))
+def test_key_enforcement_vectors(kt, case):
+    """test/unit/focus/octree_focus.cpp:228-290: node ops of the 17-node tree divide().divide(1)"""
+    c = capi()
+    start, codes, statuses, protect, want = ENFORCE_CASES[case]
+    tree = linked(kt, octree_maker(kt, (), (1,)))
+    assert tree.num_nodes == 17
+    ops = torch.tensor(start, dtype=torch.int32, device=DEV)
+    for code, status in zip(codes, statuses):
+        assert enforce(kt, tree, ops, code) == status
+    if protect:
+        conv = C.c_int(-1)
+        c._check(getattr(c.lib(), "cs_protect_ancestors_" + kt)(c._ptr(tree.prefixes), c._ptr(tree.parents),
+                                                                c._ptr(ops), C.c_int(17), C.byref(conv), c._stream()),
+                 "protect")
+    assert ops.cpu().tolist() == want
 
 
 @pytest.mark.parametrize("kt", ["u32", "u64"])
-def test_key_enforcement_vectors(kt):
-    """test/unit/focus/octree_focus.cpp:228-290: node ops of the 17-node tree divide().divide(1)"""
+@pytest.mark.parametrize("seed", [1, 2])
+def test_rebalance_kernels_equal_oracle_on_random_trees(kt, seed):
+    """rebalanceDecisionEssential, enforceKeys and protectAncestors on a real tree (Gaussian keys, bucket 16) with
+    random MAC flags and a focus in the middle of the curve: node ops, convergence flag and resolution status equal
+    the C restatement of focus/rebalance.hpp in oracle/"""
+    from _libs import oracle
+
     c = capi()
-    cstree = octree_maker(kt, (), (1,))
-    tree = linked(kt, cstree)
-    assert tree.num_nodes == 17
-    start = [1, 1] + [0] * 15
+    orc = oracle()
+    np_t, torch_t, max_level = KEYS[kt]
+    rng = np.random.default_rng(seed)
+    bits = 3 * max_level
+    keys = np.sort(np.clip(rng.normal(0.5, 0.12, 60000), 0, 0.999999) * float(1 << bits)).astype(np_t)
+    leaves, leaf_counts = orc.compute_octree(kt, keys, 16)
+    ot = orc.build_octree(kt, leaves)
+    nn, ni, nl = ot["numNodes"], ot["numInternal"], ot["numLeaves"]
+    l2i = ot["leafToInternal"][ni:]
+    counts = np.zeros(nn, dtype=np.uint32)
+    counts[l2i] = leaf_counts
+    orc._fn("upsweep_counts_" + kt)(ot["levelRange"].ctypes.data_as(C.c_void_p),
+                                    ot["childOffsets"].ctypes.data_as(C.c_void_p), counts.ctypes.data_as(C.c_void_p))
+    macs = (rng.random(nn) < 0.6).astype(np.uint8)
+    focus = (int(leaves[nl // 3]), int(leaves[2 * nl // 3]))
+    bucket = 8  # smaller than the bucket of the tree: splits, merges and stays all occur
+    parents = np.ascontiguousarray(ot["parents"])
+    p_ = lambda a: a.ctypes.data_as(C.c_void_p)  # noqa: E731
+    cast = C.c_uint64 if kt == "u64" else C.c_uint32
 
-    ops = torch.tensor(start, dtype=torch.int32, device=DEV)
-    assert enforce(kt, tree, ops, 0o111) == CANCEL_MERGE
-    assert ops.cpu().tolist() == [1] * 17
+    want = np.zeros(nn, dtype=np.int32)
+    orc._fn("rebalance_decision_essential_" + kt)(p_(ot["prefixes"]), C.c_int(nn), p_(ot["childOffsets"]), p_(parents),
+                                                  p_(counts), p_(macs), cast(focus[0]), cast(focus[1]), C.c_uint(bucket),
+                                                  p_(want))
+    # mandatory keys: leaf boundaries inside the focus (present) and keys one and three levels below a leaf
+    lv = leaves[nl // 3:nl // 3 + 40].astype(np_t)
+    fine1 = (leaves[nl // 2:nl // 2 + 5] + (leaves[nl // 2 + 1:nl // 2 + 6] - leaves[nl // 2:nl // 2 + 5]) // 8).astype(np_t)
+    fine3 = (leaves[nl // 2 + 9:nl // 2 + 12] + 1).astype(np_t)
+    mandatory = np.concatenate([lv, fine1, fine3]).astype(np_t)
+    want_status = orc._fn("enforce_keys_" + kt, C.c_int)(p_(mandatory), C.c_int(mandatory.size), p_(ot["prefixes"]),
+                                                         p_(ot["childOffsets"]), p_(parents), p_(want))
+    want_conv = orc._fn("protect_ancestors_" + kt, C.c_int)(p_(ot["prefixes"]), C.c_int(nn), p_(parents), p_(want))
 
-    ops = torch.tensor(start, dtype=torch.int32, device=DEV)
-    assert enforce(kt, tree, ops, 0o1112) == REBALANCE
-    assert ops.cpu().tolist() == [1] * 10 + [8] + [1] * 6
-
-    ops = torch.tensor(start, dtype=torch.int32, device=DEV)
-    assert enforce(kt, tree, ops, 0o101) == REBALANCE
-    conv = C.c_int(-1)
-    c._check(getattr(c.lib(), "cs_protect_ancestors_" + kt)(c._ptr(tree.prefixes), c._ptr(tree.parents), c._ptr(ops),
-                                                            C.c_int(17), C.byref(conv), c._stream()), "protect")
-    assert ops.cpu().tolist() == [1, 8] + [1] * 8 + [0] * 7
-
-    ops = torch.tensor([1] * 10 + [0] * 7, dtype=torch.int32, device=DEV)
-    assert enforce(kt, tree, ops, 0o101) == REBALANCE
-    assert enforce(kt, tree, ops, 0o1011) == FAILED
-    assert ops.cpu().tolist() == [1, 8] + [1] * 8 + [0] * 7
+    view = np.int32 if kt == "u32" else np.int64
+    tree = linked(kt, leaves)
+    assert np.array_equal(tree.prefixes.cpu().numpy().view(np_t) if False else
+                          tree.prefixes.cpu().view(torch.int32 if kt == "u32" else torch.int64).numpy().view(np_t),
+                          ot["prefixes"])
+    d_counts = torch.from_numpy(counts.view(np.int32)).to(DEV).view(torch.uint32)
+    d_macs = torch.from_numpy(macs).to(DEV)
+    d_keys = torch.from_numpy(mandatory.view(view)).to(DEV).view(torch_t)
+    ops = torch.zeros(nn, dtype=torch.int32, device=DEV)
+    lib = c.lib()
+    c._check(getattr(lib, "cs_rebalance_decision_essential_" + kt)(
+        c._ptr(tree.prefixes), c._ptr(tree.child_offsets), c._ptr(tree.parents), c._ptr(d_counts), c._ptr(d_macs),
+        cast(focus[0]), cast(focus[1]), C.c_uint32(bucket), c._ptr(ops), C.c_int(nn), c._stream()), "essential")
+    status, conv = C.c_int(-1), C.c_int(-1)
+    c._check(getattr(lib, "cs_enforce_keys_" + kt)(c._ptr(d_keys), C.c_int(mandatory.size), c._ptr(tree.prefixes),
+                                                   c._ptr(tree.child_offsets), c._ptr(tree.parents), c._ptr(ops),
+                                                   C.byref(status), c._stream()), "enforce")
+    c._check(getattr(lib, "cs_protect_ancestors_" + kt)(c._ptr(tree.prefixes), c._ptr(tree.parents), c._ptr(ops),
+                                                        C.c_int(nn), C.byref(conv), c._stream()), "protect")
+    assert status.value == want_status
+    assert bool(conv.value) == bool(want_conv)
+    assert np.array_equal(ops.cpu().numpy(), want)
+    assert len(set(want.tolist())) >= 3, "the case must exercise merges, stays and splits"

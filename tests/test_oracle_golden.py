@@ -166,3 +166,67 @@ def test_compute_octree_invariants(kt):  # tree/csarray.cpp:303-348 (random Gaus
         assert counts.max() <= bucket
         ref = np.searchsorted(keys, leaves[1:], side="left") - np.searchsorted(keys, leaves[:-1], side="left")
         assert np.array_equal(counts, ref.astype(np.uint32))
+
+
+# ---------------------------------------------------------------------------------------------- LET rebalance decisions
+from _focus_vectors import ENFORCE_CASES, ESSENTIAL_CASES, decode_placeholder, octree_maker  # noqa: E402
+
+
+def _p(a):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+def _node_arrays(orc, kt, cstree, leaf_counts, leaf_macs, internal_macs):
+    tree = orc.build_octree(kt, cstree)
+    nn, ni = tree["numNodes"], tree["numInternal"]
+    l2i = tree["leafToInternal"][ni:]
+    counts = np.zeros(nn, dtype=np.uint32)
+    counts[l2i] = leaf_counts
+    orc._fn("upsweep_counts_" + kt)(_p(tree["levelRange"]), _p(tree["childOffsets"]), _p(counts))
+    macs = np.zeros(nn, dtype=np.uint8)
+    macs[l2i] = leaf_macs
+    for key, value in internal_macs:
+        (idx,) = np.nonzero(tree["prefixes"] == key)[0]
+        macs[idx] = value
+    return tree, counts, macs, l2i
+
+
+@pytest.mark.parametrize("kt", ["u32", "u64"])
+@pytest.mark.parametrize("case", range(len(ESSENTIAL_CASES)))
+def test_rebalance_decision_essential_vectors(kt, case):
+    """test/unit/focus/octree_focus.cpp:70-186: rebalanceDecisionEssential + protectAncestors, bucketSize 1"""
+    orc = oracle()
+    paths, leaf_counts, leaf_macs, imacs, focus, want, want_conv = ESSENTIAL_CASES[case]
+    cstree = octree_maker(kt, *paths)
+    tree, counts, macs, l2i = _node_arrays(orc, kt, cstree, leaf_counts, leaf_macs, imacs)
+    nn = tree["numNodes"]
+    parents = np.ascontiguousarray(tree["parents"])
+    ops = np.zeros(nn, dtype=np.int32)
+    cast = C.c_uint64 if kt == "u64" else C.c_uint32
+    orc._fn("rebalance_decision_essential_" + kt)(_p(tree["prefixes"]), C.c_int(nn), _p(tree["childOffsets"]),
+                                                  _p(parents), _p(counts), _p(macs), cast(int(cstree[focus[0]])),
+                                                  cast(int(cstree[focus[1]])), C.c_uint(1), _p(ops))
+    conv = orc._fn("protect_ancestors_" + kt, C.c_int)(_p(tree["prefixes"]), C.c_int(nn), _p(parents), _p(ops))
+    assert ops[l2i].tolist() == want
+    assert bool(conv) == want_conv
+
+
+@pytest.mark.parametrize("kt", ["u32", "u64"])
+@pytest.mark.parametrize("case", range(len(ENFORCE_CASES)))
+def test_key_enforcement_vectors(kt, case):
+    """test/unit/focus/octree_focus.cpp:228-290: enforceKeySingle on the 17-node tree divide().divide(1)"""
+    orc = oracle()
+    start, codes, statuses, protect, want = ENFORCE_CASES[case]
+    np_t, max_level = (np.uint32, 10) if kt == "u32" else (np.uint64, 21)
+    tree = orc.build_octree(kt, octree_maker(kt, (), (1,)))
+    assert tree["numNodes"] == 17
+    parents = np.ascontiguousarray(tree["parents"])
+    ops = np.array(start, dtype=np.int32)
+    for code, status in zip(codes, statuses):
+        key = np.array([decode_placeholder(code, max_level)], dtype=np_t)
+        got = orc._fn("enforce_keys_" + kt, C.c_int)(_p(key), C.c_int(1), _p(tree["prefixes"]),
+                                                     _p(tree["childOffsets"]), _p(parents), _p(ops))
+        assert got == status
+    if protect:
+        orc._fn("protect_ancestors_" + kt, C.c_int)(_p(tree["prefixes"]), C.c_int(17), _p(parents), _p(ops))
+    assert ops.tolist() == want
