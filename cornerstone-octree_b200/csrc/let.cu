@@ -6,6 +6,7 @@
  *   - range packing of the halo exchange (halos/gather_halos_gpu.cu:27-58)
  */
 #include "common.cuh"
+#include "cstone_b200.h"
 #include "focus.cuh"
 #include "hilbert.cuh"
 
@@ -711,3 +712,52 @@ template int gatherRanges4<double>(const uint32_t*, const uint32_t*, int, uint32
                                    const double*, const double*, double*, size_t, cudaStream_t);
 
 } // namespace csb
+
+extern "C"
+{
+
+/* extractMarkedElements (domain/layout.hpp:110-141) on the device: the request keys of the leaf range
+ * [firstReqIdx, secondReqIdx) - one (first key, end key) pair per run of consecutive leaves with a non-zero layout
+ * count.  Returns the number of keys written (2 per run), -1 on error, -needed if capacity is too small. */
+#define CSB_EXTRACT_ABI(SFX, K)                                                                                        \
+    long cs_extract_marked_elements_##SFX(const K* leaves, const uint32_t* layout, int numLeaves, int firstReqIdx,    \
+                                          int secondReqIdx, K* out, long capacity, void* stream)                       \
+    {                                                                                                                  \
+        cudaStream_t s = cudaStream_t(stream);                                                                         \
+        if (firstReqIdx < 0 || secondReqIdx > numLeaves || firstReqIdx > secondReqIdx)                                 \
+        {                                                                                                              \
+            csb::setLastError("cs_extract_marked_elements: invalid leaf range");                                       \
+            return -1;                                                                                                 \
+        }                                                                                                              \
+        /* two "ranks": the caller owns nothing, the requested range is the peer's */                                 \
+        const int fa[4] = {0, 0, firstReqIdx, secondReqIdx};                                                           \
+        void* scratchA = csb::scratch(s, csb::SCRATCH_A, (size_t(numLeaves) + 1) * sizeof(uint32_t) + 64);             \
+        void* scratchB = csb::scratch(s, csb::SCRATCH_B, csb::scanTempBytes(size_t(numLeaves) + 1));                    \
+        void* scratchC = csb::scratch(s, csb::SCRATCH_C, 64);                                                          \
+        if (!scratchA || !scratchB || !scratchC) { return -1; }                                                        \
+        uint32_t* starts = static_cast<uint32_t*>(scratchA);                                                           \
+        int* faDev       = static_cast<int*>(scratchC);                                                                \
+        int* status      = faDev + 4;                                                                                  \
+        if (cudaMemcpyAsync(faDev, fa, sizeof(fa), cudaMemcpyHostToDevice, s) != cudaSuccess ||                        \
+            cudaMemsetAsync(status, 0, 2 * sizeof(int), s) != cudaSuccess)                                             \
+        {                                                                                                              \
+            return -1;                                                                                                 \
+        }                                                                                                              \
+        if (csb::haloRunStarts(layout, numLeaves, faDev, 2, 0, 0xFFFFFFFFu, starts, status, s)) { return -1; }         \
+        if (csb::exclusiveScanU32(starts, starts, size_t(numLeaves) + 1, scratchB, s)) { return -1; }                  \
+        uint32_t numRuns = 0;                                                                                          \
+        if (cudaMemcpyAsync(&numRuns, starts + numLeaves, sizeof(uint32_t), cudaMemcpyDeviceToHost, s) != cudaSuccess || \
+            cudaStreamSynchronize(s) != cudaSuccess)                                                                   \
+        {                                                                                                              \
+            return -1;                                                                                                 \
+        }                                                                                                              \
+        if (long(2 * numRuns) > capacity) { return -long(2 * numRuns); }                                               \
+        if (numRuns && csb::haloRequestKeys<K>(layout, numLeaves, faDev, 2, 0, starts, leaves, out, s)) { return -1; } \
+        if (cudaStreamSynchronize(s) != cudaSuccess) { return -1; }                                                    \
+        return long(2 * numRuns);                                                                                      \
+    }
+CSB_EXTRACT_ABI(u32, uint32_t)
+CSB_EXTRACT_ABI(u64, uint64_t)
+#undef CSB_EXTRACT_ABI
+
+} // extern "C"

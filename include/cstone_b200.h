@@ -193,6 +193,14 @@ int cs_enforce_keys_u32(const uint32_t* keys, int numKeys, const uint32_t* prefi
 int cs_enforce_keys_u64(const uint64_t* keys, int numKeys, const uint64_t* prefixes, const int* childOffsets,
                         const int* parents, int* nodeOps, int* status, void* stream);
 
+/* ---- extractMarkedElements (domain/layout.hpp:110-141): request keys of the leaves [firstReqIdx, secondReqIdx) that hold
+ *      halo particles - one (first key, end key) pair per run of consecutive leaves with layout[i+1] > layout[i].
+ *      Returns the number of keys written to `out` (device), -needed if capacity is too small, -1 on error. */
+long cs_extract_marked_elements_u32(const uint32_t* leaves, const uint32_t* layout, int numLeaves, int firstReqIdx,
+                                    int secondReqIdx, uint32_t* out, long capacity, void* stream);
+long cs_extract_marked_elements_u64(const uint64_t* leaves, const uint32_t* layout, int numLeaves, int firstReqIdx,
+                                    int secondReqIdx, uint64_t* out, long capacity, void* stream);
+
 /* ---- stable merge of sorted runs: what the second sortByKey of GlobalAssignment::distribute (domain/assignment.hpp:197-201)
  *      amounts to when the present particles and the block of every source rank are already sorted.  runOffsets is a
  *      HOST array of numRuns + 1 element offsets; keyBuf / valueBuf are double buffers of runOffsets[numRuns] elements.

@@ -438,3 +438,29 @@ def test_merge_sorted_runs_equals_stable_sort(kt, run_sizes):
     torch.cuda.synchronize()
     assert np.array_equal(dk.cpu().view(torch.int32 if kt == "u32" else torch.int64).numpy().view(np_t), keys[order])
     assert np.array_equal(dv.cpu().view(torch.int32).numpy().view(np.uint32), vals[order])
+
+
+@pytest.mark.parametrize("kt", ["u32", "u64"])
+@pytest.mark.parametrize("first,second,want", [(0, 0, []), (0, 3, []), (0, 4, [3, 4]), (0, 5, [3, 5]), (0, 7, [3, 6]),
+                                               (0, 10, [3, 6, 7, 8, 9, 10]), (9, 10, [9, 10])])
+def test_extract_marked_elements_reference_vectors(kt, first, second, want):
+    """test/unit/domain/layout.cpp:60-102: request keys of the leaves marked as halos within an index range (the device
+    version of extractMarkedElements that Halos::exchangeRequests runs per peer)"""
+    import ctypes as C
+    from cstone_b200 import capi
+    np_t = np.uint32 if kt == "u32" else np.uint64
+    torch_t = torch.uint32 if kt == "u32" else torch.uint64
+    view = np.int32 if kt == "u32" else np.int64
+    leaves = torch.from_numpy(np.arange(11, dtype=np_t).view(view)).to(DEV).view(torch_t)
+    layout = torch.from_numpy(np.array([0, 0, 0, 0, 1, 2, 3, 3, 4, 4, 5], dtype=np.uint32).view(np.int32)).to(DEV)
+    out = torch.zeros(16, dtype=torch.int64 if kt == "u64" else torch.int32, device=DEV)
+    f = getattr(capi.lib(), "cs_extract_marked_elements_" + kt)
+    f.restype = C.c_long
+    n = f(capi._ptr(leaves), capi._ptr(layout), C.c_int(10), C.c_int(first), C.c_int(second), capi._ptr(out),
+          C.c_long(16), capi._stream())
+    assert n == len(want), capi.lib().cs_last_error()
+    assert out[:n].cpu().tolist() == want
+    # a buffer that is too small is reported, not overrun
+    if want:
+        assert f(capi._ptr(leaves), capi._ptr(layout), C.c_int(10), C.c_int(first), C.c_int(second), capi._ptr(out),
+                 C.c_long(len(want) - 1), capi._stream()) == -len(want)
