@@ -464,3 +464,25 @@ def test_extract_marked_elements_reference_vectors(kt, first, second, want):
     if want:
         assert f(capi._ptr(leaves), capi._ptr(layout), C.c_int(10), C.c_int(first), C.c_int(second), capi._ptr(out),
                  C.c_long(len(want) - 1), capi._stream()) == -len(want)
+
+
+@pytest.mark.parametrize("combo", ["u32f", "u64f", "u64d"])
+def test_find_halos_flags_21(combo):
+    """test/unit/traversal/discovery.cpp:52-103 on the GPU: 16 leaves + 5 internal nodes are flagged from either half of
+    the 4x4x4 tree, and the flags equal the oracle's"""
+    from cstone_b200 import capi
+    from test_oracle_golden import halo_flags_setup
+
+    orc = oracle()
+    kt, leaves, tree_o, cen_o, siz_o, sc, ss, lim, bnd = halo_flags_setup(orc, combo)
+    T = real_of(combo)
+    torch_t = torch.uint32 if kt == "u32" else torch.uint64
+    d_leaves = torch.from_numpy(leaves.view(np.int32 if kt == "u32" else np.int64)).to(DEV).view(torch_t)
+    tree = capi.Octree(d_leaves)
+    cen, siz = capi.compute_geo_centers(tree.prefixes, torch.float32 if T == np.float32 else torch.float64, lim, bnd)
+    d_sc, d_ss = torch.from_numpy(sc).to(DEV), torch.from_numpy(ss).to(DEV)
+    for first, last in ((0, 32), (32, 64)):
+        flags = capi.find_halos(tree, cen, siz, d_sc, d_ss, lim, bnd, first, last).cpu().numpy()
+        assert int(flags.sum()) == 21
+        want = orc.find_halos(combo, tree_o, cen_o, siz_o, leaves, sc, ss, lim, bnd, first, last)
+        assert np.array_equal(flags, want)

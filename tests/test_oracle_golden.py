@@ -230,3 +230,57 @@ def test_key_enforcement_vectors(kt, case):
     if protect:
         orc._fn("protect_ancestors_" + kt, C.c_int)(_p(tree["prefixes"]), C.c_int(17), _p(parents), _p(ops))
     assert ops.tolist() == want
+
+
+# ---------------------------------------------------------------------------------------------- halo discovery
+def uniform_level_tree(kt, level):
+    np_t, max_level = (np.uint32, 10) if kt == "u32" else (np.uint64, 21)
+    n = 8 ** level
+    step = 1 << (3 * (max_level - level))
+    return (np.arange(n + 1, dtype=np.uint64) * step).astype(np_t)
+
+
+def halo_flags_setup(backend, combo):
+    kt = "u32" if combo.startswith("u32") else "u64"
+    T = np.float32 if combo.endswith("f") else np.float64
+    lim, bnd = (0, 1, 0, 1, 0, 1), (0, 0, 0)
+    leaves = uniform_level_tree(kt, 2)                       # makeUniformNLevelTree(64, 1): 4 x 4 x 4 leaves
+    tree = backend.build_octree(kt, leaves)
+    cen, siz = backend.node_fp_centers(combo, tree["prefixes"], lim, bnd)
+    l2i = tree["leafToInternal"][tree["numInternal"]:]
+    cen3, siz3 = cen.reshape(-1, 3), siz.reshape(-1, 3)
+    sc = np.ascontiguousarray(cen3[l2i]).astype(T)
+    ss = np.ascontiguousarray(siz3[l2i] + T(0.1)).astype(T)  # size of one node is 0.25^3, search radius 0.1
+    return kt, leaves, tree, cen, siz, sc, ss, lim, bnd
+
+
+def all_to_all_flags(tree, leaves, cen, siz, sc, ss, first, last):
+    """findHalosAll2All of test/unit/traversal/discovery.cpp:25-49 for an open box"""
+    cen3, siz3 = cen.reshape(-1, 3), siz.reshape(-1, 3)
+    flags = np.zeros(tree["numNodes"], dtype=np.uint8)
+    max_level = 10 if leaves.dtype == np.uint32 else 21
+    lo, hi = int(leaves[first]), int(leaves[last])
+    for n in range(tree["numNodes"]):
+        p = int(tree["prefixes"][n])
+        length = p.bit_length() - 1
+        k1 = (p ^ (1 << length)) << (3 * max_level - length)
+        k2 = k1 + (1 << (3 * max_level - length))
+        if lo <= k1 and k2 <= hi:
+            continue                                          # sources inside the excluded range do not count
+        for t in range(first, last):
+            if all(abs(cen3[n][d] - sc[t][d]) - siz3[n][d] - ss[t][d] < 0 for d in range(3)):
+                flags[n] = 1
+                break
+    return flags
+
+
+@pytest.mark.parametrize("combo", ["u32f", "u64d"])
+def test_find_halos_flags_21(combo):
+    """test/unit/traversal/discovery.cpp:52-103: the surface between the first and the last 32 leaves of a 4x4x4 tree is
+    16 leaves + 5 internal nodes, from either side, and equals the all-to-all collision search"""
+    orc = oracle()
+    kt, leaves, tree, cen, siz, sc, ss, lim, bnd = halo_flags_setup(orc, combo)
+    for first, last in ((0, 32), (32, 64)):
+        flags = orc.find_halos(combo, tree, cen, siz, leaves, sc, ss, lim, bnd, first, last)
+        assert int(flags.sum()) == 21
+        assert np.array_equal(flags, all_to_all_flags(tree, leaves, cen, siz, sc, ss, first, last))
