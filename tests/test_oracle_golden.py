@@ -284,3 +284,25 @@ def test_find_halos_flags_21(combo):
         flags = orc.find_halos(combo, tree, cen, siz, leaves, sc, ss, lim, bnd, first, last)
         assert int(flags.sum()) == 21
         assert np.array_equal(flags, all_to_all_flags(tree, leaves, cen, siz, sc, ss, first, last))
+
+
+# ---------------------------------------------------------------------------------------------- sort + gather
+@pytest.mark.parametrize("kt", ["u32", "u64"])
+def test_sort_by_key_and_gather_vectors(kt):
+    """test/unit/primitives/gather.cpp:24-67: the ordering that sorts {2,1,5,4} is {1,0,3,2}; sorting
+    {0,50,10,60,...} and gathering a value array through the ordering gives the listed reference"""
+    orc = oracle()
+    K = KEYS[kt]
+    keys = np.array([2, 1, 5, 4], dtype=K)
+    order = np.arange(4, dtype=np.uint32)
+    orc.sort_by_key(kt, keys, order)
+    assert order.tolist() == [1, 0, 3, 2] and keys.tolist() == [1, 2, 4, 5]
+
+    keys = np.array([0, 50, 10, 60, 20, 70, 30, 80, 40, 90], dtype=K)
+    order = np.arange(10, dtype=np.uint32)
+    orc.sort_by_key(kt, keys, order)
+    assert keys.tolist() == [0, 10, 20, 30, 40, 50, 60, 70, 80, 90]
+    values = np.array([-2, -1, 0, 1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 11], dtype=np.float64)
+    probe = values.copy()
+    probe[2:12] = values[2:][order]                           # gatherCpu(ordering, values + 2, probe + 2)
+    assert probe.tolist() == [-2, -1, 0, 2, 4, 6, 8, 1, 3, 5, 7, 9, 10, 11]
