@@ -69,6 +69,15 @@ enum ScratchSlot : int
     type ptr = static_cast<type>(::csb::scratch(stream, slot, bytes));                                                 \
     if (!ptr) { return 1; }
 
+//! experiment knobs (cs_tuning_set; not part of the drop-in surface).  Read once per entry-point call.
+enum TuningKnob : int
+{
+    TUNE_NB_KERNEL = 0, // findNeighbors: 0 = per-candidate loop, 1 = batched bit-mask evaluation
+    TUNE_NB_GROUPS = 1, // findNeighbors target groups: 0 = leaf aligned, 1 = full groups over runs of sibling leaves
+    TUNE_COUNT     = 16
+};
+int tuning(int knob);
+
 inline unsigned iceil(size_t a, size_t b) { return unsigned((a + b - 1) / b); }
 
 /* ------------------------------------------------------------------------------------------------ key traits */

@@ -20,6 +20,9 @@ void setLastError(const std::string& msg)
     g_lastError = msg;
 }
 
+static std::atomic<int> g_tuning[TUNE_COUNT] = {};
+int tuning(int knob) { return (knob >= 0 && knob < TUNE_COUNT) ? g_tuning[knob].load(std::memory_order_relaxed) : 0; }
+
 void countLaunch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
 
 /* Library-owned scratch for entry points that need internal temporaries.  The reference takes these from the
@@ -118,6 +121,14 @@ int cs_version(void) { return 100; }
 int cs_set_l2_fetch_granularity(int bytes)
 {
     CSB_CHECK(cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, size_t(bytes)));
+    return 0;
+}
+
+/* experiment hook: select kernel variants (csb::TuningKnob); the defaults are what the library ships with */
+int cs_tuning_set(int knob, int value)
+{
+    CSB_REQUIRE(knob >= 0 && knob < csb::TUNE_COUNT, "unknown tuning knob");
+    csb::g_tuning[knob].store(value);
     return 0;
 }
 

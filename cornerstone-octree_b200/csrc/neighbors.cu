@@ -17,6 +17,13 @@
  *    walk — truncation at ngmax keeps the same entries — and the distance arithmetic is the reference's, operation by
  *    operation (no FMA contraction; norm2 is the right fold x*x + (y*y + z*z), util/array.hpp:236-240; distanceSq is
  *    (x*x + y*y) + z*z, findneighbors.hpp:33-60).  Self exclusion is by index (j != i) as on the CPU (hazard H2).
+ *  - Candidate evaluation is BATCHED (kernel variant 1): the particles of the visited leaves that survive the warp-level
+ *    cull are appended to a shared-memory buffer that is kept across leaves; whenever 64 are pending, every lane tests
+ *    them against its target with packed two-wide single-precision arithmetic (add/mul/fma.rn.f32x2, IEEE per
+ *    component, so the float search still evaluates the reference's expression bit for bit) and records the outcome as
+ *    one sign bit per candidate in a 64-bit register mask instead of branching or storing per candidate.  A per-lane
+ *    bit mask of the same shape says which buffered candidates come from leaves this lane's own walk reached.  The
+ *    accepted bits are then written out in buffer order, which is ascending particle index.
  */
 #include "common.cuh"
 #include "cstone_b200.h"
@@ -39,11 +46,17 @@ __device__ inline void leafTargets(const uint32_t* __restrict__ layout, int leaf
     if (e < s) { e = s; }
 }
 
-/*! Groups are built per internal node from its leaf children: consecutive sibling leaves are packed greedily into one
- *  group while they hold at most 32 targets together (deep trees have leaves with a handful of particles; a warp per
- *  such leaf would run mostly empty), a leaf with more than 32 targets is cut into ceil(count/32) balanced groups.
+/*! Groups are built per internal node from its leaf children.
+ *  POLICY 0: consecutive sibling leaves are packed greedily into one group while they hold at most 32 targets together
+ *  (deep trees have leaves with a handful of particles; a warp per such leaf would run mostly empty), a leaf with more
+ *  than 32 targets is cut into ceil(count/32) balanced groups: groups never straddle a leaf boundary unless they hold
+ *  whole leaves.
+ *  POLICY 1: every maximal run of consecutive leaf siblings (their particles are contiguous) is cut into
+ *  ceil(total/32) balanced groups regardless of the leaf boundaries inside the run: groups are full (a uniform tree with
+ *  32 particles per leaf gives 8 groups of 32 per parent instead of ~12 of 21), at the price of a slightly larger
+ *  bounding box where a group takes particles from two curve-adjacent leaves.
  *  FILL = false counts the groups that start at each leaf, FILL = true writes them at the scanned offsets. */
-template<bool FILL>
+template<bool FILL, int POLICY>
 __global__ void groupBuildKernel(const int* __restrict__ childOffsets, const int* __restrict__ internalToLeaf,
                                  const uint32_t* __restrict__ layout, int numNodes, uint32_t first, uint32_t last,
                                  uint32_t* __restrict__ groupCounts, const uint32_t* __restrict__ groupOffsets,
@@ -59,10 +72,10 @@ __global__ void groupBuildKernel(const int* __restrict__ childOffsets, const int
         if (!FILL) { groupCounts[leaf] = ng; }
         else
         {
-            uint32_t size = (c + ng - 1) / ng; // balanced split, <= 32
-            uint32_t off  = groupOffsets[leaf];
+            // balanced split: sizes differ by at most one, none is empty, all are <= 32
+            uint32_t off = groupOffsets[leaf];
             for (uint32_t k = 0; k < ng; ++k)
-                groups[off + k] = make_uint2(s + k * size, min(s + (k + 1) * size, e));
+                groups[off + k] = make_uint2(s + uint32_t(uint64_t(k) * c / ng), s + uint32_t(uint64_t(k + 1) * c / ng));
         }
     };
 
@@ -84,7 +97,8 @@ __global__ void groupBuildKernel(const int* __restrict__ childOffsets, const int
     {
         if (packLeaf >= 0)
         {
-            if (!FILL) { groupCounts[packLeaf] = 1; }
+            if (POLICY == 1) { standalone(packLeaf, packStart, packEnd); }
+            else if (!FILL) { groupCounts[packLeaf] = 1; }
             else { groups[groupOffsets[packLeaf]] = make_uint2(packStart, packEnd); }
         }
         packLeaf = -1;
@@ -100,6 +114,19 @@ __global__ void groupBuildKernel(const int* __restrict__ childOffsets, const int
         uint32_t s, e;
         leafTargets(layout, leaf, first, last, s, e);
         if (e == s) { continue; }
+        if (POLICY == 1)
+        {
+            // runs of leaf siblings: contiguous particle ranges are merged, cut into groups when the run ends
+            if (packLeaf >= 0 && packEnd == s) { packEnd = e; }
+            else
+            {
+                flush();
+                packLeaf  = leaf;
+                packStart = s;
+                packEnd   = e;
+            }
+            continue;
+        }
         if (packLeaf >= 0 && packEnd == s && e - packStart <= 32) { packEnd = e; }
         else
         {
@@ -533,6 +560,485 @@ __global__ void __launch_bounds__(NB_THREADS) findNeighborsKernel(const T* __res
     if (valid) { neighborsCount[i - first] = numFound; }
 }
 
+
+/* ---------------------------------------------------------------- batched candidate evaluation (variant 1) */
+
+constexpr int NB_BATCH = 64;            // candidates evaluated per batch (two 32-bit result masks per lane)
+constexpr int NB_CAP   = NB_BATCH + 32; // buffered candidates: a batch plus one more round of staging
+
+struct alignas(16) WarpSharedB
+{
+    float cx[NB_CAP], cy[NB_CAP], cz[NB_CAP]; // relative floats for T = double, the coordinates themselves for T = float
+    uint32_t cj[NB_CAP];                      // particle index
+    float4 geoC[8], geoS[8];
+    uint8_t mask[NB_MAX_DEPTH][32];
+};
+
+__device__ __forceinline__ uint64_t pack2(float lo, float hi)
+{
+    uint64_t r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+    return r;
+}
+__device__ __forceinline__ void unpack2(uint64_t v, uint32_t& lo, uint32_t& hi)
+{
+    asm("mov.b64 {%0, %1}, %2;" : "=r"(lo), "=r"(hi) : "l"(v));
+}
+//! two-wide IEEE single precision (round to nearest even per component): SASS FADD2 / FMUL2 / FFMA2
+__device__ __forceinline__ uint64_t add2(uint64_t a, uint64_t b)
+{
+    uint64_t r;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+__device__ __forceinline__ uint64_t mul2(uint64_t a, uint64_t b)
+{
+    uint64_t r;
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+__device__ __forceinline__ uint64_t fma2(uint64_t a, uint64_t b, uint64_t c)
+{
+    uint64_t r;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+    return r;
+}
+
+/*! Same traversal, pruning state and acceptance arithmetic as findNeighborsKernel; what differs is how the particles
+ *  of the visited leaves are tested (see the file header).  Result masks hold the first candidate of a 32-candidate word
+ *  in bit 31: `m = (m << 1) | sign` per candidate, the sign bit of (s - bound) being the outcome of s < bound for
+ *  non-NaN operands; arithmetic NaNs are the canonical positive NaN and therefore count as "not smaller", which is
+ *  what the comparison gives, and for T = double they end up in the uncertainty band (neither surely inside nor
+ *  surely outside) where the reference's own expression decides. */
+template<class T, bool PBC>
+__global__ void __launch_bounds__(NB_THREADS) findNeighborsBatchedKernel(const T* __restrict__ x,
+                                                                         const T* __restrict__ y,
+                                                                         const T* __restrict__ z,
+                                                                         const T* __restrict__ h,
+                                                                         uint32_t first,
+                                                                         const uint2* __restrict__ groups,
+                                                                         const uint32_t* __restrict__ numGroupsPtr,
+                                                                         Box<T> box,
+                                                                         const int* __restrict__ childOffsets,
+                                                                         const int* __restrict__ parents,
+                                                                         const int* __restrict__ internalToLeaf,
+                                                                         const uint32_t* __restrict__ layout,
+                                                                         const T* __restrict__ centers,
+                                                                         const T* __restrict__ sizes,
+                                                                         uint32_t ngmax,
+                                                                         uint32_t* __restrict__ neighbors,
+                                                                         uint32_t* __restrict__ neighborsCount)
+{
+    constexpr bool Filt = sizeof(T) == 8;
+    __shared__ WarpSharedB shAll[NB_THREADS / 32];
+
+    const unsigned lane   = threadIdx.x & 31;
+    const unsigned ltMask = (1u << lane) - 1u;
+    const size_t warpId   = (size_t(blockIdx.x) * NB_THREADS + threadIdx.x) >> 5;
+    if (warpId >= size_t(*numGroupsPtr)) { return; }
+    WarpSharedB& sh = shAll[threadIdx.x >> 5];
+
+    const uint2 grp  = groups[warpId];
+    const bool valid = grp.x + lane < grp.y;
+    const uint32_t i = valid ? grp.x + lane : grp.y - 1;
+
+    Target<T> t;
+    t.x        = x[i];
+    t.y        = y[i];
+    t.z        = z[i];
+    const T hi = h[i];
+    t.radiusSq = T(4.0) * hi * hi;
+    {
+        bool anyPbc = box.pbc(0) || box.pbc(1) || box.pbc(2);
+        T s         = T(2) * hi;
+        bool inside = (t.x - s >= box.lim[0]) && (t.y - s >= box.lim[2]) && (t.z - s >= box.lim[4]) &&
+                      (t.x + s <= box.lim[1]) && (t.y + s <= box.lim[3]) && (t.z + s <= box.lim[5]);
+        t.usePbc    = PBC && anyPbc && !inside;
+    }
+    const bool warpPbc = PBC && __any_sync(0xffffffffu, t.usePbc);
+
+    const T ox = Filt ? __shfl_sync(0xffffffffu, t.x, 0) : T(0);
+    const T oy = Filt ? __shfl_sync(0xffffffffu, t.y, 0) : T(0);
+    const T oz = Filt ? __shfl_sync(0xffffffffu, t.z, 0) : T(0);
+    const float txf = float(t.x - ox);
+    const float tyf = float(t.y - oy);
+    const float tzf = float(t.z - oz);
+    const float r2f = float(t.radiusSq);
+
+    const float lox = warpMinF(txf), hix = warpMaxF(txf);
+    const float loy = warpMinF(tyf), hiy = warpMaxF(tyf);
+    const float loz = warpMinF(tzf), hiz = warpMaxF(tzf);
+    const float DwT = fmaxf(fmaxf(fmaxf(fabsf(lox), fabsf(hix)), fmaxf(fabsf(loy), fabsf(hiy))),
+                            fmaxf(fabsf(loz), fabsf(hiz)));
+    const float r2max  = warpMaxF(r2f);
+    const float r2bMax = (r2max > 1e-30f) ? r2max * BAND_KB : __int_as_float(0x7f800000);
+
+    float r2a = r2f * BAND_KA, r2b = r2f * BAND_KB;
+    if (!(r2f > 1e-30f))
+    {
+        r2a = -1.0f;
+        r2b = __int_as_float(0x7f800000);
+    }
+    const float Dpair = 1.01f * (DwT + sqrtf(r2max));
+    const float Epair = Dpair * Dpair * 0x1p-29f;
+    const float pairA = fmaf(-Epair, BAND_SA, r2a);
+    const float pairB = fmaf(Epair, BAND_SB, r2b);
+
+    // packed per-lane constants of the batch test: -target, -lower bound, upper bound
+    const uint64_t ntx2 = pack2(-txf, -txf), nty2 = pack2(-tyf, -tyf), ntz2 = pack2(-tzf, -tzf);
+    const uint64_t nA2  = Filt ? pack2(-pairA, -pairA) : pack2(-r2f, -r2f);
+    const uint64_t pB2  = pack2(pairB, pairB);
+    const uint64_t mOne = pack2(-1.0f, -1.0f);
+
+    uint32_t* const row = neighbors + size_t(i - first) * size_t(ngmax);
+    uint32_t numFound   = 0;
+
+    // buffered candidates [0, cnt) and, per lane, which of them lie in leaves this lane's own walk has reached
+    // (bit k of own0/1/2 = buffer position k, 32 + k, 64 + k)
+    uint32_t cnt = 0, own0 = 0, own1 = 0, own2 = 0;
+
+    //! tests buffer entries [base, base + 32) against this lane's target; returns the accepted ones, first entry in bit 31
+    auto evalWord = [&](int base, uint32_t numValid, uint32_t own) -> uint32_t
+    {
+        uint32_t in = 0, ou = 0;
+#pragma unroll
+        for (int q = 0; q < 8; ++q)
+        {
+            const float4 X = *reinterpret_cast<const float4*>(&sh.cx[base + 4 * q]);
+            const float4 Y = *reinterpret_cast<const float4*>(&sh.cy[base + 4 * q]);
+            const float4 Z = *reinterpret_cast<const float4*>(&sh.cz[base + 4 * q]);
+#pragma unroll
+            for (int half = 0; half < 2; ++half)
+            {
+                const uint64_t x2 = half ? pack2(X.z, X.w) : pack2(X.x, X.y);
+                const uint64_t y2 = half ? pack2(Y.z, Y.w) : pack2(Y.x, Y.y);
+                const uint64_t z2 = half ? pack2(Z.z, Z.w) : pack2(Z.x, Z.y);
+                const uint64_t dx = add2(x2, ntx2), dy = add2(y2, nty2), dz = add2(z2, ntz2);
+                uint64_t s;
+                if (Filt)
+                {
+                    s = mul2(dz, dz);
+                    s = fma2(dy, dy, s);
+                    s = fma2(dx, dx, s);
+                }
+                else
+                {
+                    // the reference's float expression (dx*dx + dy*dy) + dz*dz, findneighbors.hpp:33-60
+                    s = add2(add2(mul2(dx, dx), mul2(dy, dy)), mul2(dz, dz));
+                }
+                uint32_t a0, a1;
+                unpack2(add2(s, nA2), a0, a1); // sign set: s < lower bound (T = float: d2 < radiusSq)
+                in = __funnelshift_l(a0, in, 1);
+                in = __funnelshift_l(a1, in, 1);
+                if (Filt)
+                {
+                    uint32_t b0, b1;
+                    unpack2(fma2(s, mOne, pB2), b0, b1); // sign set: s > upper bound
+                    ou = __funnelshift_l(b0, ou, 1);
+                    ou = __funnelshift_l(b1, ou, 1);
+                }
+            }
+        }
+        const uint32_t validMask = numValid >= 32 ? 0xffffffffu : ~(0xffffffffu >> numValid);
+        own                      = __brev(own) & validMask;
+        if (Filt)
+        {
+            // neither surely inside nor surely outside (a shell of relative width 2^-10 around the search sphere, and
+            // every candidate for degenerate magnitudes): the reference's double expression decides
+            uint32_t amb = ~(in | ou) & own;
+            in &= own;
+            if (__any_sync(0xffffffffu, amb != 0))
+            {
+                while (amb)
+                {
+                    const int k        = __clz(int(amb));
+                    const uint32_t bit = 0x80000000u >> k;
+                    amb ^= bit;
+                    if (exactInside(x, y, z, sh.cj[base + k], t.x, t.y, t.z, t.radiusSq)) { in |= bit; }
+                }
+            }
+        }
+        else { in &= own; }
+        return in;
+    };
+
+    auto emit = [&](uint32_t m, int base)
+    {
+        while (m)
+        {
+            const int k = __clz(int(m));
+            m ^= 0x80000000u >> k;
+            const uint32_t j = sh.cj[base + k];
+            if (j != i)
+            {
+                if (numFound < ngmax) { row[numFound] = j; }
+                ++numFound;
+            }
+        }
+    };
+
+    //! evaluate and write out the first min(cnt, 64) buffered candidates, keep the rest
+    auto flush = [&]()
+    {
+        __syncwarp();
+        const uint32_t n = min(cnt, uint32_t(NB_BATCH));
+#pragma unroll 1
+        for (uint32_t w = 0; w * 32 < n; ++w)
+        {
+            const uint32_t in = evalWord(int(w * 32), min(n - w * 32, 32u), w ? own1 : own0);
+            emit(in, int(w * 32));
+        }
+        __syncwarp();
+        if (cnt > NB_BATCH)
+        {
+            const uint32_t rest = cnt - NB_BATCH; // <= 31
+            float a = 0, b = 0, c = 0;
+            uint32_t d = 0;
+            if (lane < rest)
+            {
+                a = sh.cx[NB_BATCH + lane];
+                b = sh.cy[NB_BATCH + lane];
+                c = sh.cz[NB_BATCH + lane];
+                d = sh.cj[NB_BATCH + lane];
+            }
+            __syncwarp();
+            if (lane < rest)
+            {
+                sh.cx[lane] = a;
+                sh.cy[lane] = b;
+                sh.cz[lane] = c;
+                sh.cj[lane] = d;
+            }
+            own0 = own2;
+            cnt  = rest;
+        }
+        else
+        {
+            own0 = 0;
+            cnt  = 0;
+        }
+        own1 = 0;
+        own2 = 0;
+    };
+
+    //! candidates [jb, je) of a leaf; force: evaluate whatever is buffered afterwards (end of the walk)
+    auto scanLeaf = [&](uint32_t jb, uint32_t je, bool mine, bool force)
+    {
+        if (warpPbc)
+        {
+            // warps touching a periodic boundary: the reference expressions on broadcast loads
+            for (uint32_t j = jb; j < je; ++j)
+            {
+                T dx = x[j] - t.x;
+                T dy = y[j] - t.y;
+                T dz = z[j] - t.z;
+                T fx = pbcFold(dx, 0, box);
+                T fy = pbcFold(dy, 1, box);
+                T fz = pbcFold(dz, 2, box);
+                dx   = t.usePbc ? fx : dx;
+                dy   = t.usePbc ? fy : dy;
+                dz   = t.usePbc ? fz : dz;
+                T d2 = dx * dx + dy * dy + dz * dz;
+                if (mine && j != i && d2 < t.radiusSq)
+                {
+                    if (numFound < ngmax) { row[numFound] = j; }
+                    ++numFound;
+                }
+            }
+            return;
+        }
+        for (uint32_t base = jb;; base += 32)
+        {
+            if (base < je)
+            {
+                // append the candidates of this round that some lane can reach (coalesced loads, warp-level cull)
+                const uint32_t j = base + lane;
+                bool keep        = false;
+                float c0 = 0, c1 = 0, c2 = 0;
+                if (j < je)
+                {
+                    c0 = float(x[j] - ox);
+                    c1 = float(y[j] - oy);
+                    c2 = float(z[j] - oz);
+                    float D  = fmaxf(fmaxf(fabsf(c0), fabsf(c1)), fmaxf(fabsf(c2), DwT));
+                    float bc = fmaf(D * D * 0x1p-27f, BAND_SB, r2bMax);
+                    float ex = fmaxf(fmaxf(lox - c0, c0 - hix), 0.0f);
+                    float ey = fmaxf(fmaxf(loy - c1, c1 - hiy), 0.0f);
+                    float ez = fmaxf(fmaxf(loz - c2, c2 - hiz), 0.0f);
+                    keep     = !(fmaf(ex, ex, fmaf(ey, ey, ez * ez)) > bc);
+                }
+                const unsigned km = __ballot_sync(0xffffffffu, keep);
+                if (km != 0)
+                {
+                    if (keep)
+                    {
+                        const uint32_t pos = cnt + __popc(km & ltMask);
+                        sh.cx[pos]         = c0;
+                        sh.cy[pos]         = c1;
+                        sh.cz[pos]         = c2;
+                        sh.cj[pos]         = j;
+                    }
+                    const uint32_t added = __popc(km);                                // 1..32
+                    const uint32_t ones  = mine ? (0xffffffffu >> (32 - added)) : 0u; // ownership of the new entries
+                    const uint32_t sft   = cnt & 31u;
+                    const uint32_t lo    = ones << sft;
+                    const uint32_t up    = __funnelshift_l(ones, 0u, sft); // bits that spill into the next word
+                    if (cnt < 32)
+                    {
+                        own0 |= lo;
+                        own1 |= up;
+                    }
+                    else
+                    {
+                        own1 |= lo;
+                        own2 |= up;
+                    }
+                    cnt += added;
+                }
+            }
+            if (cnt >= NB_BATCH || (force && cnt)) { flush(); }
+            if (base + 32 >= je) { break; }
+        }
+    };
+
+    //! this lane's continuation decisions for the 8 children of an internal node its own walk has entered
+    auto testChildren = [&](int child0, bool mine) -> uint32_t
+    {
+        uint32_t bits = 0;
+        if (warpPbc)
+        {
+            if (mine)
+            {
+#pragma unroll
+                for (int c = 0; c < 8; ++c)
+                    bits |= uint32_t(cellOverlap<PBC>(t, centers, sizes, child0 + c, box)) << c;
+            }
+            return bits;
+        }
+        __syncwarp();
+        bool reach = false;
+        if (lane < 8)
+        {
+            int node = child0 + int(lane);
+            float4 gc, gs;
+            gc.x = float(centers[3 * node] - ox);
+            gc.y = float(centers[3 * node + 1] - oy);
+            gc.z = float(centers[3 * node + 2] - oz);
+            gc.w = 0.0f;
+            gs.x = float(sizes[3 * node]);
+            gs.y = float(sizes[3 * node + 1]);
+            gs.z = float(sizes[3 * node + 2]);
+            float D = fmaxf(fmaxf(fmaxf(fabsf(gc.x), fabsf(gc.y)), fmaxf(fabsf(gc.z), DwT)),
+                            fmaxf(gs.x, fmaxf(gs.y, gs.z)));
+            gs.w          = D * D * 0x1p-27f;
+            sh.geoC[lane] = gc;
+            sh.geoS[lane] = gs;
+            float ex = fmaxf(fmaxf(lox - (gc.x + gs.x), (gc.x - gs.x) - hix), 0.0f);
+            float ey = fmaxf(fmaxf(loy - (gc.y + gs.y), (gc.y - gs.y) - hiy), 0.0f);
+            float ez = fmaxf(fmaxf(loz - (gc.z + gs.z), (gc.z - gs.z) - hiz), 0.0f);
+            reach    = !(fmaf(ex, ex, fmaf(ey, ey, ez * ez)) > fmaf(gs.w, BAND_SB, r2bMax));
+        }
+        const unsigned reachable = __ballot_sync(0xffffffffu, reach);
+        __syncwarp(); // the staged child geometry is visible to all lanes
+        if (mine)
+        {
+#pragma unroll
+            for (int c = 0; c < 8; ++c)
+            {
+                if (!((reachable >> c) & 1u)) { continue; }
+                const float4 gc = sh.geoC[c];
+                const float4 gs = sh.geoS[c];
+                bool pass;
+                if (Filt)
+                {
+                    float dx = fmaxf(fabsf(gc.x - txf) - gs.x, 0.0f);
+                    float dy = fmaxf(fabsf(gc.y - tyf) - gs.y, 0.0f);
+                    float dz = fmaxf(fabsf(gc.z - tzf) - gs.z, 0.0f);
+                    float s2 = fmaf(dx, dx, fmaf(dy, dy, dz * dz));
+                    pass     = s2 < fmaf(-gs.w, BAND_SA, r2a);
+                    if (!pass && !(s2 > fmaf(gs.w, BAND_SB, r2b)))
+                    {
+                        pass = cellOverlap<false>(t, centers, sizes, child0 + c, box);
+                    }
+                }
+                else
+                {
+                    T dx = rabs(T(gc.x) - t.x) - T(gs.x);
+                    T dy = rabs(T(gc.y) - t.y) - T(gs.y);
+                    T dz = rabs(T(gc.z) - t.z) - T(gs.z);
+                    dx += rabs(dx);
+                    dy += rabs(dy);
+                    dz += rabs(dz);
+                    dx *= T(0.5);
+                    dy *= T(0.5);
+                    dz *= T(0.5);
+                    pass = dx * dx + (dy * dy + dz * dz) < t.radiusSq;
+                }
+                bits |= uint32_t(pass) << c;
+            }
+        }
+        return bits;
+    };
+
+    const bool rootMine = valid && cellOverlap<PBC>(t, centers, sizes, 0, box);
+    if (__any_sync(0xffffffffu, rootMine))
+    {
+        // depth-first walk in SFC order over the children that at least one lane enters (as in findNeighborsKernel).
+        // A tree that consists of the root leaf alone is walked as the single "sibling" 0 of a virtual parent, and the
+        // walk ends with one more pass through the leaf code (empty range, force) that evaluates what is still
+        // buffered: scanLeaf is instantiated once.
+        const int rootChild = childOffsets[0];
+        int depth           = 1;
+        int base            = rootChild;
+        uint32_t lm         = rootChild ? testChildren(rootChild, rootMine) : uint32_t(rootMine);
+        sh.mask[1][lane]    = uint8_t(lm);
+        uint32_t wm         = __reduce_or_sync(0xffffffffu, lm);
+        while (true)
+        {
+            uint32_t jb = 0, je = 0;
+            bool mine = false, last = false;
+            if (wm == 0)
+            {
+                if (depth > 1)
+                {
+                    const int up = parents[(base - 1) >> 3];
+                    --depth;
+                    base = ((up - 1) & ~7) + 1;
+                    lm   = sh.mask[depth][lane];
+                    wm   = __reduce_or_sync(0xffffffffu, lm) & ~((2u << ((up - 1) & 7)) - 1u);
+                    continue;
+                }
+                if (cnt == 0) { break; }
+                last = true;
+            }
+            else
+            {
+                const int c = __ffs(int(wm)) - 1;
+                wm &= wm - 1;
+                const int node  = base + c;
+                mine            = (lm >> c) & 1u;
+                const int child = childOffsets[node];
+                if (child != 0)
+                {
+                    ++depth;
+                    lm                   = testChildren(child, mine);
+                    sh.mask[depth][lane] = uint8_t(lm);
+                    wm                   = __reduce_or_sync(0xffffffffu, lm);
+                    base                 = child;
+                    continue;
+                }
+                const int leafIdx = internalToLeaf[node];
+                jb                = layout[leafIdx];
+                je                = layout[leafIdx + 1];
+            }
+            scanLeaf(jb, je, mine, last);
+            if (last) { break; }
+        }
+    }
+
+    if (valid) { neighborsCount[i - first] = numFound; }
+}
+
 } // namespace
 
 template<class T>
@@ -555,27 +1061,24 @@ int findNeighbors(const T* x, const T* y, const T* z, const T* h, uint32_t first
 
     const int numNodes = numLeaves + (numLeaves - 1) / 7;
     CSB_CHECK(cudaMemsetAsync(groupOffsets, 0, (size_t(numLeaves) + 1) * sizeof(uint32_t), s));
-    groupBuildKernel<false><<<iceil(numNodes, 256), 256, 0, s>>>(childOffsets, internalToLeaf, layout, numNodes, first,
-                                                                  last, groupOffsets, nullptr, nullptr);
+    const bool greedy = tuning(TUNE_NB_GROUPS) != 0;
+    auto countKernel  = greedy ? groupBuildKernel<false, 1> : groupBuildKernel<false, 0>;
+    auto fillKernel   = greedy ? groupBuildKernel<true, 1> : groupBuildKernel<true, 0>;
+    countKernel<<<iceil(numNodes, 256), 256, 0, s>>>(childOffsets, internalToLeaf, layout, numNodes, first, last,
+                                                     groupOffsets, nullptr, nullptr);
     CSB_LAUNCH_CHECK();
     if (int e = exclusiveScanU32(groupOffsets, groupOffsets, size_t(numLeaves) + 1, scanTmp, s)) { return e; }
-    groupBuildKernel<true><<<iceil(numNodes, 256), 256, 0, s>>>(childOffsets, internalToLeaf, layout, numNodes, first,
-                                                                 last, nullptr, groupOffsets, groups);
+    fillKernel<<<iceil(numNodes, 256), 256, 0, s>>>(childOffsets, internalToLeaf, layout, numNodes, first, last, nullptr,
+                                                    groupOffsets, groups);
     CSB_LAUNCH_CHECK();
 
-    unsigned grid = iceil(maxGroups * 32, NB_THREADS);
-    if (box.pbc(0) || box.pbc(1) || box.pbc(2))
-    {
-        findNeighborsKernel<T, true><<<grid, NB_THREADS, 0, s>>>(x, y, z, h, first, groups, groupOffsets + numLeaves,
-                                                                 box, childOffsets, parents, internalToLeaf, layout,
-                                                                 centers, sizes, ngmax, neighbors, neighborsCount);
-    }
-    else
-    {
-        findNeighborsKernel<T, false><<<grid, NB_THREADS, 0, s>>>(x, y, z, h, first, groups, groupOffsets + numLeaves,
-                                                                  box, childOffsets, parents, internalToLeaf, layout,
-                                                                  centers, sizes, ngmax, neighbors, neighborsCount);
-    }
+    unsigned grid  = iceil(maxGroups * 32, NB_THREADS);
+    const bool pbc = box.pbc(0) || box.pbc(1) || box.pbc(2);
+    auto kernel    = tuning(TUNE_NB_KERNEL) == 0
+                         ? (pbc ? findNeighborsKernel<T, true> : findNeighborsKernel<T, false>)
+                         : (pbc ? findNeighborsBatchedKernel<T, true> : findNeighborsBatchedKernel<T, false>);
+    kernel<<<grid, NB_THREADS, 0, s>>>(x, y, z, h, first, groups, groupOffsets + numLeaves, box, childOffsets, parents,
+                                       internalToLeaf, layout, centers, sizes, ngmax, neighbors, neighborsCount);
     CSB_LAUNCH_CHECK();
     return 0;
 }

@@ -35,7 +35,16 @@ def lib():
         for name in ("cs_sort_by_key_temp_bytes_u32", "cs_sort_by_key_temp_bytes_u64", "cs_scan_temp_bytes",
                      "cs_build_octree_temp_bytes_u32", "cs_build_octree_temp_bytes_u64", "cs_node_ops_temp_bytes"):
             getattr(_lib, name).restype = C.c_size_t
+        # experiments: CSB_TUNING="knob=value,knob=value" selects kernel variants (csb::TuningKnob) for this process
+        for item in filter(None, os.environ.get("CSB_TUNING", "").split(",")):
+            knob, value = item.split("=")
+            tuning_set(int(knob), int(value))
     return _lib
+
+
+def tuning_set(knob, value):
+    """experiment hook, see csb::TuningKnob in csrc/common.cuh"""
+    _check(_lib.cs_tuning_set(C.c_int(knob), C.c_int(value)), "cs_tuning_set")
 
 
 def _check(status, what):

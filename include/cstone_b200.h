@@ -314,6 +314,9 @@ int cs_domain_download(cs_domain_t* d, void* x, void* y, void* z, void* h, void*
 /* tuning hook: L2 fetch granularity hint in bytes (32, 64, 128) for the current device */
 int cs_set_l2_fetch_granularity(int bytes);
 
+/* experiment hook (not part of the drop-in surface): select a kernel variant, see csb::TuningKnob in csrc/common.cuh */
+int cs_tuning_set(int knob, int value);
+
 #ifdef __cplusplus
 }
 #endif

@@ -31,6 +31,8 @@
 #include "cstone/tree/csarray.hpp"
 #include "cstone/tree/octree.hpp"
 
+#include "coord_samples/plummer.hpp"
+
 using namespace cstone;
 
 namespace
@@ -370,6 +372,279 @@ int domainRun(int P,
     return 0;
 }
 
+/* ------------------------------------------------------------------------------------------------------------------
+ * Bench / full-size parity drivers: the same calls as domainRank, but nothing is copied out.  What comes back are the
+ * wall times of the reference calls and position-weighted wrapping sums ("digests") of every result array, which the
+ * GPU side recomputes from its own arrays: equal digests <=> equal arrays (up to 2^-64 collisions) at sizes where the
+ * arrays themselves (40 GB of neighbour lists at 64 Mi particles) cannot be held twice.  findNeighbors runs in chunks
+ * of `chunk` targets over one reused list buffer.
+ * ---------------------------------------------------------------------------------------------------------------- */
+
+constexpr uint64_t DIGEST_C1 = 0x9E3779B97F4A7C15ull, DIGEST_C2 = 0xC2B2AE3D27D4EB4Full;
+
+template<class E>
+uint64_t bitsOf(E v)
+{
+    if constexpr (sizeof(E) == 8)
+    {
+        uint64_t b;
+        std::memcpy(&b, &v, 8);
+        return b;
+    }
+    else
+    {
+        uint32_t b;
+        std::memcpy(&b, &v, 4);
+        return b;
+    }
+}
+
+//! sum_i bits(a[i]) * (i + 1) mod 2^64
+template<class E>
+uint64_t weightedSum(const E* a, size_t n)
+{
+    uint64_t s = 0;
+#pragma omp parallel for reduction(+ : s) schedule(static)
+    for (size_t i = 0; i < n; ++i)
+        s += bitsOf(a[i]) * uint64_t(i + 1);
+    return s;
+}
+
+struct BenchOut
+{
+    double tSync[4]{};
+    double tNeighbors{0};
+    double tHalos{0};
+    uint64_t digest[24]{};
+};
+std::vector<BenchOut> g_bench;
+
+//! digest slots
+enum
+{
+    DG_KEYS = 0, DG_X, DG_Y, DG_Z, DG_H, DG_LEAVES, DG_NUM_LEAVES, DG_LAYOUT, DG_NC_SUM, DG_LISTS, DG_START, DG_END,
+    DG_SIZE, DG_NUM_NODES, DG_PREFIXES, DG_CHILD_OFFSETS, DG_CENTERS, DG_SIZES, DG_HALO_FLAGS, DG_HALO_COUNT,
+    DG_LEAF_COUNTS
+};
+
+template<class T, class KeyType, class View>
+void neighborsChunked(const T* x, const T* y, const T* z, const T* h, LocalIndex first, LocalIndex last,
+                      const Box<T>& box, const View& view, unsigned ngmax, size_t chunk, double* seconds,
+                      uint64_t* ncSum, uint64_t* listDigest)
+{
+    chunk = std::max<size_t>(1, std::min<size_t>(chunk, last - first));
+    std::vector<LocalIndex> nb(chunk * ngmax);
+    std::vector<unsigned> nc(chunk);
+    double t      = 0;
+    uint64_t sNc  = 0, sList = 0;
+    for (size_t c0 = first; c0 < last; c0 += chunk)
+    {
+        size_t c1 = std::min<size_t>(c0 + chunk, last);
+        auto t0   = std::chrono::steady_clock::now();
+        findNeighbors(x, y, z, h, LocalIndex(c0), LocalIndex(c1), box, view, ngmax, nb.data(), nc.data());
+        auto t1 = std::chrono::steady_clock::now();
+        t += std::chrono::duration<double>(t1 - t0).count();
+#pragma omp parallel for reduction(+ : sNc, sList) schedule(static)
+        for (size_t i = c0; i < c1; ++i)
+        {
+            unsigned cnt = nc[i - c0];
+            sNc += cnt;
+            uint64_t row = uint64_t(i - first + 1) * DIGEST_C1;
+            unsigned m   = std::min(cnt, ngmax);
+            for (unsigned k = 0; k < m; ++k)
+                sList += (uint64_t(nb[(i - c0) * ngmax + k]) + 1) * (row + uint64_t(k + 1) * DIGEST_C2);
+        }
+    }
+    *seconds    = t;
+    *ncSum      = sNc;
+    *listDigest = sList;
+}
+
+template<class KeyType, class T>
+void benchRank(int rank, int P, unsigned bucket, unsigned bucketFocus, float theta, const double* lim, const int* bnd,
+               const T* x0, const T* y0, const T* z0, const T* h0, size_t n, int numSyncs, unsigned ngmax, size_t chunk,
+               int numThreads, int haloQuarter)
+{
+    mpishim::rankRef() = rank;
+    if (numThreads > 0) { omp_set_num_threads(numThreads); }
+    BenchOut& o = g_bench[rank];
+
+    Domain<KeyType, T> domain(execution::cpu, rank, P, bucket, bucketFocus, theta, MPI_COMM_WORLD,
+                              makeBox<T>(lim, bnd));
+    std::vector<T> x(x0, x0 + n), y(y0, y0 + n), z(z0, z0 + n), h(h0, h0 + n);
+    std::vector<KeyType> keys(n);
+    std::vector<T> s1, s2;
+    std::vector<LocalIndex> s3;
+    for (int s = 0; s < numSyncs; ++s)
+    {
+        MPI_Barrier(MPI_COMM_WORLD);
+        auto t0 = std::chrono::steady_clock::now();
+        domain.sync(keys, x, y, z, h, std::tuple{}, std::tie(s1, s2, s3));
+        auto t1 = std::chrono::steady_clock::now();
+        if (s < 4) o.tSync[s] = std::chrono::duration<double>(t1 - t0).count();
+    }
+    uint64_t* d      = o.digest;
+    d[DG_KEYS]       = weightedSum(keys.data(), keys.size());
+    d[DG_X]          = weightedSum(x.data(), x.size());
+    d[DG_Y]          = weightedSum(y.data(), y.size());
+    d[DG_Z]          = weightedSum(z.data(), z.size());
+    d[DG_H]          = weightedSum(h.data(), h.size());
+    auto fl          = domain.focusTree().treeLeaves();
+    d[DG_LEAVES]     = weightedSum(fl.data(), fl.size());
+    d[DG_NUM_LEAVES] = fl.size() - 1;
+    auto lay         = domain.layout();
+    d[DG_LAYOUT]     = weightedSum(lay.data(), lay.size());
+    d[DG_START]      = domain.startIndex();
+    d[DG_END]        = domain.endIndex();
+    d[DG_SIZE]       = x.size();
+    auto ft          = domain.focusTree().octreeViewAcc();
+    d[DG_NUM_NODES]  = ft.numNodes;
+    d[DG_PREFIXES]   = weightedSum(ft.prefixes, ft.numNodes);
+    d[DG_CHILD_OFFSETS] = weightedSum(ft.childOffsets, ft.numNodes);
+    auto gc             = domain.focusTree().geoCentersAcc();
+    auto gs             = domain.focusTree().geoSizesAcc();
+    d[DG_CENTERS]       = weightedSum(reinterpret_cast<const T*>(gc.data()), size_t(3) * ft.numNodes);
+    d[DG_SIZES]         = weightedSum(reinterpret_cast<const T*>(gs.data()), size_t(3) * ft.numNodes);
+    auto lc             = domain.focusTree().leafCountsAcc();
+    d[DG_LEAF_COUNTS]   = weightedSum(lc.data(), lc.size());
+    if (haloQuarter)
+    {
+        // standalone halo discovery like test/performance/octree.cu:110-143: the first quarter of the leaves plays
+        // the assigned range (a single rank has no foreign leaves of its own)
+        TreeNodeIndex nLeaves = TreeNodeIndex(fl.size()) - 1, firstLeaf = 0, lastLeaf = nLeaves / 4;
+        std::vector<Vec3<T>> sc(nLeaves), ss(nLeaves);
+        std::vector<uint8_t> flags(ft.numNodes, 0);
+        auto t0 = std::chrono::steady_clock::now();
+#pragma omp parallel for schedule(static)
+        for (TreeNodeIndex i = firstLeaf; i < lastLeaf; ++i)
+        {
+            Vec3<T> init = gc[ft.leafToInternal[ft.numInternalNodes + i]];
+            std::tie(sc[i], ss[i]) =
+                computeBoundingBox(x.data(), y.data(), z.data(), h.data(), lay[i], lay[i + 1], T(2), init);
+        }
+        findHalos(ft.prefixes, ft.childOffsets, ft.parents, gc.data(), gs.data(), fl.data(), sc.data(), ss.data(),
+                  domain.box(), firstLeaf, lastLeaf, flags.data());
+        auto t1           = std::chrono::steady_clock::now();
+        o.tHalos          = std::chrono::duration<double>(t1 - t0).count();
+        d[DG_HALO_FLAGS]  = weightedSum(flags.data(), flags.size());
+        d[DG_HALO_COUNT]  = std::accumulate(flags.begin(), flags.end(), uint64_t(0));
+    }
+    if (ngmax)
+    {
+        neighborsChunked<T, KeyType>(x.data(), y.data(), z.data(), h.data(), domain.startIndex(), domain.endIndex(),
+                                     domain.box(), domain.octreeProperties(), ngmax, chunk, &o.tNeighbors,
+                                     &d[DG_NC_SUM], &d[DG_LISTS]);
+    }
+}
+
+template<class KeyType, class T>
+int benchRun(int P, unsigned bucket, unsigned bucketFocus, float theta, const double* lim, const int* bnd, const T* x,
+             const T* y, const T* z, const T* h, const uint64_t* offsets, int numSyncs, unsigned ngmax, size_t chunk,
+             int numThreads, int haloQuarter)
+{
+    g_bench.clear();
+    g_bench.resize(P);
+    mpishim::world().reset(P);
+    std::vector<std::thread> threads;
+    for (int r = 0; r < P; ++r)
+    {
+        threads.emplace_back(
+            [&, r]()
+            {
+                try
+                {
+                    benchRank<KeyType, T>(r, P, bucket, bucketFocus, theta, lim, bnd, x + offsets[r], y + offsets[r],
+                                          z + offsets[r], h + offsets[r], offsets[r + 1] - offsets[r], numSyncs, ngmax,
+                                          chunk, numThreads, haloQuarter);
+                }
+                catch (std::exception& e)
+                {
+                    fprintf(stderr, "ref bench rank %d: %s\n", r, e.what());
+                    std::abort();
+                }
+            });
+    }
+    for (auto& t : threads)
+        t.join();
+    mpishim::world().reset(1);
+    mpishim::rankRef() = 0;
+    return 0;
+}
+
+/*! standalone tree build + neighbour search (BASELINE configs[0] / configs[4]): keys of either curve, sort_by_key,
+ *  gather, computeOctree, buildOctreeCpu, node centres decoded with the same curve, findNeighbors in chunks.
+ *  times: [0] keys+sort+gather+tree+link+centres, [1] findNeighbors */
+template<class KeyType, class T>
+int benchTreeNeighbors(int kind, const T* x0, const T* y0, const T* z0, const T* h0, size_t n, unsigned bucket,
+                       const double* lim, const int* bnd, unsigned ngmax, size_t chunk, double* times, uint64_t* d)
+{
+    auto box = makeBox<T>(lim, bnd);
+    std::vector<T> x(x0, x0 + n), y(y0, y0 + n), z(z0, z0 + n), h(h0, h0 + n);
+    auto t0 = std::chrono::steady_clock::now();
+    std::vector<KeyType> keys(n);
+    sfcKeys<KeyType, T>(kind, x.data(), y.data(), z.data(), keys.data(), n, lim, bnd);
+    std::vector<LocalIndex> order(n);
+    std::iota(order.begin(), order.end(), LocalIndex(0));
+    sort_by_key(keys.begin(), keys.end(), order.begin());
+    {
+        std::vector<T> tmp(n);
+        gatherArrays(execution::cpu, order, 0, std::tie(x, y, z, h), std::tie(tmp));
+    }
+    auto [leaves, counts] = computeOctree<KeyType>(std::span<const KeyType>(keys), bucket);
+    int nLeaves           = int(nNodes(leaves));
+    int numInternal       = (nLeaves - 1) / 7;
+    int numNodes          = nLeaves + numInternal;
+    std::vector<KeyType> prefixes(numNodes);
+    std::vector<TreeNodeIndex> co(numNodes + 1, 0), par(std::max(1, (numNodes - 1) / 8), 0), i2l(numNodes),
+        l2i(numNodes), levelRange(maxTreeLevel<KeyType>{} + 2);
+    buildOctreeCpu(leaves.data(), nLeaves, numInternal, prefixes.data(), co.data(), par.data(), levelRange.data(),
+                   i2l.data(), l2i.data());
+    std::vector<Vec3<T>> centers(numNodes), sizes(numNodes);
+    if (kind == 0) { nodeFpCenters<KeyType>(std::span<const KeyType>(prefixes), centers.data(), sizes.data(), box); }
+    else
+    {
+        // nodeFpCenters decodes node boxes as Hilbert keys whatever curve produced the tree; for a
+        // Morton tree the same two reference functions are applied with the Morton decode
+#pragma omp parallel for schedule(static)
+        for (int i = 0; i < numNodes; ++i)
+        {
+            KeyType startKey                = decodePlaceholderBit(prefixes[i]);
+            unsigned level                  = decodePrefixLength(prefixes[i]) / 3;
+            auto nodeBox                    = sfcIBox(MortonKey<KeyType>(startKey), level);
+            util::tie(centers[i], sizes[i]) = centerAndSize<KeyType>(nodeBox, box);
+        }
+    }
+    std::vector<LocalIndex> layout(nLeaves + 1, 0);
+    std::exclusive_scan(counts.begin(), counts.end(), layout.begin(), LocalIndex(0));
+    layout[nLeaves] = LocalIndex(n);
+    auto t1         = std::chrono::steady_clock::now();
+    times[0]        = std::chrono::duration<double>(t1 - t0).count();
+
+    OctreeNsView<T, KeyType> view{nLeaves,      numNodes,   prefixes.data(),   co.data(),     par.data(),
+                                  i2l.data(),   l2i.data(), levelRange.data(), leaves.data(), layout.data(),
+                                  centers.data(), sizes.data()};
+    d[DG_KEYS]       = weightedSum(keys.data(), n);
+    d[DG_X]          = weightedSum(x.data(), n);
+    d[DG_Y]          = weightedSum(y.data(), n);
+    d[DG_Z]          = weightedSum(z.data(), n);
+    d[DG_H]          = weightedSum(h.data(), n);
+    d[DG_LEAVES]     = weightedSum(leaves.data(), leaves.size());
+    d[DG_NUM_LEAVES] = nLeaves;
+    d[DG_LAYOUT]     = weightedSum(layout.data(), layout.size());
+    d[DG_START]      = 0;
+    d[DG_END]        = n;
+    d[DG_SIZE]       = n;
+    d[DG_NUM_NODES]  = numNodes;
+    d[DG_PREFIXES]   = weightedSum(prefixes.data(), numNodes);
+    d[DG_CHILD_OFFSETS] = weightedSum(co.data(), numNodes);
+    d[DG_CENTERS]       = weightedSum(reinterpret_cast<const T*>(centers.data()), size_t(3) * numNodes);
+    d[DG_SIZES]         = weightedSum(reinterpret_cast<const T*>(sizes.data()), size_t(3) * numNodes);
+    d[DG_LEAF_COUNTS]   = weightedSum(counts.data(), counts.size());
+    neighborsChunked<T, KeyType>(x.data(), y.data(), z.data(), h.data(), 0, LocalIndex(n), box, view, ngmax, chunk,
+                                 &times[1], &d[DG_NC_SUM], &d[DG_LISTS]);
+    return 0;
+}
+
 template<class V, class O>
 long fetch(const V& v, O* out, long cap)
 {
@@ -424,6 +699,51 @@ long fetch(const V& v, O* out, long cap)
 CS_INST_KT(u32f, uint32_t, float)
 CS_INST_KT(u64f, uint64_t, float)
 CS_INST_KT(u64d, uint64_t, double)
+
+#define CS_INST_BENCH(SUFFIX, KeyType, T)                                                                              \
+    extern "C" int ref_bench_run_##SUFFIX(int P, unsigned bucket, unsigned bucketFocus, float theta,                   \
+                                          const double* lim, const int* bnd, const T* x, const T* y, const T* z,       \
+                                          const T* h, const uint64_t* offsets, int numSyncs, unsigned ngmax,           \
+                                          size_t chunk, int numThreads, int haloQuarter)                               \
+    {                                                                                                                  \
+        return benchRun<KeyType, T>(P, bucket, bucketFocus, theta, lim, bnd, x, y, z, h, offsets, numSyncs, ngmax,     \
+                                    chunk, numThreads, haloQuarter);                                                   \
+    }                                                                                                                  \
+    extern "C" int ref_bench_tree_neighbors_##SUFFIX(int kind, const T* x, const T* y, const T* z, const T* h,         \
+                                                     size_t n, unsigned bucket, const double* lim, const int* bnd,     \
+                                                     unsigned ngmax, size_t chunk, double* times, uint64_t* digest)    \
+    {                                                                                                                  \
+        return benchTreeNeighbors<KeyType, T>(kind, x, y, z, h, n, bucket, lim, bnd, ngmax, chunk, times, digest);     \
+    }
+
+CS_INST_BENCH(u32f, uint32_t, float)
+CS_INST_BENCH(u64f, uint64_t, float)
+CS_INST_BENCH(u64d, uint64_t, double)
+
+//! results of the last ref_bench_run_*: times = {sync[0..3], neighbors, halo discovery}, digest[24]
+extern "C" void ref_bench_get(int rank, double* times6, uint64_t* digest24)
+{
+    std::memcpy(times6, g_bench[rank].tSync, sizeof(double) * 4);
+    times6[4] = g_bench[rank].tNeighbors;
+    times6[5] = g_bench[rank].tHalos;
+    std::memcpy(digest24, g_bench[rank].digest, sizeof(uint64_t) * 24);
+}
+
+//! the reference's Plummer sphere (test/coord_samples/plummer.hpp:15-78, srand48(42))
+extern "C" void ref_plummer_d(size_t n, double* x, double* y, double* z)
+{
+    auto pos = plummer<double>(n);
+    std::copy(pos[0].begin(), pos[0].end(), x);
+    std::copy(pos[1].begin(), pos[1].end(), y);
+    std::copy(pos[2].begin(), pos[2].end(), z);
+}
+extern "C" void ref_plummer_f(size_t n, float* x, float* y, float* z)
+{
+    auto pos = plummer<float>(n);
+    std::copy(pos[0].begin(), pos[0].end(), x);
+    std::copy(pos[1].begin(), pos[1].end(), y);
+    std::copy(pos[2].begin(), pos[2].end(), z);
+}
 
 #define CS_INST_K(SUFFIX, KeyType)                                                                                     \
     extern "C" void ref_sort_by_key_##SUFFIX(KeyType* keys, unsigned* values, size_t n)                                \

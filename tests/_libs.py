@@ -266,3 +266,62 @@ def ref_domain_run(combo, P, bucket, bucket_focus, theta, lim, bnd, x, y, z, h, 
         d.update(start=int(se[0]), end=int(se[1]), box=box, t_sync=ts, t_neighbors=tn.value)
         out.append(d)
     return out
+
+
+# ---- bench / full-size parity drivers of oracle/ref_api.cpp: wall times + position-weighted digests, nothing copied out
+DIGEST_SLOTS = ["keys", "x", "y", "z", "h", "leaves", "num_leaves", "layout", "nc_sum", "lists", "start", "end", "size",
+                "num_nodes", "prefixes", "child_offsets", "centers", "sizes", "halo_flags", "halo_count", "leaf_counts"]
+DIGEST_C1, DIGEST_C2 = 0x9E3779B97F4A7C15, 0xC2B2AE3D27D4EB4F
+
+
+def _digest_dict(raw):
+    return {name: int(raw[i]) for i, name in enumerate(DIGEST_SLOTS)}
+
+
+def ref_bench_run(combo, P, bucket, bucket_focus, theta, lim, bnd, x, y, z, h, offsets, num_syncs=1, ngmax=0,
+                  chunk=1 << 20, threads=0, halo_quarter=False):
+    """P thread-ranks of the reference Domain: num_syncs x sync (+ standalone halo discovery over the first quarter of
+    the leaves, + findNeighbors in chunks); returns per rank {t_sync[4], t_neighbors, t_halos, digest{}}"""
+    lib = ref_lib()
+    assert lib is not None
+    lim, bnd = box_args(lim, bnd)
+    offsets = np.ascontiguousarray(offsets, dtype=np.uint64)
+    f = getattr(lib, "ref_bench_run_" + combo)
+    f.argtypes = ([C.c_int, C.c_uint, C.c_uint, C.c_float] + [C.c_void_p] * 7 +
+                  [C.c_int, C.c_uint, C.c_size_t, C.c_int, C.c_int])
+    f(P, bucket, bucket_focus, theta, _p(lim), _p(bnd), _p(x), _p(y), _p(z), _p(h), _p(offsets), num_syncs, ngmax,
+      chunk, threads, int(halo_quarter))
+    out = []
+    for r in range(P):
+        times = np.zeros(6)
+        dg = np.zeros(24, dtype=np.uint64)
+        lib.ref_bench_get(C.c_int(r), _p(times), _p(dg))
+        out.append(dict(t_sync=times[:4].copy(), t_neighbors=float(times[4]), t_halos=float(times[5]),
+                        digest=_digest_dict(dg)))
+    return out
+
+
+def ref_bench_tree_neighbors(combo, kind, x, y, z, h, bucket, lim, bnd, ngmax, chunk=1 << 20):
+    """standalone keys(kind) -> sort -> gather -> computeOctree -> link -> centres -> findNeighbors with the reference;
+    returns {t_build, t_neighbors, digest{}}"""
+    lib = ref_lib()
+    assert lib is not None
+    lim, bnd = box_args(lim, bnd)
+    times = np.zeros(2)
+    dg = np.zeros(24, dtype=np.uint64)
+    f = getattr(lib, "ref_bench_tree_neighbors_" + combo)
+    f.argtypes = [C.c_int] + [C.c_void_p] * 4 + [C.c_size_t, C.c_uint, C.c_void_p, C.c_void_p, C.c_uint, C.c_size_t,
+                                                  C.c_void_p, C.c_void_p]
+    f(kind, _p(x), _p(y), _p(z), _p(h), x.size, bucket, _p(lim), _p(bnd), ngmax, chunk, _p(times), _p(dg))
+    return dict(t_build=float(times[0]), t_neighbors=float(times[1]), digest=_digest_dict(dg))
+
+
+def ref_plummer(n, T=np.float64):
+    """the reference's Plummer sphere generator (test/coord_samples/plummer.hpp, srand48(42))"""
+    lib = ref_lib()
+    assert lib is not None
+    x, y, z = (np.zeros(n, dtype=T) for _ in range(3))
+    f = lib.ref_plummer_d if T == np.float64 else lib.ref_plummer_f
+    f.argtypes = [C.c_size_t] + [C.c_void_p] * 3
+    f(n, _p(x), _p(y), _p(z))
+    return x, y, z

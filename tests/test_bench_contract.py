@@ -19,7 +19,7 @@ def run_bench(extra_env, *args):
 
 
 def test_reference_arm_prints_one_json_line():
-    out = run_bench({"OMP_NUM_THREADS": "1"}, "--impl", "reference", "--steps", "1", "--warmup", "0", "--ref-n", "65536")
+    out = run_bench({"OMP_NUM_THREADS": "1"}, "--impl", "reference", "--steps", "1", "--warmup", "0", "--n", "65536")
     lines = [l for l in out.splitlines() if l.strip()]
     assert len(lines) == 1, out
     d = json.loads(lines[0])
@@ -31,6 +31,21 @@ def test_reference_arm_prints_one_json_line():
     assert cb["kind"] in ("reference", "port") and cb["sample"]
     if cb["kind"] == "reference":
         assert cb["cores"] == os.cpu_count(), "the reference arm must not inherit OMP_NUM_THREADS=1 from the launcher"
+    # the reference arm runs the workload our arm prints as `config` (N=1: at full size) and publishes the digests
+    # of its results so that the two lines can be compared
+    assert d["config"]["particles_per_gpu"] == 65536 and cb["particles_per_rank"] == 65536
+    assert d["results"]["digest"]["num_leaves"] > 0 and d["results"]["digest"]["nc_sum"] > 0
+
+
+def test_reference_arm_other_workloads_and_ranks():
+    for extra in (["--config", "plummer"], ["--config", "morton"]):
+        out = run_bench({}, "--impl", "reference", "--steps", "1", "--warmup", "0", "--n", "32768", *extra)
+        d = json.loads(out.strip())
+        assert d["config"]["name"] == extra[1] and d["value"] > 0
+    # N>1: a reduced-size run of ONE reference Domain over N ranks (threads), not N single-rank runs
+    out = run_bench({}, "--impl", "reference", "--gpus", "2", "--steps", "1", "--warmup", "0", "--ref-n", "262144")
+    d = json.loads(out.strip())
+    assert d["n_gpus"] == 2 and d["cpu_baseline"]["ranks"] == 2 and d["cpu_baseline"]["particles_per_rank"] == 32768
 
 
 def test_reference_arm_is_silent_on_other_ranks():
