@@ -391,11 +391,16 @@ uint64_t bitsOf(E v)
         std::memcpy(&b, &v, 8);
         return b;
     }
-    else
+    else if constexpr (sizeof(E) == 4)
     {
         uint32_t b;
         std::memcpy(&b, &v, 4);
         return b;
+    }
+    else
+    {
+        static_assert(sizeof(E) == 1);
+        return uint64_t(uint8_t(v));
     }
 }
 
