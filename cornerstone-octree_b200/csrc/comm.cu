@@ -193,13 +193,41 @@ public:
         if (int e = allgatherHost(&rec, sizeof(Rec), all.data(), s)) { return e; }
         peers.resize(size_t(w_->size) * count);
         extras.resize(w_->size);
+        // ranks may live on different devices: kernel stores into a peer's arrays need peer access.  Every rank checks
+        // what it is going to address; if any pair cannot be mapped, all ranks report 2 (caller falls back to exchange())
+        int ok = 1, myDev = 0;
+        CSB_CHECK(cudaGetDevice(&myDev));
         for (int r = 0; r < w_->size; ++r)
         {
             for (int k = 0; k < count; ++k)
-                peers[size_t(r) * count + k] = all[r].p[k];
+            {
+                void* p                      = all[r].p[k];
+                peers[size_t(r) * count + k] = p;
+                cudaPointerAttributes attr{};
+                if (p == nullptr || cudaPointerGetAttributes(&attr, p) != cudaSuccess)
+                {
+                    cudaGetLastError();
+                    continue; // nothing to address
+                }
+                if (attr.type != cudaMemoryTypeDevice || attr.device == myDev) { continue; }
+                int can = 0;
+                if (cudaDeviceCanAccessPeer(&can, myDev, attr.device) != cudaSuccess || !can)
+                {
+                    cudaGetLastError();
+                    ok = 0;
+                    continue;
+                }
+                cudaError_t err = cudaDeviceEnablePeerAccess(attr.device, 0);
+                if (err != cudaSuccess && err != cudaErrorPeerAccessAlreadyEnabled) { ok = 0; }
+                cudaGetLastError();
+            }
             extras[r] = all[r].extra;
         }
-        return 0;
+        std::vector<int> oks(w_->size);
+        if (int e = allgatherHost(&ok, sizeof(int), oks.data(), s)) { return e; }
+        for (int v : oks)
+            ok = ok && v;
+        return ok ? 0 : 2;
     }
 
     int barrier(cudaStream_t s) override
@@ -291,7 +319,7 @@ public:
     ~NcclComm() override
     {
         for (auto& kv : ipcCache_)
-            cudaIpcCloseMemHandle(kv.second);
+            cudaIpcCloseMemHandle(kv.second.ptr);
         if (comm_) { api_->CommDestroy(comm_); }
         cudaFree(stage_);
     }
@@ -380,8 +408,16 @@ public:
                     peers[size_t(r) * count + k] = mine[k];
                     continue;
                 }
-                std::string key(reinterpret_cast<const char*>(&all[r].h[k]), sizeof(cudaIpcMemHandle_t));
-                auto it = ipcCache_.find(key);
+                // one live mapping per (rank, slot): when rank r publishes a new handle for slot k (it reallocated),
+                // the mapping it replaces is closed; nothing that the current call hands out is ever evicted
+                std::string handle(reinterpret_cast<const char*>(&all[r].h[k]), sizeof(cudaIpcMemHandle_t));
+                auto it = ipcCache_.find({r, k});
+                if (it != ipcCache_.end() && it->second.handle != handle)
+                {
+                    cudaIpcCloseMemHandle(it->second.ptr);
+                    ipcCache_.erase(it);
+                    it = ipcCache_.end();
+                }
                 if (it == ipcCache_.end())
                 {
                     void* p = nullptr;
@@ -391,16 +427,9 @@ public:
                         ok = 0;
                         break;
                     }
-                    if (ipcOrder_.size() >= 64) // peers reallocate rarely; unmap the oldest mapping
-                    {
-                        cudaIpcCloseMemHandle(ipcCache_[ipcOrder_.front()]);
-                        ipcCache_.erase(ipcOrder_.front());
-                        ipcOrder_.erase(ipcOrder_.begin());
-                    }
-                    it = ipcCache_.emplace(key, p).first;
-                    ipcOrder_.push_back(key);
+                    it = ipcCache_.emplace(std::make_pair(r, k), IpcMapping{handle, p}).first;
                 }
-                peers[size_t(r) * count + k] = it->second;
+                peers[size_t(r) * count + k] = it->second.ptr;
             }
         }
         // every rank must take the same path
@@ -428,8 +457,12 @@ private:
     ncclComm_t comm_;
     int rank_, size_;
     bool ipcDisabled_{std::getenv("CSB_NO_PEER_PUSH") != nullptr};
-    std::map<std::string, void*> ipcCache_;
-    std::vector<std::string> ipcOrder_;
+    struct IpcMapping
+    {
+        std::string handle;
+        void* ptr;
+    };
+    std::map<std::pair<int, int>, IpcMapping> ipcCache_; // (rank, slot) -> the peer allocation currently mapped
     char* stage_{nullptr};
     size_t stageCap_{0};
 };

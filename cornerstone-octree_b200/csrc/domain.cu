@@ -9,10 +9,14 @@
  * every tree update.  What changes is where things run: every array lives in HBM, each step is one of the kernels in
  * this library, and the host only reads back the handful of scalars the control flow needs.
  *
- * Scope of this file in round 1: ONE rank (numRanks == 1).  With a single rank nothing is exchanged, every leaf is in
- * focus (so MAC flags cannot change any rebalance decision, focus/rebalance.hpp:31-73) and no search box can leave
- * the assigned SFC range (traversal/collisions.hpp:81-90), therefore halo flags are all zero; those two stages are
- * skipped.  Multi-rank construction is rejected loudly ("what comes next").
+ * One rank: nothing is exchanged, every leaf is in focus (so MAC flags cannot change any rebalance decision,
+ * focus/rebalance.hpp:31-73) and no search box can leave the assigned SFC range (traversal/collisions.hpp:81-90),
+ * therefore halo flags are all zero; those two stages are skipped.  Several ranks (a communicator attached with
+ * cs_domain_attach_comm): global assignment, exchangeParticles, LET and halo exchange as described in DESIGN.md 4.
+ *
+ * Errors in collective phases: a rank whose local precondition fails returns its error; its peers are released by
+ * cs_local_world_abort (thread ranks) or by the job launcher tearing down the process group (NCCL), as with an MPI
+ * abort in the reference.
  */
 #include <algorithm>
 #include <chrono>
@@ -438,11 +442,7 @@ public:
                     CSB_REQUIRE(runs.back() == size_t(numAssigned), "merge runs do not cover the assigned particles");
                     CSB_TRY(keyBuf_.resize(std::max<size_t>(numAssigned, 1), s));
                     CSB_TRY(valueBuf_.resize(std::max<size_t>(numAssigned, 1), s));
-                    if (std::getenv("CSB_SORT_RECEIVED"))
-                    {
-                        CSB_TRY(sortPairs(assignedKeys_.p, assignedOrder_.p, numAssigned, s));
-                    }
-                    else if (numPresent > numRecv)
+                    if (numPresent > numRecv)
                     {
                         // steady state, few particles migrate: merge the small received runs among themselves first,
                         // the large present run then takes part in a single round instead of log2(P)

@@ -3,6 +3,7 @@
 #include <atomic>
 #include <map>
 #include <mutex>
+#include <thread>
 
 #include "common.cuh"
 #include "cstone_b200.h"
@@ -20,7 +21,7 @@ void setLastError(const std::string& msg)
     g_lastError = msg;
 }
 
-static std::atomic<int> g_tuning[TUNE_COUNT] = {};
+static std::atomic<int> g_tuning[TUNE_COUNT] = {{1}}; // TUNE_NB_KERNEL = 1
 int tuning(int knob) { return (knob >= 0 && knob < TUNE_COUNT) ? g_tuning[knob].load(std::memory_order_relaxed) : 0; }
 
 void countLaunch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
@@ -29,19 +30,24 @@ void countLaunch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
  * stream-ordered allocator on every call (primitives_gpu.cu:289,302, octree_gpu.cu:190-199); with the default pool's
  * release threshold of zero that returns the memory to the driver at every synchronisation, which on a GPU holding
  * >100 GB of allocations costs up to hundreds of ms per call (measured: profiles/r1_notes.md).  Instead each
- * (device, stream, slot) owns one buffer that only ever grows.  State is keyed per device AND stream, so two streams
- * (or two devices) never share scratch ("Threading / stream semantics"). */
+ * (device, stream, host thread, slot) owns one buffer that only ever grows.  State is keyed per device, stream AND
+ * calling thread: two streams, two devices, or two host threads that share a stream (ranks as threads, the C++
+ * forwarder's default stream) never see each other's temporaries, so the multi-kernel sequences that use them
+ * (findNeighbors, computeNodeCounts, mergeSortedRuns, gatherArrays) cannot interleave on shared scratch (SURVEY.md 8b,
+ * "Threading / stream semantics").  A buffer is only freed or grown by the thread that owns it. */
 namespace
 {
 struct ScratchKey
 {
     int device;
     cudaStream_t stream;
+    std::thread::id thread;
     int slot;
     bool operator<(const ScratchKey& o) const
     {
         if (device != o.device) { return device < o.device; }
         if (stream != o.stream) { return stream < o.stream; }
+        if (thread != o.thread) { return thread < o.thread; }
         return slot < o.slot;
     }
 };
@@ -63,7 +69,7 @@ void* scratch(cudaStream_t s, int slot, size_t bytes)
         return nullptr;
     }
     std::lock_guard<std::mutex> lk(g_scratchMutex);
-    ScratchBuf& b = g_scratch[ScratchKey{dev, s, slot}];
+    ScratchBuf& b = g_scratch[ScratchKey{dev, s, std::this_thread::get_id(), slot}];
     if (bytes > b.cap)
     {
         if (b.p)

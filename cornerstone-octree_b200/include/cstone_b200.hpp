@@ -222,6 +222,8 @@ public:
     Domain(int rank, int nRanks, unsigned bucketSize, unsigned bucketSizeFocus, float theta, const BoxT& box)
     {
         BoxArgs<BoxT> b(box);
+        static_assert(sizeof(KeyType) == 8 || std::is_same_v<T, float>,
+                      "32-bit keys come with float coordinates only (the instantiations of the reference's Domain)");
         if constexpr (sizeof(KeyType) == 4) { d_ = cs_domain_create_u32f(rank, nRanks, bucketSize, bucketSizeFocus, theta, b.lim, b.bnd); }
         else if constexpr (std::is_same_v<T, float>) { d_ = cs_domain_create_u64f(rank, nRanks, bucketSize, bucketSizeFocus, theta, b.lim, b.bnd); }
         else { d_ = cs_domain_create_u64d(rank, nRanks, bucketSize, bucketSizeFocus, theta, b.lim, b.bnd); }

@@ -39,7 +39,7 @@ dom = capi.Domain(0, 1, bench.BUCKET, bench.BUCKET, 0.5, (0, 1, 0, 1, 0, 1), (0,
 dom.sync(x, y, z, h)
 del x, y, z, h
 ref_nb = ref_nc = None
-combos = [(0, 0), (1, 0), (0, 1), (1, 1)]
+combos = [(0, 0), (1, 0), (1, 1), (2, 0)]  # per-lane walks, certified, certified leaf-aligned, cooperative
 if args.only:
     combos = [tuple(int(v) for v in args.only.split(","))]
 nb = torch.zeros(n * ngmax, dtype=torch.uint32, device=dev)
