@@ -72,9 +72,8 @@ enum ScratchSlot : int
 //! experiment knobs (cs_tuning_set; not part of the drop-in surface).  Read once per entry-point call.
 enum TuningKnob : int
 {
-    TUNE_NB_KERNEL = 0, // findNeighbors: 0 = per-warp search with per-lane walks, 1 (default) = certified per-warp
-                        // search, 2 = cooperative search
-    TUNE_NB_GROUPS = 1, // per-warp search: 0 (default) = full groups over runs of sibling leaves, 1 = leaf aligned
+    TUNE_NB_GROUPS = 1, // findNeighbors target groups: 0 (default) = full groups over runs of sibling leaves,
+                        // 1 = leaf aligned
     TUNE_COUNT     = 16
 };
 int tuning(int knob);

@@ -21,7 +21,7 @@ void setLastError(const std::string& msg)
     g_lastError = msg;
 }
 
-static std::atomic<int> g_tuning[TUNE_COUNT] = {{1}}; // TUNE_NB_KERNEL = 1
+static std::atomic<int> g_tuning[TUNE_COUNT] = {};
 int tuning(int knob) { return (knob >= 0 && knob < TUNE_COUNT) ? g_tuning[knob].load(std::memory_order_relaxed) : 0; }
 
 void countLaunch() { g_launches.fetch_add(1, std::memory_order_relaxed); }

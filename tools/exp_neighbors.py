@@ -39,13 +39,12 @@ dom = capi.Domain(0, 1, bench.BUCKET, bench.BUCKET, 0.5, (0, 1, 0, 1, 0, 1), (0,
 dom.sync(x, y, z, h)
 del x, y, z, h
 ref_nb = ref_nc = None
-combos = [(0, 0), (1, 0), (1, 1), (2, 0)]  # per-lane walks, certified, certified leaf-aligned, cooperative
+combos = [(0, 0), (0, 1)]  # (unused, target groups): full groups over sibling runs, leaf aligned
 if args.only:
     combos = [tuple(int(v) for v in args.only.split(","))]
 nb = torch.zeros(n * ngmax, dtype=torch.uint32, device=dev)
 nc = torch.zeros(n, dtype=torch.uint32, device=dev)
 for kern, grp in combos:
-    capi.tuning_set(0, kern)
     capi.tuning_set(1, grp)
     ms = []
     for _ in range(args.reps):
