@@ -504,6 +504,27 @@ template int minMaxPartials<double>(const double*, size_t, double*, int, cudaStr
 extern "C"
 {
 
+/* countSfcGapsGpu / fillSfcGapsGpu (tree/csarray_gpu.h:78-82, csarray_gpu.cu:238-270): number of octree nodes that span
+ * each gap [tree[i], tree[i+1]) of a sorted key sequence, and the nodes themselves at the scanned offsets */
+int cs_count_sfc_gaps_u32(const uint32_t* tree, int numNodes, int* nodeOps, void* stream)
+{
+    return csb::countGaps<uint32_t>(tree, numNodes, reinterpret_cast<uint32_t*>(nodeOps), cudaStream_t(stream));
+}
+int cs_count_sfc_gaps_u64(const uint64_t* tree, int numNodes, int* nodeOps, void* stream)
+{
+    return csb::countGaps<uint64_t>(tree, numNodes, reinterpret_cast<uint32_t*>(nodeOps), cudaStream_t(stream));
+}
+int cs_fill_sfc_gaps_u32(const uint32_t* tree, int numNodes, const int* nodeOps, uint32_t* newTree, void* stream)
+{
+    return csb::fillGaps<uint32_t>(tree, numNodes, reinterpret_cast<const uint32_t*>(nodeOps), newTree,
+                                   cudaStream_t(stream));
+}
+int cs_fill_sfc_gaps_u64(const uint64_t* tree, int numNodes, const int* nodeOps, uint64_t* newTree, void* stream)
+{
+    return csb::fillGaps<uint64_t>(tree, numNodes, reinterpret_cast<const uint32_t*>(nodeOps), newTree,
+                                   cudaStream_t(stream));
+}
+
 /* rebalanceDecisionEssentialGpu / protectAncestorsGpu / enforceKeysGpu (focus/rebalance_gpu.h:27-79); the host-value
  * results the reference returns (converged flag, ResolutionStatus) come back through the last pointer argument, which
  * synchronises the stream exactly as the reference functions do */

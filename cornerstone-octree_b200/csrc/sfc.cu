@@ -206,7 +206,7 @@ __device__ inline K encodeOne(T x, T y, T z, const KeyParams<T>& p, const uint16
 }
 
 template<class E, int N>
-struct alignas(16) Pack
+struct alignas(sizeof(E) * N) Pack
 {
     E v[N];
 };
@@ -245,9 +245,11 @@ __global__ void __launch_bounds__(256) sfcKeysKernel(const T* __restrict__ x,
         auto* xv        = reinterpret_cast<const Pack<T, V>*>(x);
         auto* yv        = reinterpret_cast<const Pack<T, V>*>(y);
         auto* zv        = reinterpret_cast<const Pack<T, V>*>(z);
-        auto* kv        = reinterpret_cast<Pack<K, 16 / sizeof(K)>*>(keys);
-        constexpr int KP = V * sizeof(K) / 16; // 16-byte key packs per particle vector
-        constexpr int KV = 16 / sizeof(K);
+        // keys of one particle vector: KP packs of KV keys (16 bytes each, or one 8-byte pack for 32-bit keys of
+        // double coordinates)
+        constexpr int KV = (16 / sizeof(K)) < V ? int(16 / sizeof(K)) : V;
+        constexpr int KP = V / KV;
+        auto* kv         = reinterpret_cast<Pack<K, KV>*>(keys);
         for (size_t i = tid; i < nvec; i += nthreads)
         {
             Pack<T, V> px = xv[i], py = yv[i], pz = zv[i];
@@ -356,6 +358,12 @@ int cs_compute_sfc_keys_u32f(int kind, const float* x, const float* y, const flo
                              const double* lim, const int* bnd, void* stream)
 {
     return csb::computeSfcKeys<uint32_t, float>(kind, x, y, z, keys, n, lim, bnd, cudaStream_t(stream));
+}
+
+int cs_compute_sfc_keys_u32d(int kind, const double* x, const double* y, const double* z, uint32_t* keys, size_t n,
+                             const double* lim, const int* bnd, void* stream)
+{
+    return csb::computeSfcKeys<uint32_t, double>(kind, x, y, z, keys, n, lim, bnd, cudaStream_t(stream));
 }
 
 int cs_compute_sfc_keys_u64f(int kind, const float* x, const float* y, const float* z, uint64_t* keys, size_t n,

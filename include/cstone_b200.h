@@ -44,6 +44,8 @@ int cs_release_scratch(void);
  * keys[i] = sfc3D(x[i],y[i],z[i], box) unless keys[i] == removeKey = 2^(3*maxTreeLevel) (sfc/sfc.hpp:274). */
 int cs_compute_sfc_keys_u32f(int kind, const float* x, const float* y, const float* z, uint32_t* keys, size_t n,
                              const double* lim, const int* bnd, void* stream);
+int cs_compute_sfc_keys_u32d(int kind, const double* x, const double* y, const double* z, uint32_t* keys, size_t n,
+                             const double* lim, const int* bnd, void* stream);
 int cs_compute_sfc_keys_u64f(int kind, const float* x, const float* y, const float* z, uint64_t* keys, size_t n,
                              const double* lim, const int* bnd, void* stream);
 int cs_compute_sfc_keys_u64d(int kind, const double* x, const double* y, const double* z, uint64_t* keys, size_t n,
@@ -100,6 +102,13 @@ int cs_rebalance_tree_u32(const uint32_t* leaves, int numLeaves, int newNumLeave
                           uint32_t* newLeaves, void* stream);
 int cs_rebalance_tree_u64(const uint64_t* leaves, int numLeaves, int newNumLeaves, const int* nodeOps,
                           uint64_t* newLeaves, void* stream);
+/* countSfcGapsGpu / fillSfcGapsGpu (tree/csarray_gpu.h:78-82, csarray_gpu.cu:238-270): nodeOps[i] = number of octree
+ * nodes that span [tree[i], tree[i+1]) (nodeOps has numNodes + 1 entries, the last is set to 0); after an exclusive
+ * scan, fill writes those nodes to newTree + nodeOps[i] and tree[numNodes] to newTree[nodeOps[numNodes]] */
+int cs_count_sfc_gaps_u32(const uint32_t* tree, int numNodes, int* nodeOps, void* stream);
+int cs_count_sfc_gaps_u64(const uint64_t* tree, int numNodes, int* nodeOps, void* stream);
+int cs_fill_sfc_gaps_u32(const uint32_t* tree, int numNodes, const int* nodeOps, uint32_t* newTree, void* stream);
+int cs_fill_sfc_gaps_u64(const uint64_t* tree, int numNodes, const int* nodeOps, uint64_t* newTree, void* stream);
 /* computeOctree (csarray.hpp:429-440 / test/unit_cuda/tree/csarray.cu:164-185): converge a leaf array from the root
  * for sorted keys.  leaves: capacity+1 keys, counts: capacity.  Synchronises; returns the leaf count in
  * *numLeaves (host), status 3 if capacity is too small (then *numLeaves = required). */

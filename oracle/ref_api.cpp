@@ -701,6 +701,12 @@ long fetch(const V& v, O* out, long cap)
                                      moves);                                                                           \
     }
 
+extern "C" void ref_sfc_keys_u32d(int kind, const double* x, const double* y, const double* z, uint32_t* keys, size_t n,
+                                  const double* lim, const int* bnd)
+{
+    sfcKeys<uint32_t, double>(kind, x, y, z, keys, n, lim, bnd);
+}
+
 CS_INST_KT(u32f, uint32_t, float)
 CS_INST_KT(u64f, uint64_t, float)
 CS_INST_KT(u64d, uint64_t, double)

@@ -486,3 +486,26 @@ def test_find_halos_flags_21(combo):
         assert int(flags.sum()) == 21
         want = orc.find_halos(combo, tree_o, cen_o, siz_o, leaves, sc, ss, lim, bnd, first, last)
         assert np.array_equal(flags, want)
+
+
+@pytest.mark.skipif(ref() is None, reason="needs oracle/_ref")
+@pytest.mark.parametrize("kind", [0, 1])
+def test_sfc_keys_u32_from_double_coordinates(kind):
+    """computeSfcKeys<{Hilbert,Morton}Key<unsigned>, double> (sfc/sfc_gpu.cu:46-62) vs the unmodified reference"""
+    import ctypes as C
+
+    from _libs import ref_lib
+    n = 100003
+    rng = np.random.default_rng(11)
+    x, y, z = (rng.random(n) * 3.0 - 1.0 for _ in range(3))
+    lim, bnd = (-1, 2, -1, 2, -1, 2), (0, 1, 0)
+    want = np.zeros(n, dtype=np.uint32)
+    lim_a, bnd_a = np.array(lim, dtype=np.float64), np.array(bnd, dtype=np.int32)
+    ref_lib().ref_sfc_keys_u32d(C.c_int(kind), x.ctypes.data_as(C.c_void_p), y.ctypes.data_as(C.c_void_p),
+                                z.ctypes.data_as(C.c_void_p), want.ctypes.data_as(C.c_void_p), C.c_size_t(n),
+                                lim_a.ctypes.data_as(C.c_void_p), bnd_a.ctypes.data_as(C.c_void_p))
+    for off in (0, 1):  # aligned (vector path) and misaligned (scalar path) pointers
+        dx, dy, dz = (dev(np.concatenate([np.zeros(off), a]))[off:] for a in (x, y, z))
+        keys = torch.zeros(n + off, dtype=torch.uint32, device="cuda")[off:]
+        capi().compute_sfc_keys(dx, dy, dz, keys, lim, bnd, kind=kind)
+        assert np.array_equal(host(keys), want), (kind, off)
