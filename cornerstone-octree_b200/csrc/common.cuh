@@ -245,11 +245,6 @@ __device__ inline T pbcFold(T d, int dim, const Box<T>& box)
     return d - f * box.len[dim] * rrint(d * box.ilen[dim]);
 }
 
-/* ------------------------------------------------------------------------------------------------ Hilbert LUT */
-
-//! 3-levels-per-lookup state machine tables for the reference's Hilbert curve variant; built by sfc.cu
-constexpr int hilbertMaxStates = 32;
-
 /* ------------------------------------------------------------------------------------------------ scans */
 
 //! exclusive scan of u32/i32 values on the stream; in may equal out. tmp must hold scanTempBytes(n)

@@ -18,86 +18,204 @@ namespace
 /* ---------------------------------------------------------------- node counts */
 
 /* counts[i] = lower_bound(keys, leaves[i+1]) - lower_bound(keys, leaves[i]) (calculateNodeCount, tree/csarray.hpp:68-79).
- * Leaves and keys are both sorted, so a block of NC_LEAVES consecutive leaves needs one contiguous window of keys:
- *   1. coarseBoundsKernel: lower bound of every NC_LEAVES-th leaf key by binary search over all keys (few searches,
- *      all in flight at once);
- *   2. nodeCountsKernel: each block streams its key window through shared memory with coalesced loads - every key is
- *      read from HBM once - and the threads search their leaf keys there.  Very long windows (coarse trees with few
- *      leaves) are searched in global memory instead, bounded by the window.
+ * Leaves and keys are both sorted, so a chunk of consecutive leaves needs one contiguous window of keys:
+ *   1. coarseBoundsKernel: lower bound of the first leaf key of every chunk among all keys (a warp-cooperative 32-ary
+ *      search per chunk);
+ *   2. nodeCountsPipelinedKernel: the key windows are streamed through shared memory - every key is read from HBM
+ *      once - and the threads search their leaf keys there.  Windows that do not fit (coarse trees with few leaves) are
+ *      searched in global memory instead, bounded by the window.
  */
-constexpr int NC_LEAVES  = 64;   // leaves per block
-constexpr int NC_THREADS = 256;  // threads per block: all of them stream keys, the first NC_LEAVES search
-constexpr int NC_WINDOW  = 3072; // keys staged in shared memory per tile (24 KiB of 64-bit keys: 8 blocks per SM)
-constexpr int NC_MAX_TILES = 8; // longer windows (coarse trees) are searched in global memory
-
+/*! lower bound of every NC_LEAVES-th leaf key among all keys: one WARP per search, 32 probes per round (a 32-ary
+ *  search: 6 dependent rounds for 64 Mi keys instead of the 26 of a binary search - this latency chain was 12 % of the
+ *  stage, profiles/r1_notes.md) */
 template<class K>
 __global__ void coarseBoundsKernel(const K* __restrict__ leaves, int numLeaves, const K* __restrict__ keys, size_t n,
-                                   int numChunks, uint64_t* __restrict__ coarse)
+                                   int numChunks, int NC_LEAVES, uint64_t* __restrict__ coarse)
 {
-    int j = blockIdx.x * blockDim.x + threadIdx.x;
+    const int j         = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const unsigned lane = threadIdx.x & 31;
     if (j > numChunks) { return; }
-    int leaf  = min(j * NC_LEAVES, numLeaves);
-    coarse[j] = lowerBound(keys, n, leaves[leaf]);
+    const K v = leaves[min(j * NC_LEAVES, numLeaves)];
+    // invariant: keys before lo are < v, keys from lo + len on are >= v
+    size_t lo = 0, len = n;
+    while (len > 0)
+    {
+        const size_t step = (len + 31) / 32;
+        const size_t q    = lo + (lane + 1) * step - 1; // probes are ascending: the lanes that see a smaller key form a prefix
+        const bool valid  = q < lo + len;
+        const bool less   = valid && keys[q] < v;
+        const unsigned c  = __popc(__ballot_sync(0xffffffffu, less));
+        const size_t end  = lo + len;
+        lo += c * step;
+        // probe c (if it exists) holds a key >= v: the answer is at most its position
+        const size_t qc = lo + step - 1;
+        len             = qc < end ? step - 1 : end - lo;
+    }
+    if (lane == 0) { coarse[j] = lo; }
 }
 
-template<class K>
-__global__ void __launch_bounds__(NC_THREADS) nodeCountsKernel(const K* __restrict__ leaves,
-                                                              uint32_t* __restrict__ counts,
-                                                              int numLeaves,
-                                                              const K* __restrict__ keys,
-                                                              const uint64_t* __restrict__ coarse,
-                                                              uint32_t maxCount)
+/* ---- persistent blocks, key windows brought in by the bulk-copy engine ----
+ * A block that loads one window, searches it and exits exposes the DRAM latency of its loads once per window (round 1:
+ * 0.154 ms, 0.56 of the HBM peak).  Here each block walks its share of the chunks with the key windows of the next
+ * STAGES - 1 chunks in flight (0.137 ms, 0.63 of the peak; shapes tried: profiles/r2_notes.md): thread 0 issues one `cp.async.bulk` (global -> shared, 1D, completion counted in bytes on an mbarrier) per
+ * window, the threads only search.  The bulk engine needs 16-byte aligned addresses and sizes, so the copied range is
+ * the window rounded outwards to 16 bytes (clipped to the key array; clipped-off head / tail keys - at most 3, only in
+ * the first and last window of an array - are loaded normally). */
+__device__ __forceinline__ uint32_t smemAddr(const void* p) { return uint32_t(__cvta_generic_to_shared(p)); }
+
+__device__ __forceinline__ void mbarInit(uint64_t* bar, uint32_t count)
 {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smemAddr(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbarExpectTx(uint64_t* bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smemAddr(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbarWait(uint64_t* bar, uint32_t parity)
+{
+    asm volatile("{\n .reg .pred p;\n WAIT_LOOP:\n mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+                 " @p bra WAIT_DONE;\n bra WAIT_LOOP;\n WAIT_DONE:\n}" ::"r"(smemAddr(bar)),
+                 "r"(parity)
+                 : "memory");
+}
+__device__ __forceinline__ void bulkCopyG2S(void* dstShared, const void* srcGlobal, uint32_t bytes, uint64_t* bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     smemAddr(dstShared)),
+                 "l"(srcGlobal), "r"(bytes), "r"(smemAddr(bar))
+                 : "memory");
+}
+
+template<int LEAVES, int WINDOW, int STAGES>
+struct NcPipeShape
+{
+    static constexpr int leaves = LEAVES, window = WINDOW, stages = STAGES;
+};
+
+struct NcStageMeta
+{
+    unsigned long long first; // index of the first key of the window (coarse[chunk])
+    uint32_t width;           // number of keys in the window
+    uint32_t shift;           // window[i] = buffer[shift + i]
+    uint32_t headEnd;         // window keys [0, headEnd) and
+    uint32_t tailBegin;       // [tailBegin, width) were clipped off the bulk copy: loaded normally
+    uint32_t staged;          // 0: window too long for shared memory, searched in global memory
+};
+
+template<class K, class Shape>
+__global__ void __launch_bounds__(Shape::leaves) nodeCountsPipelinedKernel(const K* __restrict__ leaves,
+                                                                          uint32_t* __restrict__ counts,
+                                                                          int numLeaves,
+                                                                          const K* __restrict__ keys,
+                                                                          size_t n,
+                                                                          const uint64_t* __restrict__ coarse,
+                                                                          int numChunks,
+                                                                          uint32_t maxCount)
+{
+    constexpr int LEAVES = Shape::leaves, WINDOW = Shape::window, STAGES = Shape::stages;
+    constexpr int BUF = WINDOW + 48 / int(sizeof(K)); // keys per buffer: the window plus alignment slack on both sides
     extern __shared__ __align__(16) unsigned char ncSmem[];
-    K* window = reinterpret_cast<K*>(ncSmem);
-    __shared__ uint32_t bound[NC_LEAVES + 1];
+    K* buffers = reinterpret_cast<K*>(ncSmem);
+    __shared__ __align__(8) uint64_t bar[STAGES];
+    __shared__ NcStageMeta meta[STAGES];
+    __shared__ uint32_t bound[LEAVES + 1];
 
-    const int c0   = blockIdx.x * NC_LEAVES;
-    const int nl   = min(NC_LEAVES, numLeaves - c0);
-    const size_t A = coarse[blockIdx.x], B = coarse[blockIdx.x + 1];
-    const size_t W = B - A;
-    const int t    = threadIdx.x;
-    const K mine   = leaves[c0 + min(t, nl)]; // thread nl would look for leaves[c0 + nl], whose bound is B
-
-    if (W <= size_t(NC_WINDOW) * NC_MAX_TILES)
+    const int t = threadIdx.x;
+    if (t == 0)
     {
-        // stream the window through shared memory tile by tile; a thread's bound is the number of window keys smaller
-        // than its leaf key: whole tiles below it count fully, the tile that straddles it is searched
-        uint32_t below = 0;
-        bool open      = t < nl;
-        for (size_t base = 0; base < W; base += NC_WINDOW)
-        {
-            const uint32_t tw = uint32_t(min(size_t(NC_WINDOW), W - base));
-            const K* src      = keys + A + base;
-            if (base) { __syncthreads(); }
-            // fixed trip count, fully unrolled: all 12 loads of a thread are in flight together (a `for (i < tw)`
-            // loop issues them a few at a time and the block waits on one DRAM round trip after the other)
-#pragma unroll
-            for (int u = 0; u < NC_WINDOW / NC_THREADS; ++u)
-            {
-                uint32_t i = uint32_t(u) * NC_THREADS + t;
-                if (i < tw) { window[i] = src[i]; }
-            }
-            __syncthreads();
-            if (open)
-            {
-                if (window[tw - 1] < mine) { below += tw; }
-                else
-                {
-                    below += lowerBound(window, tw, mine);
-                    open = false;
-                }
-            }
-        }
-        if (t < nl) { bound[t] = below; }
+        for (int b = 0; b < STAGES; ++b)
+            mbarInit(&bar[b], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    else if (t < nl) { bound[t] = uint32_t(lowerBound(keys + A, W, mine)); } // W < 2^32: fewer than 2^32 keys per call
-    if (t == 0) { bound[nl] = uint32_t(W); }
     __syncthreads();
-    if (t < nl)
+
+    //! thread 0: describe the window of `chunk` in stage b and start its bulk copy
+    auto issue = [&](int chunk, int b)
     {
-        uint32_t c     = bound[t + 1] - bound[t];
-        counts[c0 + t] = c < maxCount ? c : maxCount;
+        const unsigned long long A = coarse[chunk], B = coarse[chunk + 1];
+        const uint32_t W           = uint32_t(B - A);
+        NcStageMeta m;
+        m.first  = A;
+        m.width  = W;
+        m.staged = W <= uint32_t(WINDOW);
+        m.shift = 0, m.headEnd = 0, m.tailBegin = W;
+        uint32_t bytes = 0;
+        if (m.staged && W)
+        {
+            const uintptr_t base = reinterpret_cast<uintptr_t>(keys), end = base + n * sizeof(K);
+            const uintptr_t a = base + A * sizeof(K), e = base + B * sizeof(K);
+            uintptr_t lo      = a & ~uintptr_t(15);          // rounded outwards ...
+            uintptr_t hi      = (e + 15) & ~uintptr_t(15);
+            if (lo < base) { lo += 16; }                     // ... and clipped to the array
+            if (hi > end) { hi -= 16; }
+            // buffer position of key A: 16 bytes of slack in front keep the copy destination aligned like its source
+            m.shift = uint32_t((16 + (a & 15)) / sizeof(K));
+            if (hi > lo)
+            {
+                bytes       = uint32_t(hi - lo);
+                m.headEnd   = lo > a ? uint32_t((lo - a) / sizeof(K)) : 0u;
+                m.tailBegin = hi < e ? uint32_t((hi - a) / sizeof(K)) : W;
+                K* dst      = buffers + size_t(b) * BUF + m.shift + (long long)(lo - a) / (long long)sizeof(K);
+                mbarExpectTx(&bar[b], bytes);
+                bulkCopyG2S(dst, reinterpret_cast<const void*>(lo), bytes, &bar[b]);
+            }
+            else { m.headEnd = W; } // the whole (tiny) window is loaded normally
+        }
+        meta[b] = m;
+        if (bytes == 0) { mbarExpectTx(&bar[b], 0); }
+    };
+
+    // prologue: the first STAGES - 1 windows of this block
+    if (t == 0)
+    {
+        for (int k = 0; k < STAGES - 1; ++k)
+        {
+            const int chunk = blockIdx.x + k * gridDim.x;
+            if (chunk < numChunks) { issue(chunk, k); }
+        }
+    }
+    int chunk = blockIdx.x;
+    K mine    = K(0);
+    if (chunk < numChunks) { mine = leaves[min(chunk * LEAVES + t, numLeaves)]; }
+
+    for (int it = 0; chunk < numChunks; ++it, chunk += gridDim.x)
+    {
+        const int b = it % STAGES;
+        // keep STAGES - 1 windows in flight: the stage that was consumed in the previous iteration is free again
+        const int ahead = chunk + (STAGES - 1) * gridDim.x;
+        if (t == 0 && ahead < numChunks) { issue(ahead, (it + STAGES - 1) % STAGES); }
+        // this thread's leaf key of the next chunk, one iteration ahead of its use
+        const int nextChunk = chunk + gridDim.x;
+        K mineNext          = K(0);
+        if (nextChunk < numChunks) { mineNext = leaves[min(nextChunk * LEAVES + t, numLeaves)]; }
+
+        mbarWait(&bar[b], uint32_t(it / STAGES) & 1u);
+        const NcStageMeta m = meta[b];
+        const int c0        = chunk * LEAVES;
+        const int nl        = min(LEAVES, numLeaves - c0);
+        K* window           = buffers + size_t(b) * BUF + m.shift;
+        if (m.staged)
+        {
+            if (m.headEnd || m.tailBegin < m.width) // first / last window of the key array only
+            {
+                for (uint32_t i = t; i < m.headEnd; i += LEAVES)
+                    window[i] = keys[m.first + i];
+                for (uint32_t i = m.tailBegin + t; i < m.width; i += LEAVES)
+                    window[i] = keys[m.first + i];
+                __syncthreads();
+            }
+            if (t < nl) { bound[t] = lowerBound(window, m.width, mine); }
+        }
+        else if (t < nl) { bound[t] = uint32_t(lowerBound(keys + m.first, size_t(m.width), mine)); }
+        if (t == 0) { bound[nl] = m.width; }
+        __syncthreads();
+        if (t < nl)
+        {
+            const uint32_t c = bound[t + 1] - bound[t];
+            counts[c0 + t]   = c < maxCount ? c : maxCount;
+        }
+        __syncthreads(); // stage b and bound[] are free
+        mine = mineNext;
     }
 }
 
@@ -196,13 +314,21 @@ int computeNodeCounts(const K* leaves, uint32_t* counts, int numLeaves, const K*
 {
     if (numLeaves <= 0) { return 0; }
     CSB_REQUIRE(n < (size_t(1) << 32), "computeNodeCounts supports fewer than 2^32 keys");
-    const int numChunks = int(iceil(numLeaves, NC_LEAVES));
+    using Shape         = NcPipeShape<128, 6144, 2>; // 2 x 48 KiB of 64-bit keys per block, two blocks per SM
+    const int numChunks = int(iceil(numLeaves, Shape::leaves));
     CSB_SCRATCH(coarse, uint64_t*, s, SCRATCH_E, (size_t(numChunks) + 1) * sizeof(uint64_t));
-    coarseBoundsKernel<K><<<iceil(numChunks + 1, 128), 128, 0, s>>>(leaves, numLeaves, keys, n, numChunks, coarse);
+    coarseBoundsKernel<K><<<iceil((size_t(numChunks) + 1) * 32, 128), 128, 0, s>>>(leaves, numLeaves, keys, n, numChunks,
+                                                                                    Shape::leaves, coarse);
     CSB_LAUNCH_CHECK();
-    constexpr size_t smem = size_t(NC_WINDOW) * sizeof(K);
-    CSB_CHECK(cudaFuncSetAttribute(nodeCountsKernel<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
-    nodeCountsKernel<K><<<numChunks, NC_THREADS, smem, s>>>(leaves, counts, numLeaves, keys, coarse, maxCount);
+    int dev = 0, numSm = 0;
+    CSB_CHECK(cudaGetDevice(&dev));
+    CSB_CHECK(cudaDeviceGetAttribute(&numSm, cudaDevAttrMultiProcessorCount, dev));
+    constexpr size_t smem = size_t(Shape::stages) * (Shape::window + 48 / sizeof(K)) * sizeof(K);
+    CSB_CHECK(cudaFuncSetAttribute(nodeCountsPipelinedKernel<K, Shape>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                   int(smem)));
+    const int grid = std::min(numChunks, numSm * 2);
+    nodeCountsPipelinedKernel<K, Shape><<<grid, Shape::leaves, smem, s>>>(leaves, counts, numLeaves, keys, n, coarse,
+                                                                         numChunks, maxCount);
     CSB_LAUNCH_CHECK();
     return 0;
 }

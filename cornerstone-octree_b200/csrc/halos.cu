@@ -81,7 +81,7 @@ __global__ void __launch_bounds__(256) boundingBoxKernel(const T* __restrict__ x
 /* ---------------------------------------------------------------- collisions */
 
 template<class K, class T>
-__device__ inline K sfc3DHilbert(T x, T y, T z, const Box<T>& box)
+__device__ inline K sfc3DHilbert(T x, T y, T z, const Box<T>& box, const unsigned char* hilbertTables)
 {
     constexpr unsigned cubeLength = 1u << KeyTraits<K>::maxLevel;
     constexpr int mcoord          = int(cubeLength - 1);
@@ -92,12 +92,13 @@ __device__ inline K sfc3DHilbert(T x, T y, T z, const Box<T>& box)
     ix     = min(ix, mcoord);
     iy     = min(iy, mcoord);
     iz     = min(iz, mcoord);
-    return iHilbertLoop<K>(unsigned(ix), unsigned(iy), unsigned(iz));
+    return hilbertEncode<K>(unsigned(ix), unsigned(iy), unsigned(iz), hilbertTables);
 }
 
 //! traversal/boxoverlap.hpp:127-152
 template<class K, class T>
-__device__ inline bool containedIn(K codeStart, K codeEnd, const T* c, const T* s, const Box<T>& box)
+__device__ inline bool containedIn(K codeStart, K codeEnd, const T* c, const T* s, const Box<T>& box,
+                                   const unsigned char* hilbertTables)
 {
     T bmin[3], bmax[3];
     T dFromMin = 0, dFromMax = 0;
@@ -118,8 +119,8 @@ __device__ inline bool containedIn(K codeStart, K codeEnd, const T* c, const T* 
     for (int d = 0; d < 3; ++d)
         bmax[d] += box.len[d] * (T(1) / gridDim_);
 
-    K lowCode      = sfc3DHilbert<K>(bmin[0], bmin[1], bmin[2], box);
-    K highCode     = sfc3DHilbert<K>(bmax[0], bmax[1], bmax[2], box);
+    K lowCode      = sfc3DHilbert<K>(bmin[0], bmin[1], bmin[2], box, hilbertTables);
+    K highCode     = sfc3DHilbert<K>(bmax[0], bmax[1], bmax[2], box, hilbertTables);
     unsigned level = unsigned(commonPrefix(lowCode, highCode)) / 3;
     K nodeStart    = lowCode & ~(nodeRange<K>(level) - 1);
     K nodeEnd      = nodeStart + nodeRange<K>(level);
@@ -158,6 +159,9 @@ __global__ void __launch_bounds__(128) findHalosKernel(const K* __restrict__ pre
                                                        int lastLeaf,
                                                        uint8_t* flags)
 {
+    __shared__ unsigned char hilbertTables[hilbertTableBytes];
+    stageHilbertTables(hilbertTables);
+    __syncthreads();
     int leaf = firstLeaf + blockIdx.x * blockDim.x + threadIdx.x;
     if (leaf >= lastLeaf) { return; }
 
@@ -166,7 +170,7 @@ __global__ void __launch_bounds__(128) findHalosKernel(const K* __restrict__ pre
     T tc[3]      = {searchCenters[3 * leaf], searchCenters[3 * leaf + 1], searchCenters[3 * leaf + 2]};
     T ts[3]      = {searchSizes[3 * leaf], searchSizes[3 * leaf + 1], searchSizes[3 * leaf + 2]};
 
-    if (containedIn(lowestKey, highestKey, tc, ts, box)) { return; }
+    if (containedIn(lowestKey, highestKey, tc, ts, box, hilbertTables)) { return; }
 
     auto overlaps = [&](int idx)
     {

@@ -50,6 +50,9 @@ __global__ void __launch_bounds__(128) markMacsKernel(const K* __restrict__ pref
                                                       int numFocusNodes,
                                                       uint8_t* markings)
 {
+    __shared__ unsigned char hilbertTables[hilbertTableBytes];
+    stageHilbertTables(hilbertTables);
+    __syncthreads();
     const int tid          = blockIdx.x * blockDim.x + threadIdx.x;
     constexpr int maxCoord = 1 << KeyTraits<K>::maxLevel;
     constexpr T uL         = T(1) / maxCoord;
@@ -65,7 +68,7 @@ __global__ void __launch_bounds__(128) markMacsKernel(const K* __restrict__ pref
     unsigned cubeLength = unsigned(maxCoord) >> level;
     unsigned mask       = ~(cubeLength - 1);
     unsigned ix, iy, iz;
-    decodeHilbert(a, ix, iy, iz);
+    hilbertDecode(a, ix, iy, iz, hilbertTables);
     int lo[3] = {int(ix & mask), int(iy & mask), int(iz & mask)};
     int hi[3] = {lo[0] + int(cubeLength), lo[1] + int(cubeLength), lo[2] + int(cubeLength)};
     /* containedIn(focusStart, focusEnd, leaf box extended by one unit) (traversal/boxoverlap.hpp:96-117) without

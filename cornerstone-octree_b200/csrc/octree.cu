@@ -139,6 +139,12 @@ template<class K, class T>
 __global__ void geoCentersKernel(int kind, const K* __restrict__ prefixes, int numNodes, T* __restrict__ centers,
                                  T* __restrict__ sizes, Box<T> box)
 {
+    __shared__ unsigned char hilbertTables[hilbertTableBytes];
+    if (kind == 0)
+    {
+        stageHilbertTables(hilbertTables);
+        __syncthreads();
+    }
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= numNodes) { return; }
     constexpr int maxCoord = 1 << KeyTraits<K>::maxLevel;
@@ -150,7 +156,7 @@ __global__ void geoCentersKernel(int kind, const K* __restrict__ prefixes, int n
     unsigned cubeLength = unsigned(maxCoord) >> level;
     unsigned mask       = ~(cubeLength - 1);
     unsigned ix, iy, iz;
-    if (kind == 0) { decodeHilbert(startKey, ix, iy, iz); }
+    if (kind == 0) { hilbertDecode(startKey, ix, iy, iz, hilbertTables); }
     else { decodeMorton(startKey, ix, iy, iz); }
     int imin[3] = {int(ix & mask), int(iy & mask), int(iz & mask)};
 #pragma unroll

@@ -5,7 +5,7 @@
  * here the curve is a finite state machine over (axis permutation, axis flips) advanced THREE levels per lookup
  * through a 512-entry-per-state table staged in shared memory, so a 64-bit key costs 7 LDS + ~100 integer ops and
  * the kernel stays HBM-bound (40 B/particle for u64/double).  x,y,z,key traffic uses 128-bit vector accesses.
- * The state machine is derived on the host by composing the reference's per-level flip/rotate rules, so it encodes
+ * The state machine (hilbert.cuh) is derived by composing the reference's per-level flip/rotate rules, so it encodes
  * exactly the same curve (checked bit-for-bit against the oracle in tests/).
  */
 #include <mutex>
@@ -13,6 +13,7 @@
 
 #include "common.cuh"
 #include "cstone_b200.h"
+#include "hilbert.cuh"
 
 namespace csb
 {
@@ -20,47 +21,7 @@ namespace csb
 namespace
 {
 
-/* ---------------------------------------------------------------- host: Hilbert state machine construction */
-
-struct HState
-{
-    int perm[3];
-    int flip[3];
-};
-
-inline int stateCode(const HState& s)
-{
-    return ((s.perm[0] * 3 + s.perm[1]) * 3 + s.perm[2]) * 8 + (s.flip[0] << 2 | s.flip[1] << 1 | s.flip[2]);
-}
-
-//! one level of hilbert.hpp:59-91 applied to raw coordinate bits (rx,ry,rz) under transformation state s
-inline HState hilbertStep(const HState& s, unsigned rx, unsigned ry, unsigned rz, unsigned& digit)
-{
-    static const unsigned mortonToHilbert[8] = {0, 1, 3, 2, 7, 6, 4, 5};
-    unsigned raw[3]                          = {rx, ry, rz};
-    unsigned t[3];
-    for (int a = 0; a < 3; ++a)
-        t[a] = raw[s.perm[a]] ^ unsigned(s.flip[a]);
-    unsigned xi = t[0], yi = t[1], zi = t[2];
-    digit       = mortonToHilbert[(xi << 2) | (yi << 1) | zi];
-
-    unsigned F[3];
-    F[0] = xi & ((!yi) | zi);
-    F[1] = (xi & (yi | zi)) | (yi & (!zi));
-    F[2] = (xi & (!yi) & (!zi)) | (yi & (!zi));
-
-    int q[3] = {0, 1, 2};
-    if (zi) { q[0] = 1, q[1] = 2, q[2] = 0; } // px <- py, py <- pz, pz <- px
-    else if (!yi) { q[0] = 2, q[1] = 1, q[2] = 0; } // swap x,z
-
-    HState n;
-    for (int a = 0; a < 3; ++a)
-    {
-        n.perm[a] = s.perm[q[a]];
-        n.flip[a] = s.flip[q[a]] ^ int(F[q[a]] & 1u);
-    }
-    return n;
-}
+/* ---------------------------------------------------------------- host: three-level table of the state machine */
 
 struct HilbertLut
 {
@@ -70,43 +31,26 @@ struct HilbertLut
 
 HilbertLut buildHilbertLut()
 {
-    // enumerate reachable states, identity first
-    std::vector<HState> states;
-    std::vector<int> idOf(6 * 27 * 8, -1);
-    HState id{{0, 1, 2}, {0, 0, 0}};
-    states.push_back(id);
-    idOf[stateCode(id)] = 0;
-    for (size_t i = 0; i < states.size(); ++i)
-    {
-        for (unsigned o = 0; o < 8; ++o)
-        {
-            unsigned d;
-            HState n = hilbertStep(states[i], (o >> 2) & 1, (o >> 1) & 1, o & 1, d);
-            if (idOf[stateCode(n)] < 0)
-            {
-                idOf[stateCode(n)] = int(states.size());
-                states.push_back(n);
-            }
-        }
-    }
-
+    // the one-level machine of hilbert.cuh, advanced three levels per table entry
+    const HilbertFsm& fsm = hilbertFsm;
     HilbertLut lut;
-    lut.numStates = int(states.size());
+    lut.numStates = fsm.numStates;
     lut.table.resize(size_t(lut.numStates) * 512);
     for (int s = 0; s < lut.numStates; ++s)
     {
         for (unsigned c = 0; c < 512; ++c)
         {
             unsigned cx = (c >> 6) & 7, cy = (c >> 3) & 7, cz = c & 7;
-            HState cur  = states[s];
+            int cur      = s;
             unsigned key = 0;
             for (int b = 2; b >= 0; --b)
             {
-                unsigned d;
-                cur = hilbertStep(cur, (cx >> b) & 1, (cy >> b) & 1, (cz >> b) & 1, d);
-                key = (key << 3) | d;
+                unsigned octant = (((cx >> b) & 1) << 2) | (((cy >> b) & 1) << 1) | ((cz >> b) & 1);
+                unsigned e      = fsm.enc[cur * 8 + octant];
+                key             = (key << 3) | (e & 7u);
+                cur             = int(e >> 3);
             }
-            lut.table[size_t(s) * 512 + c] = uint16_t((idOf[stateCode(cur)] << 9) | key);
+            lut.table[size_t(s) * 512 + c] = uint16_t((cur << 9) | key);
         }
     }
     return lut;
