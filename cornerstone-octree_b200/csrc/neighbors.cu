@@ -301,6 +301,24 @@ __device__ __forceinline__ void appendIf(uint32_t& outLo, uint32_t& outHi, unsig
     }
 }
 
+//! the reference's acceptance test with the periodic fold of findneighbors.hpp:33-48, applied if the target's search
+//! sphere leaves the box (usePbc, :104-106)
+template<class T>
+__device__ __noinline__ bool exactInsidePbc(const T* __restrict__ x, const T* __restrict__ y, const T* __restrict__ z,
+                                            uint32_t j, T tx, T ty, T tz, T radiusSq, bool usePbc, const Box<T>& box)
+{
+    T dx = x[j] - tx;
+    T dy = y[j] - ty;
+    T dz = z[j] - tz;
+    if (usePbc)
+    {
+        dx = pbcFold(dx, 0, box);
+        dy = pbcFold(dy, 1, box);
+        dz = pbcFold(dz, 2, box);
+    }
+    return dx * dx + dy * dy + dz * dz < radiusSq;
+}
+
 constexpr int NB_MAX_DEPTH = 23; // >= maxTreeLevel<uint64_t> + 2
 constexpr int NB_STAGE     = 64; // staged candidates per round (two half-rounds of 32 loads)
 
@@ -319,7 +337,7 @@ struct alignas(16) WarpShared
  *  fold is needed is decided per warp (any lane whose search sphere leaves the box); such warps run the reference
  *  expressions directly on broadcast loads, lanes that do not need the fold select the unfolded difference exactly as
  *  the reference picks per particle (findneighbors.hpp:104-106,150-151).  Interior warps take the staged path. */
-template<class T, bool PBC>
+template<class T, bool PBC, bool FOLD>
 __device__ __forceinline__ void warpSearch(WarpShared& sh, const uint2 grp, const T* __restrict__ x, const T* __restrict__ y,
                            const T* __restrict__ z, const T* __restrict__ h, uint32_t first, const Box<T>& box,
                            const int* __restrict__ childOffsets, const int* __restrict__ parents,
@@ -373,6 +391,24 @@ __device__ __forceinline__ void warpSearch(WarpShared& sh, const uint2 grp, cons
         r2b = __int_as_float(0x7f800000);
     }
     // every staged (un-culled) candidate has |coordinate| <= 1.01 (DwT + sqrt(r2max)), see the cull test
+    /* Warps that touch a periodic boundary: if the group and its search spheres are small against the box (they always
+     * are unless the box holds only a few leaves), every lane sees the same periodic image of a nearby particle or node,
+     * so the fold is applied ONCE while staging, to the coordinates relative to the group origin, and the certified
+     * single-precision path runs unchanged; the shell it cannot decide (and nodes that are large against the box) take
+     * the reference's own folded expressions per lane.  Otherwise, and for float searches (whose staged operands must be
+     * the reference's), the whole warp evaluates the reference expressions directly (slowPbc). */
+    bool foldOk = Filt && FOLD;
+    if (PBC && Filt && FOLD)
+    {
+        const float reach = 1.01f * sqrtf(r2max);
+        const float ext[3] = {hix - lox, hiy - loy, hiz - loz};
+#pragma unroll
+        for (int d = 0; d < 3; ++d)
+            if (box.pbc(d) && !(ext[d] + reach < 0.124f * float(box.len[d]))) { foldOk = false; }
+    }
+    const bool slowPbc = warpPbc && !foldOk;
+    const bool foldPbc = warpPbc && foldOk;
+
     const float Dpair = 1.01f * (DwT + sqrtf(r2max));
     const float Epair = Dpair * Dpair * 0x1p-29f;
     const float pairA = fmaf(-Epair, BAND_SA, r2a);
@@ -443,7 +479,8 @@ __device__ __forceinline__ void warpSearch(WarpShared& sh, const uint2 grp, cons
                         bool in = s[c] < thrLo;
                         if (!in && !(s[c] > thrHi) && k + c < cnt)
                         {
-                            in = exactInside(x, y, z, jj[c], t.x, t.y, t.z, t.radiusSq);
+                            in = foldPbc ? exactInsidePbc(x, y, z, jj[c], t.x, t.y, t.z, t.radiusSq, t.usePbc, box)
+                                         : exactInside(x, y, z, jj[c], t.x, t.y, t.z, t.radiusSq);
                         }
                         if (in && jj[c] != i) { append(jj[c]); }
                     }
@@ -464,9 +501,9 @@ __device__ __forceinline__ void warpSearch(WarpShared& sh, const uint2 grp, cons
         int leafIdx = internalToLeaf[node];
         uint32_t jb = layout[leafIdx];
         uint32_t je = layout[leafIdx + 1];
-        if (warpPbc)
+        if (slowPbc)
         {
-            // warps touching a periodic boundary: the reference expressions on broadcast loads
+            // the reference expressions on broadcast loads
             for (uint32_t j = jb; j < je; ++j)
             {
                 T dx = x[j] - t.x;
@@ -514,9 +551,16 @@ __device__ __forceinline__ void warpSearch(WarpShared& sh, const uint2 grp, cons
                 float c0 = 0, c1 = 0, c2 = 0;
                 if (j < je)
                 {
-                    c0 = float(x[j] - ox);
-                    c1 = float(y[j] - oy);
-                    c2 = float(z[j] - oz);
+                    T rx = x[j] - ox, ry = y[j] - oy, rz = z[j] - oz;
+                    if (foldPbc)
+                    {
+                        rx = pbcFold(rx, 0, box);
+                        ry = pbcFold(ry, 1, box);
+                        rz = pbcFold(rz, 2, box);
+                    }
+                    c0 = float(rx);
+                    c1 = float(ry);
+                    c2 = float(rz);
                     float D  = fmaxf(fmaxf(fabsf(c0), fabsf(c1)), fmaxf(fabsf(c2), DwT));
                     float bc = fmaf(D * D * 0x1p-27f, BAND_SB, r2bMax);
                     float ex = fmaxf(fmaxf(lox - c0, c0 - hix), 0.0f);
@@ -565,7 +609,7 @@ __device__ __forceinline__ void warpSearch(WarpShared& sh, const uint2 grp, cons
     auto testChildren = [&](int child0, bool mine) -> uint32_t
     {
         uint32_t bits = 0;
-        if (warpPbc)
+        if (slowPbc)
         {
             if (mine)
             {
@@ -581,16 +625,28 @@ __device__ __forceinline__ void warpSearch(WarpShared& sh, const uint2 grp, cons
         {
             int node = child0 + int(lane);
             float4 gc, gs;
-            gc.x = float(centers[3 * node] - ox);
-            gc.y = float(centers[3 * node + 1] - oy);
-            gc.z = float(centers[3 * node + 2] - oz);
-            gc.w = 0.0f;
+            T rx = centers[3 * node] - ox, ry = centers[3 * node + 1] - oy, rz = centers[3 * node + 2] - oz;
             gs.x = float(sizes[3 * node]);
             gs.y = float(sizes[3 * node + 1]);
             gs.z = float(sizes[3 * node + 2]);
+            bool large = false; // a node that is large against the periodic box: the lanes may see different images
+            if (foldPbc)
+            {
+                rx    = pbcFold(rx, 0, box);
+                ry    = pbcFold(ry, 1, box);
+                rz    = pbcFold(rz, 2, box);
+                large = (box.pbc(0) && !(gs.x < 0.124f * float(box.len[0]))) ||
+                        (box.pbc(1) && !(gs.y < 0.124f * float(box.len[1]))) ||
+                        (box.pbc(2) && !(gs.z < 0.124f * float(box.len[2])));
+            }
+            gc.x = float(rx);
+            gc.y = float(ry);
+            gc.z = float(rz);
+            gc.w = 0.0f;
             float D = fmaxf(fmaxf(fmaxf(fabsf(gc.x), fabsf(gc.y)), fmaxf(fabsf(gc.z), DwT)),
                             fmaxf(gs.x, fmaxf(gs.y, gs.z)));
-            gs.w          = D * D * 0x1p-27f;
+            // an infinite error term sends every lane to the reference's own (folded) test and keeps the node reachable
+            gs.w          = large ? __int_as_float(0x7f800000) : D * D * 0x1p-27f;
             sh.geoC[lane] = gc;
             sh.geoS[lane] = gs;
             // warp-level cull: a child whose box is certainly farther from the targets' bounding box than the
@@ -619,7 +675,7 @@ __device__ __forceinline__ void warpSearch(WarpShared& sh, const uint2 grp, cons
                     pass     = s2 < fmaf(-gs.w, BAND_SA, r2a);
                     if (!pass && !(s2 > fmaf(gs.w, BAND_SB, r2b)))
                     {
-                        pass = cellOverlap<false>(t, centers, sizes, child0 + c, box);
+                        pass = cellOverlap<PBC>(t, centers, sizes, child0 + c, box);
                     }
                 }
                 else
@@ -690,7 +746,11 @@ __device__ __forceinline__ void warpSearch(WarpShared& sh, const uint2 grp, cons
     if (valid) { neighborsCount[i - first] = ngmax - uint32_t((long long)(rowEnd - out) >> 2); }
 }
 
-template<class T, bool PBC>
+/*! DEFER (periodic boxes): groups with a target whose search sphere crosses a periodic boundary are not searched here
+ *  but appended to `deferred` ([0] = count, then group numbers); this launch then runs the code of the open-box search
+ *  for all interior groups, and a second launch (groupList = deferred) handles the few boundary groups with the
+ *  periodic code, whose register footprint would otherwise slow down every warp. */
+template<class T, bool PBC, bool FOLD, bool DEFER>
 __global__ void __launch_bounds__(NB_THREADS) findNeighborsKernel(const T* __restrict__ x,
                                                                   const T* __restrict__ y,
                                                                   const T* __restrict__ z,
@@ -698,6 +758,8 @@ __global__ void __launch_bounds__(NB_THREADS) findNeighborsKernel(const T* __res
                                                                   uint32_t first,
                                                                   const uint2* __restrict__ groups,
                                                                   const uint32_t* __restrict__ numGroupsPtr,
+                                                                  const uint32_t* __restrict__ groupList,
+                                                                  uint32_t* __restrict__ deferred,
                                                                   Box<T> box,
                                                                   const int* __restrict__ childOffsets,
                                                                   const int* __restrict__ parents,
@@ -710,10 +772,30 @@ __global__ void __launch_bounds__(NB_THREADS) findNeighborsKernel(const T* __res
                                                                   uint32_t* __restrict__ neighborsCount)
 {
     __shared__ WarpShared shAll[NB_THREADS / 32];
-    const size_t warpId = (size_t(blockIdx.x) * NB_THREADS + threadIdx.x) >> 5;
-    if (warpId >= size_t(*numGroupsPtr)) { return; }
-    warpSearch<T, PBC>(shAll[threadIdx.x >> 5], groups[warpId], x, y, z, h, first, box, childOffsets, parents,
-                       internalToLeaf, layout, centers, sizes, ngmax, neighbors, neighborsCount);
+    size_t warpId = (size_t(blockIdx.x) * NB_THREADS + threadIdx.x) >> 5;
+    if (groupList)
+    {
+        if (warpId >= size_t(groupList[0])) { return; }
+        warpId = groupList[1 + warpId];
+    }
+    else if (warpId >= size_t(*numGroupsPtr)) { return; }
+    const uint2 grp = groups[warpId];
+    if (DEFER)
+    {
+        const unsigned lane = threadIdx.x & 31;
+        const uint32_t i    = min(grp.x + lane, grp.y - 1);
+        const T tx = x[i], ty = y[i], tz = z[i], s = T(2) * h[i];
+        // insideBox of findneighbors.hpp:104-106
+        const bool inside = (tx - s >= box.lim[0]) && (ty - s >= box.lim[2]) && (tz - s >= box.lim[4]) &&
+                            (tx + s <= box.lim[1]) && (ty + s <= box.lim[3]) && (tz + s <= box.lim[5]);
+        if (__any_sync(0xffffffffu, !inside))
+        {
+            if (lane == 0) { deferred[1 + atomicAdd(&deferred[0], 1u)] = uint32_t(warpId); }
+            return;
+        }
+    }
+    warpSearch<T, PBC, FOLD>(shAll[threadIdx.x >> 5], grp, x, y, z, h, first, box, childOffsets, parents, internalToLeaf,
+                             layout, centers, sizes, ngmax, neighbors, neighborsCount);
 }
 
 } // namespace
@@ -751,9 +833,25 @@ int findNeighbors(const T* x, const T* y, const T* z, const T* h, uint32_t first
     CSB_LAUNCH_CHECK();
 
     unsigned grid = iceil(maxGroups * 32, NB_THREADS);
-    auto kernel   = pbc ? findNeighborsKernel<T, true> : findNeighborsKernel<T, false>;
-    kernel<<<grid, NB_THREADS, 0, s>>>(x, y, z, h, first, groups, groupOffsets + numLeaves, box, childOffsets, parents,
-                                       internalToLeaf, layout, centers, sizes, ngmax, neighbors, neighborsCount);
+    if (!pbc)
+    {
+        findNeighborsKernel<T, false, false, false><<<grid, NB_THREADS, 0, s>>>(
+            x, y, z, h, first, groups, groupOffsets + numLeaves, nullptr, nullptr, box, childOffsets, parents,
+            internalToLeaf, layout, centers, sizes, ngmax, neighbors, neighborsCount);
+    }
+    else
+    {
+        // interior groups with the open-box code, then the groups at the periodic boundaries
+        CSB_SCRATCH(deferred, uint32_t*, s, SCRATCH_E, (maxGroups + 1) * sizeof(uint32_t));
+        CSB_CHECK(cudaMemsetAsync(deferred, 0, sizeof(uint32_t), s));
+        findNeighborsKernel<T, false, false, true><<<grid, NB_THREADS, 0, s>>>(
+            x, y, z, h, first, groups, groupOffsets + numLeaves, nullptr, deferred, box, childOffsets, parents,
+            internalToLeaf, layout, centers, sizes, ngmax, neighbors, neighborsCount);
+        CSB_LAUNCH_CHECK();
+        findNeighborsKernel<T, true, true, false><<<grid, NB_THREADS, 0, s>>>(
+            x, y, z, h, first, groups, groupOffsets + numLeaves, deferred, nullptr, box, childOffsets, parents,
+            internalToLeaf, layout, centers, sizes, ngmax, neighbors, neighborsCount);
+    }
     CSB_LAUNCH_CHECK();
     return 0;
 }

@@ -20,6 +20,8 @@ ap.add_argument("n", nargs="?", type=int, default=64 * 1024 * 1024)
 ap.add_argument("--config", default="uniform")
 ap.add_argument("--only", default="")
 ap.add_argument("--reps", type=int, default=3)
+ap.add_argument("--pbc", type=int, default=0)
+ap.add_argument("--knob3", default="0")
 args = ap.parse_args()
 
 dev = torch.device("cuda:0")
@@ -34,7 +36,7 @@ else:
     x, y, z = (torch.rand(n, dtype=torch.float32, device=dev, generator=g).clamp_(max=0.99999994) for _ in range(3))
     h = torch.full((n,), bench.h_for(n, 300), dtype=torch.float32, device=dev)
     ngmax, key, real = 384, "u32", "f"
-dom = capi.Domain(0, 1, bench.BUCKET, bench.BUCKET, 0.5, (0, 1, 0, 1, 0, 1), (0, 0, 0), key=key, real=real,
+dom = capi.Domain(0, 1, bench.BUCKET, bench.BUCKET, 0.5, (0, 1, 0, 1, 0, 1), (args.pbc,) * 3, key=key, real=real,
                   device="cuda:0")
 dom.sync(x, y, z, h)
 del x, y, z, h
@@ -44,7 +46,7 @@ if args.only:
     combos = [tuple(int(v) for v in args.only.split(","))]
 nb = torch.zeros(n * ngmax, dtype=torch.uint32, device=dev)
 nc = torch.zeros(n, dtype=torch.uint32, device=dev)
-for kern, grp in combos:
+for kern, grp in [(k3, g) for k3 in [int(v) for v in args.knob3.split(',')] for _, g in combos]:
     capi.tuning_set(1, grp)
     ms = []
     for _ in range(args.reps):
