@@ -866,8 +866,14 @@ void computeBoundingBoxGpu(execution::Gpu exec, const Tc* x, const Tc* y, const 
                            const LocalIndex* layout, TreeNodeIndex first, TreeNodeIndex last, Th scale,
                            Vec3<Tc>* centers, Vec3<Tc>* sizes)
 {
-    static_assert(std::is_same_v<Tc, Th>, "mixed coordinate / smoothing-length precision is not exported yet");
-    if constexpr (std::is_same_v<Tc, float>)
+    if constexpr (std::is_same_v<Tc, double> && std::is_same_v<Th, float>)
+    {
+        csCheck(cs_compute_bounding_boxes_df(x, y, z, h, layout, first, last, scale,
+                                             reinterpret_cast<double*>(centers), reinterpret_cast<double*>(sizes),
+                                             cudaStream_t(exec)),
+                "computeBoundingBoxGpu");
+    }
+    else if constexpr (std::is_same_v<Tc, float>)
     {
         csCheck(cs_compute_bounding_boxes_f(x, y, z, h, layout, first, last, scale, reinterpret_cast<float*>(centers),
                                             reinterpret_cast<float*>(sizes), cudaStream_t(exec)),
@@ -882,6 +888,9 @@ void computeBoundingBoxGpu(execution::Gpu exec, const Tc* x, const Tc* y, const 
 }
 template void computeBoundingBoxGpu(execution::Gpu, const double*, const double*, const double*, const double*,
                                     const LocalIndex*, TreeNodeIndex, TreeNodeIndex, double, Vec3<double>*,
+                                    Vec3<double>*);
+template void computeBoundingBoxGpu(execution::Gpu, const double*, const double*, const double*, const float*,
+                                    const LocalIndex*, TreeNodeIndex, TreeNodeIndex, float, Vec3<double>*,
                                     Vec3<double>*);
 template void computeBoundingBoxGpu(execution::Gpu, const float*, const float*, const float*, const float*,
                                     const LocalIndex*, TreeNodeIndex, TreeNodeIndex, float, Vec3<float>*, Vec3<float>*);

@@ -210,6 +210,14 @@ public:
 
     ~DomainImpl() override
     {
+        for (auto ps : pushStreams_)
+        {
+            cudaStreamSynchronize(ps);
+            cudaStreamDestroy(ps);
+        }
+        for (auto e : pushDone_)
+            cudaEventDestroy(e);
+        if (pushReady_) { cudaEventDestroy(pushReady_); }
         if (copyStream_)
         {
             cudaStreamSynchronize(copyStream_);
@@ -675,7 +683,10 @@ public:
         CSB_CHECK(cudaStreamSynchronize(s));
         fLower_.assign(b.begin(), b.begin() + P + 1);
         fAssign_.assign(P, {0, 0});
-        std::vector<int> flat(size_t(2) * P);
+        // (a member: the asynchronous upload below reads it after this function has returned; the next call writes it
+        // only after its own download has synchronised the stream)
+        std::vector<int>& flat = fAssignFlat_;
+        flat.resize(size_t(2) * P);
         for (int r = 0; r < P; ++r)
         {
             int lo = b[r], hi = b[P + 1 + r + 1];
@@ -687,7 +698,6 @@ public:
         // device copy of the focus assignment for the layout / halo request kernels
         CSB_TRY(fAssignDev_.resize(flat.size(), s));
         CSB_CHECK(cudaMemcpyAsync(fAssignDev_.p, flat.data(), flat.size() * sizeof(int), cudaMemcpyHostToDevice, s));
-        CSB_CHECK(cudaStreamSynchronize(s)); // flat is a host temporary
         return 0;
     }
 
@@ -868,7 +878,9 @@ public:
         Comm& comm          = *comm_;
         const int numLeaves = fTree_.numLeaves;
         // leaves outside my and my peers' ranges take their counts from the global tree (layout.hpp:59-91)
-        std::vector<int> idxFromGlob;
+        // (a member: uploaded asynchronously, rewritten only after later synchronisations of this function's callers)
+        std::vector<int>& idxFromGlob = idxFromGlob_;
+        idxFromGlob.clear();
         {
             int cur = 0;
             for (auto r : peerRanges_)
@@ -889,7 +901,6 @@ public:
                                   s));
         CSB_TRY(rangeCount<K>(gLeaves_.p, numGlobalLeaves_, gCountScan_.p, fLeaves_.p, idxBuf_.p, int(idxFromGlob.size()),
                               fLeafCounts_.p, s));
-        CSB_CHECK(cudaStreamSynchronize(s)); // idxFromGlob is a host temporary
 
         CSB_TRY(fCounts_.resize(fTree_.numNodes, s));
         CSB_TRY(scatterCounts(fTree_.leafToInternalLeaves(), numLeaves, fLeafCounts_.p, fCounts_.p, s));
@@ -946,8 +957,8 @@ public:
         CSB_CHECK(cudaMemsetAsync(layout_.p + lastNode, 0, sizeof(uint32_t), s));
         CSB_TRY(scanTmp_.resize(scanTempBytes(cnt + 1), s));
         CSB_TRY(exclusiveScanU32(layout_.p + firstNode, layout_.p + firstNode, cnt + 1, scanTmp_.p, s));
-        CSB_TRY(computeBoundingBoxes<T>(sx_.p, sy_.p, sz_.p, sh_.p, layout_.p, firstNode, lastNode, T(2),
-                                        searchCenters_.p, searchSizes_.p, s));
+        CSB_TRY((computeBoundingBoxes<T, T>(sx_.p, sy_.p, sz_.p, sh_.p, layout_.p, firstNode, lastNode, T(2),
+                                            searchCenters_.p, searchSizes_.p, s)));
         CSB_CHECK(cudaMemsetAsync(macs_.p, 0, size_t(fTree_.numNodes), s));
         return findHalos<K, T>(fTree_.prefixes.p, fTree_.childOffsets.p, fTree_.parents.p, geoCenters_.p, geoSizes_.p,
                                fLeaves_.p, searchCenters_.p, searchSizes_.p, focusLim_, bnd_, firstNode, lastNode,
@@ -1360,8 +1371,23 @@ private:
                     if (r != me) { received += allCounts[size_t(r) * P + me]; }
                 CSB_REQUIRE(received == numRecv,
                             "exchangeParticles: incoming particle count does not match the assignment");
-                // destinations in the order me+1, me+2, ...: at any time every rank is the target of one sender
-                // instead of all ranks storing into rank 0 first
+                // one pack kernel per destination, all in flight together on side streams (a single kernel does not
+                // keep enough bytes in flight to fill an NVLink direction); destinations in the order me+1, me+2, ...
+                // so that the senders start with different targets
+                if (pushStreams_.empty())
+                {
+                    pushStreams_.resize(4);
+                    for (auto& ps : pushStreams_)
+                        CSB_CHECK(cudaStreamCreateWithFlags(&ps, cudaStreamNonBlocking));
+                    CSB_CHECK(cudaEventCreateWithFlags(&pushReady_, cudaEventDisableTiming));
+                    pushDone_.resize(pushStreams_.size());
+                    for (auto& e : pushDone_)
+                        CSB_CHECK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+                }
+                CSB_CHECK(cudaEventRecord(pushReady_, s)); // ordering and particle arrays are final on s
+                for (auto& ps : pushStreams_)
+                    CSB_CHECK(cudaStreamWaitEvent(ps, pushReady_, 0));
+                int launched = 0;
                 for (int k = 1; k < P; ++k)
                 {
                     const int r = (me + k) % P;
@@ -1374,8 +1400,14 @@ private:
                     void* dst4[4];
                     for (int k = 0; k < 4; ++k)
                         dst4[k] = static_cast<T*>(peers[size_t(r) * 4 + k]) + dstOffset;
-                    CSB_TRY(cs_gather4(ordering_.p + start_ + sendIdx[r], c, src4, dst4, int(sizeof(T)), s));
+                    cudaStream_t ps = pushStreams_[size_t(launched++) % pushStreams_.size()];
+                    CSB_TRY(cs_gather4(ordering_.p + start_ + sendIdx[r], c, src4, dst4, int(sizeof(T)), ps));
                     comm.bytesSent += 4 * c * sizeof(T);
+                }
+                for (size_t q = 0; q < pushStreams_.size(); ++q)
+                {
+                    CSB_CHECK(cudaEventRecord(pushDone_[q], pushStreams_[q]));
+                    CSB_CHECK(cudaStreamWaitEvent(s, pushDone_[q], 0));
                 }
                 CSB_CHECK(cudaStreamSynchronize(s)); // my stores have landed ...
                 return comm.barrier(s);              // ... and so have everybody else's
@@ -1603,6 +1635,7 @@ private:
     std::vector<int> fLower_;                                                // findNodeAbove of the rank boundaries
     std::vector<std::pair<int, int>> fAssign_, peerRanges_;
     std::vector<int> extPeers_, intPeers_, haloExtPeers_, haloIntPeers_, globDispl_, treeletOffsets_, outNumRanges_;
+    std::vector<int> fAssignFlat_, idxFromGlob_; // host sources of asynchronous uploads
     std::vector<uint32_t> layoutAt_, runsAt_; // layout / halo-run number at {first, last leaf of rank r}..., total
     std::vector<size_t> outTableOff_, outTotals_;
     std::vector<std::pair<uint32_t, uint32_t>> incoming_;
@@ -1630,6 +1663,9 @@ private:
     bool firstCall_{true};
     LocalIndex start_{0}, end_{0}, bufSize_{0};
     cudaStream_t copyStream_{nullptr}; // upload of h from host memory, concurrent with the first stages of sync
+    std::vector<cudaStream_t> pushStreams_; // exchangeParticles through peer memory: pack kernels in flight together
+    cudaEvent_t pushReady_{nullptr};
+    std::vector<cudaEvent_t> pushDone_;
     cudaEvent_t copyReady_{nullptr}, copyDone_{nullptr};
     bool hUploadPending_{false};
 

@@ -123,9 +123,9 @@ size_t sortTempBytesU64(size_t n);
 size_t sortTempBytesU32(size_t n);
 
 /* halos.cu / neighbors.cu */
-template<class T>
-int computeBoundingBoxes(const T* x, const T* y, const T* z, const T* h, const uint32_t* layout, int firstLeaf,
-                         int lastLeaf, T scale, T* sc, T* ss, cudaStream_t s);
+template<class T, class Th>
+int computeBoundingBoxes(const T* x, const T* y, const T* z, const Th* h, const uint32_t* layout, int firstLeaf,
+                         int lastLeaf, Th scale, T* sc, T* ss, cudaStream_t s);
 template<class K, class T>
 int findHalos(const K* prefixes, const int* childOffsets, const int* parents, const T* centers, const T* sizes,
               const K* leaves, const T* searchCenters, const T* searchSizes, const double* lim, const int* bnd,

@@ -21,15 +21,17 @@ __device__ inline T shflXor(T v, int m)
     return __shfl_xor_sync(0xffffffffu, v, m);
 }
 
-template<class T>
+//! T: coordinate type, Th: type of the smoothing lengths and of `scale` (the reference instantiates (double, double),
+//! (double, float) and (float, float), focus/source_center_gpu.cu:90-92): r = h * scale is formed in Th and promoted
+template<class T, class Th>
 __global__ void __launch_bounds__(256) boundingBoxKernel(const T* __restrict__ x,
                                                          const T* __restrict__ y,
                                                          const T* __restrict__ z,
-                                                         const T* __restrict__ h,
+                                                         const Th* __restrict__ h,
                                                          const uint32_t* __restrict__ layout,
                                                          int firstLeaf,
                                                          int lastLeaf,
-                                                         T scale,
+                                                         Th scale,
                                                          T* __restrict__ sc,
                                                          T* __restrict__ ss)
 {
@@ -45,8 +47,9 @@ __global__ void __launch_bounds__(256) boundingBoxKernel(const T* __restrict__ x
     uint32_t jb = layout[l], je = layout[l + 1];
     for (uint32_t j = jb + sub; j < je; j += G)
     {
-        T r    = h[j] * scale;
-        T p[3] = {x[j], y[j], z[j]};
+        const Th rh = h[j] * scale;
+        const T r   = T(rh);
+        T p[3]      = {x[j], y[j], z[j]};
 #pragma unroll
         for (int d = 0; d < 3; ++d)
         {
@@ -216,13 +219,13 @@ __global__ void __launch_bounds__(128) findHalosKernel(const K* __restrict__ pre
 
 } // namespace
 
-template<class T>
-int computeBoundingBoxes(const T* x, const T* y, const T* z, const T* h, const uint32_t* layout, int firstLeaf,
-                         int lastLeaf, T scale, T* sc, T* ss, cudaStream_t s)
+template<class T, class Th>
+int computeBoundingBoxes(const T* x, const T* y, const T* z, const Th* h, const uint32_t* layout, int firstLeaf,
+                         int lastLeaf, Th scale, T* sc, T* ss, cudaStream_t s)
 {
     if (lastLeaf <= firstLeaf) { return 0; }
     size_t threads = size_t(lastLeaf - firstLeaf) * 8;
-    boundingBoxKernel<T><<<iceil(threads, 256), 256, 0, s>>>(x, y, z, h, layout, firstLeaf, lastLeaf, scale, sc, ss);
+    boundingBoxKernel<T, Th><<<iceil(threads, 256), 256, 0, s>>>(x, y, z, h, layout, firstLeaf, lastLeaf, scale, sc, ss);
     CSB_LAUNCH_CHECK();
     return 0;
 }
@@ -241,10 +244,12 @@ int findHalos(const K* prefixes, const int* childOffsets, const int* parents, co
     return 0;
 }
 
-template int computeBoundingBoxes<float>(const float*, const float*, const float*, const float*, const uint32_t*, int,
-                                         int, float, float*, float*, cudaStream_t);
-template int computeBoundingBoxes<double>(const double*, const double*, const double*, const double*, const uint32_t*,
-                                          int, int, double, double*, double*, cudaStream_t);
+template int computeBoundingBoxes<float, float>(const float*, const float*, const float*, const float*, const uint32_t*,
+                                                int, int, float, float*, float*, cudaStream_t);
+template int computeBoundingBoxes<double, double>(const double*, const double*, const double*, const double*,
+                                                  const uint32_t*, int, int, double, double*, double*, cudaStream_t);
+template int computeBoundingBoxes<double, float>(const double*, const double*, const double*, const float*,
+                                                 const uint32_t*, int, int, float, double*, double*, cudaStream_t);
 template int findHalos<uint32_t, float>(const uint32_t*, const int*, const int*, const float*, const float*,
                                         const uint32_t*, const float*, const float*, const double*, const int*, int,
                                         int, uint8_t*, cudaStream_t);
@@ -264,15 +269,23 @@ int cs_compute_bounding_boxes_f(const float* x, const float* y, const float* z, 
                                 int firstLeaf, int lastLeaf, float scale, float* searchCenters, float* searchSizes,
                                 void* stream)
 {
-    return csb::computeBoundingBoxes<float>(x, y, z, h, layout, firstLeaf, lastLeaf, scale, searchCenters, searchSizes,
+    return csb::computeBoundingBoxes<float, float>(x, y, z, h, layout, firstLeaf, lastLeaf, scale, searchCenters, searchSizes,
                                             cudaStream_t(stream));
 }
 int cs_compute_bounding_boxes_d(const double* x, const double* y, const double* z, const double* h,
                                 const uint32_t* layout, int firstLeaf, int lastLeaf, double scale,
                                 double* searchCenters, double* searchSizes, void* stream)
 {
-    return csb::computeBoundingBoxes<double>(x, y, z, h, layout, firstLeaf, lastLeaf, scale, searchCenters,
+    return csb::computeBoundingBoxes<double, double>(x, y, z, h, layout, firstLeaf, lastLeaf, scale, searchCenters,
                                              searchSizes, cudaStream_t(stream));
+}
+
+int cs_compute_bounding_boxes_df(const double* x, const double* y, const double* z, const float* h, const uint32_t* layout,
+                                 int firstLeaf, int lastLeaf, float scale, double* searchCenters, double* searchSizes,
+                                 void* stream)
+{
+    return csb::computeBoundingBoxes<double, float>(x, y, z, h, layout, firstLeaf, lastLeaf, scale, searchCenters,
+                                                    searchSizes, cudaStream_t(stream));
 }
 
 int cs_find_halos_u32f(const uint32_t* prefixes, const int* childOffsets, const int* parents, const float* centers,

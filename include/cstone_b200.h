@@ -152,6 +152,11 @@ int cs_compute_bounding_boxes_f(const float* x, const float* y, const float* z, 
 int cs_compute_bounding_boxes_d(const double* x, const double* y, const double* z, const double* h,
                                 const uint32_t* layout, int firstLeaf, int lastLeaf, double scale,
                                 double* searchCenters, double* searchSizes, void* stream);
+/* mixed precision: double coordinates, float smoothing lengths (the (double, float) instantiation of
+ * source_center_gpu.cu:91): r = h * scale is formed in float and promoted, as in the reference */
+int cs_compute_bounding_boxes_df(const double* x, const double* y, const double* z, const float* h,
+                                 const uint32_t* layout, int firstLeaf, int lastLeaf, float scale,
+                                 double* searchCenters, double* searchSizes, void* stream);
 /* findHalosGpu (traversal/collisions_gpu.h:46-58, collisions_gpu.cu:23-88): flags[numNodes] must be zeroed by the
  * caller unless accumulating */
 int cs_find_halos_u32f(const uint32_t* prefixes, const int* childOffsets, const int* parents, const float* centers,

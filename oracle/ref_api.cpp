@@ -179,15 +179,15 @@ void halos(const KeyType* prefixes,
               reinterpret_cast<const Vec3<T>*>(searchSizes), box, firstNode, lastNode, flags);
 }
 
-template<class T>
+template<class T, class Th = T>
 void boundingBoxes(const T* x,
                    const T* y,
                    const T* z,
-                   const T* h,
+                   const Th* h,
                    const unsigned* layout,
                    int firstLeaf,
                    int lastLeaf,
-                   T scale,
+                   Th scale,
                    T* searchCenters,
                    T* searchSizes)
 {
@@ -797,6 +797,12 @@ extern "C" void ref_bounding_boxes_f(const float* x, const float* y, const float
                                      float* ss)
 {
     boundingBoxes<float>(x, y, z, h, layout, firstLeaf, lastLeaf, scale, sc, ss);
+}
+extern "C" void ref_bounding_boxes_df(const double* x, const double* y, const double* z, const float* h,
+                                      const unsigned* layout, int firstLeaf, int lastLeaf, float scale, double* sc,
+                                      double* ss)
+{
+    boundingBoxes<double, float>(x, y, z, h, layout, firstLeaf, lastLeaf, scale, sc, ss);
 }
 extern "C" void ref_bounding_boxes_d(const double* x, const double* y, const double* z, const double* h,
                                      const unsigned* layout, int firstLeaf, int lastLeaf, double scale, double* sc,

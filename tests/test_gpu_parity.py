@@ -509,3 +509,32 @@ def test_sfc_keys_u32_from_double_coordinates(kind):
         keys = torch.zeros(n + off, dtype=torch.uint32, device="cuda")[off:]
         capi().compute_sfc_keys(dx, dy, dz, keys, lim, bnd, kind=kind)
         assert np.array_equal(host(keys), want), (kind, off)
+
+
+@pytest.mark.skipif(ref() is None, reason="needs oracle/_ref")
+def test_bounding_boxes_double_coordinates_float_h():
+    """computeBoundingBoxGpu<double, float> (focus/source_center_gpu.cu:91) vs the unmodified reference"""
+    import ctypes as C
+
+    from _libs import ref_lib
+    n, nl = 50000, 1000
+    rng = np.random.default_rng(3)
+    x, y, z = (rng.random(n) for _ in range(3))
+    h = (0.01 + 0.02 * rng.random(n)).astype(np.float32)
+    layout = np.sort(np.concatenate([[0, n], rng.integers(0, n, nl - 1)])).astype(np.uint32)
+    first, last = 17, nl - 5
+    init = rng.random((nl, 3))
+    want_c, want_s = init.copy(), np.zeros_like(init)
+    P = lambda a: a.ctypes.data_as(C.c_void_p)  # noqa: E731
+    ref_lib().ref_bounding_boxes_df(P(x), P(y), P(z), P(h), P(layout), C.c_int(first), C.c_int(last), C.c_float(2.0),
+                                    P(want_c), P(want_s))
+    sc, ss = dev(init.copy()), dev(np.zeros_like(init))
+    dx, dy, dz, dh, dl = dev(x), dev(y), dev(z), dev(h), dev(layout)
+    st = capi().lib().cs_compute_bounding_boxes_df(
+        C.c_void_p(dx.data_ptr()), C.c_void_p(dy.data_ptr()), C.c_void_p(dz.data_ptr()), C.c_void_p(dh.data_ptr()),
+        C.c_void_p(dl.data_ptr()), C.c_int(first), C.c_int(last), C.c_float(2.0), C.c_void_p(sc.data_ptr()),
+        C.c_void_p(ss.data_ptr()), None)
+    assert st == 0
+    torch.cuda.synchronize()
+    assert np.array_equal(host(sc)[first:last], want_c[first:last])
+    assert np.array_equal(host(ss)[first:last], want_s[first:last])
