@@ -1224,7 +1224,7 @@ public:
     int neighbors(uint32_t ngmax, uint32_t* nb, uint32_t* nc, cudaStream_t s) override
     {
         CSB_REQUIRE(!firstCall_, "findNeighbors needs a synchronised domain");
-        return findNeighbors<T>(x_.p, y_.p, z_.p, h_.p, start_, end_, lim_, bnd_, fTree_.numLeaves,
+        return findNeighbors<T, T>(x_.p, y_.p, z_.p, h_.p, start_, end_, lim_, bnd_, fTree_.numLeaves,
                                 fTree_.childOffsets.p,
                                 fTree_.parents.p, fTree_.internalToLeaf.p, layout_.p, geoCenters_.p, geoSizes_.p,
                                 ngmax, nb, nc, s);

@@ -130,8 +130,8 @@ template<class K, class T>
 int findHalos(const K* prefixes, const int* childOffsets, const int* parents, const T* centers, const T* sizes,
               const K* leaves, const T* searchCenters, const T* searchSizes, const double* lim, const int* bnd,
               int firstLeaf, int lastLeaf, uint8_t* flags, cudaStream_t s);
-template<class T>
-int findNeighbors(const T* x, const T* y, const T* z, const T* h, uint32_t first, uint32_t last, const double* lim,
+template<class T, class Th>
+int findNeighbors(const T* x, const T* y, const T* z, const Th* h, uint32_t first, uint32_t last, const double* lim,
                   const int* bnd, int numLeaves, const int* childOffsets, const int* parents,
                   const int* internalToLeaf, const uint32_t* layout, const T* centers, const T* sizes, uint32_t ngmax,
                   uint32_t* neighbors,

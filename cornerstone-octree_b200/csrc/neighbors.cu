@@ -337,9 +337,9 @@ struct alignas(16) WarpShared
  *  fold is needed is decided per warp (any lane whose search sphere leaves the box); such warps run the reference
  *  expressions directly on broadcast loads, lanes that do not need the fold select the unfolded difference exactly as
  *  the reference picks per particle (findneighbors.hpp:104-106,150-151).  Interior warps take the staged path. */
-template<class T, bool PBC, bool FOLD>
+template<class T, bool PBC, bool FOLD, class Th>
 __device__ __forceinline__ void warpSearch(WarpShared& sh, const uint2 grp, const T* __restrict__ x, const T* __restrict__ y,
-                           const T* __restrict__ z, const T* __restrict__ h, uint32_t first, const Box<T>& box,
+                           const T* __restrict__ z, const Th* __restrict__ h, uint32_t first, const Box<T>& box,
                            const int* __restrict__ childOffsets, const int* __restrict__ parents,
                            const int* __restrict__ internalToLeaf, const uint32_t* __restrict__ layout,
                            const T* __restrict__ centers, const T* __restrict__ sizes, uint32_t ngmax,
@@ -355,11 +355,12 @@ __device__ __forceinline__ void warpSearch(WarpShared& sh, const uint2 grp, cons
     t.x        = x[i];
     t.y        = y[i];
     t.z        = z[i];
-    const T hi = h[i];
-    t.radiusSq = T(4.0) * hi * hi;
+    // Th may be float with double coordinates: the radius is formed in Th and promoted (findneighbors.hpp:89-99)
+    const Th hi = h[i];
+    t.radiusSq  = T(Th(4.0) * hi * hi);
     {
         bool anyPbc = box.pbc(0) || box.pbc(1) || box.pbc(2);
-        T s         = T(2) * hi;
+        T s         = T(2) * T(hi);
         bool inside = (t.x - s >= box.lim[0]) && (t.y - s >= box.lim[2]) && (t.z - s >= box.lim[4]) &&
                       (t.x + s <= box.lim[1]) && (t.y + s <= box.lim[3]) && (t.z + s <= box.lim[5]);
         t.usePbc    = PBC && anyPbc && !inside;
@@ -750,11 +751,11 @@ __device__ __forceinline__ void warpSearch(WarpShared& sh, const uint2 grp, cons
  *  but appended to `deferred` ([0] = count, then group numbers); this launch then runs the code of the open-box search
  *  for all interior groups, and a second launch (groupList = deferred) handles the few boundary groups with the
  *  periodic code, whose register footprint would otherwise slow down every warp. */
-template<class T, bool PBC, bool FOLD, bool DEFER>
+template<class T, bool PBC, bool FOLD, bool DEFER, class Th>
 __global__ void __launch_bounds__(NB_THREADS) findNeighborsKernel(const T* __restrict__ x,
                                                                   const T* __restrict__ y,
                                                                   const T* __restrict__ z,
-                                                                  const T* __restrict__ h,
+                                                                  const Th* __restrict__ h,
                                                                   uint32_t first,
                                                                   const uint2* __restrict__ groups,
                                                                   const uint32_t* __restrict__ numGroupsPtr,
@@ -784,7 +785,7 @@ __global__ void __launch_bounds__(NB_THREADS) findNeighborsKernel(const T* __res
     {
         const unsigned lane = threadIdx.x & 31;
         const uint32_t i    = min(grp.x + lane, grp.y - 1);
-        const T tx = x[i], ty = y[i], tz = z[i], s = T(2) * h[i];
+        const T tx = x[i], ty = y[i], tz = z[i], s = T(2) * T(h[i]);
         // insideBox of findneighbors.hpp:104-106
         const bool inside = (tx - s >= box.lim[0]) && (ty - s >= box.lim[2]) && (tz - s >= box.lim[4]) &&
                             (tx + s <= box.lim[1]) && (ty + s <= box.lim[3]) && (tz + s <= box.lim[5]);
@@ -794,14 +795,14 @@ __global__ void __launch_bounds__(NB_THREADS) findNeighborsKernel(const T* __res
             return;
         }
     }
-    warpSearch<T, PBC, FOLD>(shAll[threadIdx.x >> 5], grp, x, y, z, h, first, box, childOffsets, parents, internalToLeaf,
+    warpSearch<T, PBC, FOLD, Th>(shAll[threadIdx.x >> 5], grp, x, y, z, h, first, box, childOffsets, parents, internalToLeaf,
                              layout, centers, sizes, ngmax, neighbors, neighborsCount);
 }
 
 } // namespace
 
-template<class T>
-int findNeighbors(const T* x, const T* y, const T* z, const T* h, uint32_t first, uint32_t last, const double* lim,
+template<class T, class Th>
+int findNeighbors(const T* x, const T* y, const T* z, const Th* h, uint32_t first, uint32_t last, const double* lim,
                   const int* bnd, int numLeaves, const int* childOffsets, const int* parents, const int* internalToLeaf,
                   const uint32_t* layout, const T* centers, const T* sizes, uint32_t ngmax, uint32_t* neighbors,
                   uint32_t* neighborsCount, cudaStream_t s)
@@ -835,7 +836,7 @@ int findNeighbors(const T* x, const T* y, const T* z, const T* h, uint32_t first
     unsigned grid = iceil(maxGroups * 32, NB_THREADS);
     if (!pbc)
     {
-        findNeighborsKernel<T, false, false, false><<<grid, NB_THREADS, 0, s>>>(
+        findNeighborsKernel<T, false, false, false, Th><<<grid, NB_THREADS, 0, s>>>(
             x, y, z, h, first, groups, groupOffsets + numLeaves, nullptr, nullptr, box, childOffsets, parents,
             internalToLeaf, layout, centers, sizes, ngmax, neighbors, neighborsCount);
     }
@@ -844,11 +845,11 @@ int findNeighbors(const T* x, const T* y, const T* z, const T* h, uint32_t first
         // interior groups with the open-box code, then the groups at the periodic boundaries
         CSB_SCRATCH(deferred, uint32_t*, s, SCRATCH_E, (maxGroups + 1) * sizeof(uint32_t));
         CSB_CHECK(cudaMemsetAsync(deferred, 0, sizeof(uint32_t), s));
-        findNeighborsKernel<T, false, false, true><<<grid, NB_THREADS, 0, s>>>(
+        findNeighborsKernel<T, false, false, true, Th><<<grid, NB_THREADS, 0, s>>>(
             x, y, z, h, first, groups, groupOffsets + numLeaves, nullptr, deferred, box, childOffsets, parents,
             internalToLeaf, layout, centers, sizes, ngmax, neighbors, neighborsCount);
         CSB_LAUNCH_CHECK();
-        findNeighborsKernel<T, true, true, false><<<grid, NB_THREADS, 0, s>>>(
+        findNeighborsKernel<T, true, true, false, Th><<<grid, NB_THREADS, 0, s>>>(
             x, y, z, h, first, groups, groupOffsets + numLeaves, deferred, nullptr, box, childOffsets, parents,
             internalToLeaf, layout, centers, sizes, ngmax, neighbors, neighborsCount);
     }
@@ -856,12 +857,18 @@ int findNeighbors(const T* x, const T* y, const T* z, const T* h, uint32_t first
     return 0;
 }
 
-template int findNeighbors<float>(const float*, const float*, const float*, const float*, uint32_t, uint32_t,
-                                  const double*, const int*, int, const int*, const int*, const int*, const uint32_t*,
-                                  const float*, const float*, uint32_t, uint32_t*, uint32_t*, cudaStream_t);
-template int findNeighbors<double>(const double*, const double*, const double*, const double*, uint32_t, uint32_t,
-                                   const double*, const int*, int, const int*, const int*, const int*, const uint32_t*,
-                                   const double*, const double*, uint32_t, uint32_t*, uint32_t*, cudaStream_t);
+template int findNeighbors<float, float>(const float*, const float*, const float*, const float*, uint32_t, uint32_t,
+                                         const double*, const int*, int, const int*, const int*, const int*,
+                                         const uint32_t*, const float*, const float*, uint32_t, uint32_t*, uint32_t*,
+                                         cudaStream_t);
+template int findNeighbors<double, double>(const double*, const double*, const double*, const double*, uint32_t,
+                                           uint32_t, const double*, const int*, int, const int*, const int*, const int*,
+                                           const uint32_t*, const double*, const double*, uint32_t, uint32_t*,
+                                           uint32_t*, cudaStream_t);
+template int findNeighbors<double, float>(const double*, const double*, const double*, const float*, uint32_t, uint32_t,
+                                          const double*, const int*, int, const int*, const int*, const int*,
+                                          const uint32_t*, const double*, const double*, uint32_t, uint32_t*, uint32_t*,
+                                          cudaStream_t);
 
 } // namespace csb
 
@@ -873,7 +880,7 @@ int cs_find_neighbors_f(const float* x, const float* y, const float* z, const fl
                         const int* parents, const int* internalToLeaf, const uint32_t* layout, const float* centers,
                         const float* sizes, uint32_t ngmax, uint32_t* neighbors, uint32_t* neighborsCount, void* stream)
 {
-    return csb::findNeighbors<float>(x, y, z, h, firstId, lastId, lim, bnd, numLeaves, childOffsets, parents,
+    return csb::findNeighbors<float, float>(x, y, z, h, firstId, lastId, lim, bnd, numLeaves, childOffsets, parents,
                                      internalToLeaf, layout, centers, sizes, ngmax, neighbors, neighborsCount,
                                      cudaStream_t(stream));
 }
@@ -884,9 +891,21 @@ int cs_find_neighbors_d(const double* x, const double* y, const double* z, const
                         const double* sizes, uint32_t ngmax, uint32_t* neighbors, uint32_t* neighborsCount,
                         void* stream)
 {
-    return csb::findNeighbors<double>(x, y, z, h, firstId, lastId, lim, bnd, numLeaves, childOffsets, parents,
+    return csb::findNeighbors<double, double>(x, y, z, h, firstId, lastId, lim, bnd, numLeaves, childOffsets, parents,
                                       internalToLeaf, layout, centers, sizes, ngmax, neighbors, neighborsCount,
                                       cudaStream_t(stream));
+}
+
+/* double coordinates, float smoothing lengths (Th != Tc, findneighbors.hpp:89-99): radiusSq is formed in float */
+int cs_find_neighbors_df(const double* x, const double* y, const double* z, const float* h, uint32_t firstId,
+                         uint32_t lastId, const double* lim, const int* bnd, int numLeaves, const int* childOffsets,
+                         const int* parents, const int* internalToLeaf, const uint32_t* layout, const double* centers,
+                         const double* sizes, uint32_t ngmax, uint32_t* neighbors, uint32_t* neighborsCount,
+                         void* stream)
+{
+    return csb::findNeighbors<double, float>(x, y, z, h, firstId, lastId, lim, bnd, numLeaves, childOffsets, parents,
+                                             internalToLeaf, layout, centers, sizes, ngmax, neighbors, neighborsCount,
+                                             cudaStream_t(stream));
 }
 
 } // extern "C"

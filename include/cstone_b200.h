@@ -186,6 +186,12 @@ int cs_find_neighbors_d(const double* x, const double* y, const double* z, const
                         const int* parents, const int* internalToLeaf, const uint32_t* layout, const double* centers,
                         const double* sizes, uint32_t ngmax, uint32_t* neighbors, uint32_t* neighborsCount,
                         void* stream);
+/* double coordinates, float smoothing lengths (Th != Tc, findneighbors.hpp:89-99) */
+int cs_find_neighbors_df(const double* x, const double* y, const double* z, const float* h, uint32_t firstId,
+                         uint32_t lastId, const double* lim, const int* bnd, int numLeaves, const int* childOffsets,
+                         const int* parents, const int* internalToLeaf, const uint32_t* layout, const double* centers,
+                         const double* sizes, uint32_t ngmax, uint32_t* neighbors, uint32_t* neighborsCount,
+                         void* stream);
 
 /* ---- focus-tree (LET) rebalance decisions: focus/rebalance_gpu.h:27-79 ----
  * rebalanceDecisionEssentialGpu: nodeOps[numNodes] from node counts and MAC flags of the fully linked tree, for the focus

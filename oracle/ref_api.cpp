@@ -117,11 +117,11 @@ void fpCenters(const KeyType* prefixes, size_t n, T* centers, T* sizes, const do
                            reinterpret_cast<Vec3<T>*>(sizes), box);
 }
 
-template<class KeyType, class T>
+template<class KeyType, class T, class Th = T>
 void neighbors(const T* x,
                const T* y,
                const T* z,
-               const T* h,
+               const Th* h,
                unsigned first,
                unsigned last,
                const double* lim,
@@ -705,6 +705,20 @@ extern "C" void ref_sfc_keys_u32d(int kind, const double* x, const double* y, co
                                   const double* lim, const int* bnd)
 {
     sfcKeys<uint32_t, double>(kind, x, y, z, keys, n, lim, bnd);
+}
+
+//! mixed precision (H4): double coordinates, float smoothing lengths
+extern "C" void ref_find_neighbors_u64df(const double* x, const double* y, const double* z, const float* h,
+                                         unsigned first, unsigned last, const double* lim, const int* bnd,
+                                         int numLeaves, int numNodes, const uint64_t* prefixes, const int* childOffsets,
+                                         const int* parents, const int* internalToLeaf, const int* leafToInternal,
+                                         const int* levelRange, const uint64_t* leaves, const unsigned* layout,
+                                         const double* centers, const double* sizes, unsigned ngmax, unsigned* nb,
+                                         unsigned* nc)
+{
+    neighbors<uint64_t, double, float>(x, y, z, h, first, last, lim, bnd, numLeaves, numNodes, prefixes, childOffsets,
+                                       parents, internalToLeaf, leafToInternal, levelRange, leaves, layout, centers,
+                                       sizes, ngmax, nb, nc);
 }
 
 CS_INST_KT(u32f, uint32_t, float)

@@ -538,3 +538,47 @@ def test_bounding_boxes_double_coordinates_float_h():
     torch.cuda.synchronize()
     assert np.array_equal(host(sc)[first:last], want_c[first:last])
     assert np.array_equal(host(ss)[first:last], want_s[first:last])
+
+
+@pytest.mark.skipif(ref() is None, reason="needs oracle/_ref")
+@pytest.mark.parametrize("pbc", [0, 1])
+def test_find_neighbors_double_coordinates_float_h(pbc):
+    """findNeighbors with Th = float, Tc = double (findneighbors.hpp:89-99): radiusSq is formed in float"""
+    import ctypes as C
+
+    from _libs import ref_lib
+    n, ngmax = 30000, 96
+    keys, (x, y, z), lim, _ = sorted_keys("u64d", n, "uniform")
+    bnd = (pbc, pbc, pbc)
+    lo, co = oracle().compute_octree("u64", keys, 16)
+    to = oracle().build_octree("u64", lo)
+    cen_o, siz_o = oracle().node_fp_centers("u64d", to["prefixes"], lim, bnd)
+    layout_o = np.zeros(lo.size, dtype=np.uint32)
+    layout_o[1:] = np.cumsum(co)
+    rng = np.random.default_rng(4)
+    h = (const_h(n, 40, np.float64, 8.0) * (0.6 + 0.8 * rng.random(n))).astype(np.float32)
+    P = lambda a: a.ctypes.data_as(C.c_void_p)  # noqa: E731
+    lim_a, bnd_a = np.array(lim, dtype=np.float64), np.array(bnd, dtype=np.int32)
+    nb_o, nc_o = np.zeros(n * ngmax, dtype=np.uint32), np.zeros(n, dtype=np.uint32)
+    ref_lib().ref_find_neighbors_u64df(P(x), P(y), P(z), P(h), C.c_uint(0), C.c_uint(n), P(lim_a), P(bnd_a),
+                                       C.c_int(to["numLeaves"]), C.c_int(to["numNodes"]), P(to["prefixes"]),
+                                       P(to["childOffsets"]), P(to["parents"]), P(to["internalToLeaf"]),
+                                       P(to["leafToInternal"]), P(to["levelRange"]), P(lo), P(layout_o), P(cen_o),
+                                       P(siz_o), C.c_uint(ngmax), P(nb_o), P(nc_o))
+    tree = capi().Octree(dev(lo))
+    cen, siz = capi().compute_geo_centers(tree.prefixes, torch.float64, lim, bnd)
+    dx, dy, dz, dh, dl = dev(x), dev(y), dev(z), dev(h), dev(layout_o)
+    nb = torch.zeros(n * ngmax, dtype=torch.uint32, device="cuda")
+    nc = torch.zeros(n, dtype=torch.uint32, device="cuda")
+    lim_c, bnd_c = (C.c_double * 6)(*lim), (C.c_int * 3)(*bnd)
+    V = lambda t: C.c_void_p(t.data_ptr())  # noqa: E731
+    st = capi().lib().cs_find_neighbors_df(V(dx), V(dy), V(dz), V(dh), C.c_uint32(0), C.c_uint32(n), lim_c, bnd_c,
+                                           C.c_int(tree.num_leaves), V(tree.child_offsets), V(tree.parents),
+                                           V(tree.internal_to_leaf), V(dl), V(cen), V(siz), C.c_uint32(ngmax), V(nb),
+                                           V(nc), None)
+    assert st == 0
+    torch.cuda.synchronize()
+    assert np.array_equal(host(nc), nc_o)
+    m = np.arange(ngmax)[None, :] < np.minimum(nc_o, ngmax)[:, None]
+    assert np.array_equal(host(nb).reshape(n, ngmax)[m], nb_o.reshape(n, ngmax)[m])
+    assert nc_o.max() > 10
