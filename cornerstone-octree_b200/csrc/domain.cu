@@ -186,6 +186,9 @@ struct DomainBase
     virtual int reset(cudaStream_t s)                                                              = 0;
     virtual int attachComm(Comm* c)                                                                = 0;
     virtual int exchangeHaloFields(void* const* arrays, const int* elemBytes, int numArrays, cudaStream_t s) = 0;
+    virtual int reapplySync(const void* const* before, void* const* after, const int* elemBytes, int numArrays,
+                            cudaStream_t s)                                                                  = 0;
+    virtual int replayInfo(uint64_t* info) const                                                             = 0;
     int keyBytes{0}, realBytes{0};
 };
 
@@ -231,6 +234,7 @@ public:
     int reset(cudaStream_t s) override
     {
         firstCall_ = true;
+        log_.valid = false;
         start_ = end_ = bufSize_ = 0;
         std::copy(lim0_, lim0_ + 6, lim_);
         const double unitBox[6] = {0, 1, 0, 1, 0, 1};
@@ -324,10 +328,12 @@ public:
         CSB_REQUIRE(size_t(bufSize_) < (size_t(1) << 30), "at most 2^30 - 1 particles per rank");
         CSB_REQUIRE(comm_->size() == numRanks_, "multi-rank domains need cs_domain_attach_comm before the first sync");
 
-        const size_t numPart = end_ - start_;
-        Comm& comm           = *comm_;
-        const int P          = comm.size();
-        const int me         = comm.rank();
+        const size_t numPart      = end_ - start_;
+        const LocalIndex prevSize = bufSize_;
+        Comm& comm                = *comm_;
+        const int P               = comm.size();
+        const int me              = comm.rank();
+        log_.valid                = false;
 
         phase(nullptr, s);
         /* ---- GlobalAssignment::assign (assignment.hpp:92-144) */
@@ -415,6 +421,9 @@ public:
             const LocalIndex recvStart = receiveStart(o1e, numRecv);
             std::vector<uint32_t> recvCounts;
             CSB_TRY(exchangeParticles(sendIdx, recvStart, numRecv, recvCounts, s));
+            log_.recvStart  = recvStart;
+            log_.numRecv    = numRecv;
+            log_.recvCounts = recvCounts;
             phase("exchangeParticles", s);
             assignedEnvelope(o1e, numRecv, &envStart, &envEnd);
             bufSize_ = exchangeSize;
@@ -470,6 +479,15 @@ public:
                 orderView = assignedOrder_.p;
             }
         }
+
+        // what reapplySync replays (ExchangeLog, domain/index_ranges.hpp:186-210, plus the assigned ordering)
+        log_.order       = orderView;
+        log_.numAssigned = numAssigned;
+        log_.prevStart   = start_;
+        log_.prevSize    = prevSize;
+        log_.sendIdx     = sendIdx;
+        if (P == 1) { log_.recvStart = log_.numRecv = 0, log_.recvCounts.assign(1, 0); }
+        log_.valid = true;
 
         phase("keys+sort received", s);
         /* ---- gatherArrays(x,y,z,h) to offset 0 (domain.hpp:187) */
@@ -1167,6 +1185,77 @@ public:
         return 0;
     }
 
+    /*! Domain::reapplySync (domain/domain.hpp:297-329): send further fields of the particles through the exchange that
+     *  the last sync performed.  before[k] holds the field in the particle order and buffer layout the caller had when
+     *  it called sync (replayInfo()[0] elements); after[k] (replayInfo()[1] elements, the current buffer size) receives
+     *  the values of the assigned particles at [startIndex, endIndex) in their new order, halos stay untouched.
+     *  The reference replays redoExchange (assignment.hpp:206-215) into the enlarged arrays and then gathers through
+     *  the stored ordering; here the incoming blocks land in a staging buffer and one kernel reads either side. */
+    int reapplySync(const void* const* before, void* const* after, const int* elemBytes, int numArrays,
+                    cudaStream_t s) override
+    {
+        CSB_REQUIRE(!firstCall_ && log_.valid, "reapplySync needs a completed sync to replay");
+        Comm& comm   = *comm_;
+        const int P  = comm.size();
+        const int me = comm.rank();
+        for (int k = 0; k < numArrays; ++k)
+            CSB_REQUIRE(before[k] != nullptr && after[k] != nullptr && elemBytes[k] > 0 && elemBytes[k] % 4 == 0,
+                        "reapplySync: element sizes must be positive multiples of 4 bytes");
+        auto pad16 = [](size_t b) { return (b + 15) & ~size_t(15); };
+        for (int k = 0; k < numArrays; ++k)
+        {
+            const size_t eb = size_t(elemBytes[k]);
+            const int words = elemBytes[k] / 4;
+            size_t recvOff  = 0;
+            if (P > 1)
+            {
+                size_t sendTotal = 0;
+                for (int r = 0; r < P; ++r)
+                    if (r != me) { sendTotal += pad16(size_t(log_.sendIdx[r + 1] - log_.sendIdx[r]) * eb); }
+                recvOff = sendTotal;
+                CSB_TRY(fieldSendBuf_.resize(std::max<size_t>(sendTotal + pad16(size_t(log_.numRecv) * eb), 16), s));
+                std::vector<CommMessage> sends, recvs;
+                size_t off = 0;
+                for (int r = 0; r < P; ++r)
+                {
+                    const uint32_t c = r == me ? 0 : log_.sendIdx[r + 1] - log_.sendIdx[r];
+                    if (c == 0) { continue; }
+                    CSB_TRY(gatherWords(ordering_.p + log_.prevStart + log_.sendIdx[r], c, words, before[k],
+                                        fieldSendBuf_.p + off, s));
+                    sends.push_back({r, fieldSendBuf_.p + off, size_t(c) * eb});
+                    off += pad16(size_t(c) * eb);
+                }
+                size_t received = 0;
+                for (int r = 0; r < P; ++r)
+                {
+                    const size_t c = log_.recvCounts[r];
+                    if (c == 0 || r == me) { continue; }
+                    recvs.push_back({r, fieldSendBuf_.p + recvOff + received * eb, c * eb});
+                    received += c;
+                }
+                CSB_REQUIRE(received == log_.numRecv, "reapplySync: the recorded exchange is inconsistent");
+                CSB_TRY(comm.exchange(sends, recvs, s));
+            }
+            CSB_TRY(replayGatherWords(log_.order, log_.numAssigned, words, before[k], fieldSendBuf_.p + recvOff,
+                                      log_.recvStart, log_.numRecv, static_cast<char*>(after[k]) + size_t(start_) * eb,
+                                      s));
+            // the staging buffer is reused by the next field
+            CSB_CHECK(cudaStreamSynchronize(s));
+        }
+        return 0;
+    }
+
+    //! {elements of the arrays before the sync, elements after, startIndex, endIndex}
+    int replayInfo(uint64_t* info) const override
+    {
+        CSB_REQUIRE(!firstCall_ && log_.valid, "reapplySync needs a completed sync to replay");
+        info[0] = log_.prevSize;
+        info[1] = bufSize_;
+        info[2] = start_;
+        info[3] = end_;
+        return 0;
+    }
+
     int attachComm(Comm* c) override
     {
         CSB_REQUIRE(c != nullptr, "null communicator");
@@ -1672,6 +1761,15 @@ private:
     DevBuf<T> x_, y_, z_, h_, sx_, sy_, sz_, sh_, partials_, geoCenters_, geoSizes_, sendBuf_;
     DevBuf<K> keys_, keyBuf_, boundaryKeys_, assignedKeys_;
     DevBuf<uint32_t> ordering_, valueBuf_, scalars_, gapCounts_, layout_, assignedOrder_;
+    //! the particle exchange of the last sync, kept for reapplySync; `order` points into ordering_ / assignedOrder_,
+    //! which stay untouched until the next sync
+    struct ReplayLog
+    {
+        bool valid{false};
+        const uint32_t* order{nullptr};
+        LocalIndex numAssigned{0}, prevStart{0}, prevSize{0}, recvStart{0}, numRecv{0};
+        std::vector<uint32_t> sendIdx, recvCounts;
+    } log_;
     DevBuf<unsigned char> sortTmp_, linkTmp_, opsTmp_, scanTmp_;
     DevBuf<int> nodeOps_, nodeOpsAll_;
 
@@ -1771,6 +1869,19 @@ int cs_domain_exchange_halos(cs_domain_t* d, void* const* arrays, const int* ele
 {
     CSB_REQUIRE(d != nullptr, "null domain");
     return csb::impl(d)->exchangeHaloFields(arrays, elemBytes, numArrays, cudaStream_t(stream));
+}
+
+int cs_domain_reapply_sync(cs_domain_t* d, const void* const* before, void* const* after, const int* elemBytes,
+                           int numArrays, void* stream)
+{
+    CSB_REQUIRE(d != nullptr, "null domain");
+    return csb::impl(d)->reapplySync(before, after, elemBytes, numArrays, cudaStream_t(stream));
+}
+
+int cs_domain_replay_info(const cs_domain_t* d, uint64_t* info4)
+{
+    CSB_REQUIRE(d != nullptr && info4 != nullptr, "null argument");
+    return csb::impl(const_cast<cs_domain_t*>(d))->replayInfo(info4);
 }
 
 int cs_domain_reset(cs_domain_t* d, void* stream)

@@ -83,6 +83,11 @@ int gatherU32(const int* idx, int n, const uint32_t* src, uint32_t* dst, cudaStr
 int scatterU32(const int* idx, int n, const uint32_t* src, uint32_t* dst, cudaStream_t s);
 int gatherRangesWords(const uint32_t* rangeScan, const uint32_t* rangeStart, int numRanges, uint32_t total, int words,
                       const void* src, void* out, cudaStream_t s);
+//! out[k] = src[order[k]], elements of `words` 32-bit words
+int gatherWords(const uint32_t* order, uint32_t n, int words, const void* src, void* out, cudaStream_t s);
+//! replay of a recorded particle exchange for one more field (reapplySync, domain/domain.hpp:297-329)
+int replayGatherWords(const uint32_t* order, uint32_t n, int words, const void* before, const void* received,
+                      uint32_t recvStart, uint32_t numRecv, void* out, cudaStream_t s);
 template<class E>
 int gatherRanges4(const uint32_t* rangeScan, const uint32_t* rangeStart, int numRanges, uint32_t total, const E* a,
                   const E* b, const E* c, const E* d, E* out, size_t blockElems, cudaStream_t s);

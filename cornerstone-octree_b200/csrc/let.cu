@@ -425,6 +425,33 @@ __global__ void gatherRangesWordsKernel(const uint32_t* __restrict__ rangeScan, 
     out[t]     = src[e * words + w];
 }
 
+/*! out[k] = value of the particle at exchange-buffer position order[k]: positions inside [recvStart, recvStart+numRecv)
+ *  come from the receive staging buffer, all others from the array as it was before the sync (the replay of
+ *  Domain::reapplySync, domain/domain.hpp:297-329, in one pass instead of redoExchange + gatherArrays) */
+__global__ void replayGatherWordsKernel(const uint32_t* __restrict__ order, uint32_t n, int words,
+                                        const uint32_t* __restrict__ before, const uint32_t* __restrict__ received,
+                                        uint32_t recvStart, uint32_t numRecv, uint32_t* __restrict__ out)
+{
+    size_t t = size_t(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (t >= size_t(n) * words) { return; }
+    uint32_t k = uint32_t(t / words);
+    int w      = int(t - size_t(k) * words);
+    uint32_t p = order[k];
+    uint32_t q = p - recvStart;
+    out[t]     = q < numRecv ? received[size_t(q) * words + w] : before[size_t(p) * words + w];
+}
+
+//! out[k] = src[order[k]] for elements of `words` 32-bit words
+__global__ void gatherWordsKernel(const uint32_t* __restrict__ order, uint32_t n, int words,
+                                  const uint32_t* __restrict__ src, uint32_t* __restrict__ out)
+{
+    size_t t = size_t(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (t >= size_t(n) * words) { return; }
+    uint32_t k = uint32_t(t / words);
+    int w      = int(t - size_t(k) * words);
+    out[t]     = src[size_t(order[k]) * words + w];
+}
+
 /* ---- device-side checkLayout (domain/layout.hpp:187-219), halo request keys (extractMarkedElements,
  *      domain/layout.hpp:110-141, per peer range) and their translation into outgoing index ranges
  *      (halos/halos.hpp:64-80, domain/exchange_keys.hpp:45-99) ---- */
@@ -682,6 +709,26 @@ int gatherRangesWords(const uint32_t* rangeScan, const uint32_t* rangeStart, int
     if (total == 0) { return 0; }
     gatherRangesWordsKernel<<<iceil(size_t(total) * words, 256), 256, 0, s>>>(
         rangeScan, rangeStart, numRanges, total, words, static_cast<const uint32_t*>(src), static_cast<uint32_t*>(out));
+    CSB_LAUNCH_CHECK();
+    return 0;
+}
+
+int gatherWords(const uint32_t* order, uint32_t n, int words, const void* src, void* out, cudaStream_t s)
+{
+    if (n == 0) { return 0; }
+    gatherWordsKernel<<<iceil(size_t(n) * words, 256), 256, 0, s>>>(order, n, words, static_cast<const uint32_t*>(src),
+                                                                    static_cast<uint32_t*>(out));
+    CSB_LAUNCH_CHECK();
+    return 0;
+}
+
+int replayGatherWords(const uint32_t* order, uint32_t n, int words, const void* before, const void* received,
+                      uint32_t recvStart, uint32_t numRecv, void* out, cudaStream_t s)
+{
+    if (n == 0) { return 0; }
+    replayGatherWordsKernel<<<iceil(size_t(n) * words, 256), 256, 0, s>>>(
+        order, n, words, static_cast<const uint32_t*>(before), static_cast<const uint32_t*>(received), recvStart,
+        numRecv, static_cast<uint32_t*>(out));
     CSB_LAUNCH_CHECK();
     return 0;
 }

@@ -481,6 +481,25 @@ class Domain:
             _check(lib().cs_domain_exchange_halos(C.c_void_p(self.handle), ptrs, sizes, C.c_int(n), _stream()),
                    "cs_domain_exchange_halos")
 
+    def reapply_sync(self, *fields):
+        """Domain::reapplySync: fields are device tensors in the particle order the last sync() consumed; returns new
+        tensors with n_particles_with_halos rows whose assigned rows [start_index, end_index) hold the fields of the
+        particles now assigned to this rank (halo rows are zero until exchange_halos)."""
+        info = (C.c_uint64 * 4)()
+        _check(lib().cs_domain_replay_info(C.c_void_p(self.handle), info), "cs_domain_replay_info")
+        n = len(fields)
+        outs = []
+        for f in fields:
+            assert f.is_cuda and f.is_contiguous() and f.shape[0] == info[0], (f.shape, info[0])
+            outs.append(torch.zeros((int(info[1]),) + tuple(f.shape[1:]), dtype=f.dtype, device=f.device))
+        src = (C.c_void_p * n)(*[f.data_ptr() for f in fields])
+        dst = (C.c_void_p * n)(*[o.data_ptr() for o in outs])
+        sizes = (C.c_int * n)(*[f.element_size() * (f.numel() // max(f.shape[0], 1)) for f in fields])
+        with torch.cuda.device(self.device):
+            _check(lib().cs_domain_reapply_sync(C.c_void_p(self.handle), src, dst, sizes, C.c_int(n), _stream()),
+                   "cs_domain_reapply_sync")
+        return outs
+
     def download(self, x, y, z, h, keys):
         """asynchronous device -> (pinned) host copy of the synchronised arrays"""
         ptrs = [C.c_void_p(t.data_ptr()) if t is not None else C.c_void_p(0) for t in (x, y, z, h, keys)]

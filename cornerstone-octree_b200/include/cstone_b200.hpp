@@ -15,6 +15,7 @@
 #include <stdexcept>
 #include <string>
 #include <type_traits>
+#include <utility>
 
 #include "cstone_b200.h"
 
@@ -275,6 +276,25 @@ public:
         void* ptrs[]  = {static_cast<void*>(arrays)...};
         int sizes[]   = {int(sizeof(Arrays))...};
         csCheck(cs_domain_exchange_halos(d_, ptrs, sizes, int(sizeof...(Arrays)), stream), "Domain::exchangeHalos");
+    }
+
+    /*! reapplySync(std::tie(fields...), ...) domain.hpp:297-329: replay the particle exchange and reordering of the last
+     *  sync for further fields.  Pass (before, after) device pointer pairs: `before` in the order the sync consumed
+     *  (replaySizeBefore() elements), `after` with nParticlesWithHalos() elements. */
+    template<class... Arrays>
+    void reapplySync(void* stream, std::pair<const Arrays*, Arrays*>... fields)
+    {
+        const void* src[] = {static_cast<const void*>(fields.first)...};
+        void* dst[]       = {static_cast<void*>(fields.second)...};
+        int sizes[]       = {int(sizeof(Arrays))...};
+        csCheck(cs_domain_reapply_sync(d_, src, dst, sizes, int(sizeof...(Arrays)), stream), "Domain::reapplySync");
+    }
+
+    uint64_t replaySizeBefore() const
+    {
+        uint64_t info[4];
+        csCheck(cs_domain_replay_info(d_, info), "Domain::replaySizeBefore");
+        return info[0];
     }
 
     cs_domain_t* handle() { return d_; }

@@ -325,6 +325,16 @@ int cs_domain_attach_comm(cs_domain_t* d, cs_comm_t* comm);
  * replaced by the owning ranks' values with the pattern recorded by the last cs_domain_sync.  No-op on one rank.
  * Synchronises the stream. */
 int cs_domain_exchange_halos(cs_domain_t* d, void* const* arrays, const int* elemBytes, int numArrays, void* stream);
+/* Domain::reapplySync(std::tie(fields...), sendBuf, recvBuf, ordering) (domain/domain.hpp:297-329) and the ExchangeLog
+ * it replays (domain/index_ranges.hpp:186-210, GlobalAssignment::redoExchange, domain/assignment.hpp:206-215): move
+ * further per-particle fields through the particle exchange and reordering of the LAST cs_domain_sync.  before[k] is
+ * the field as it was when that sync was called (info4[0] elements, same order and layout as the coordinates the sync
+ * consumed); after[k] (info4[1] = nParticlesWithHalos elements) receives the values of the assigned particles at
+ * [startIndex, endIndex), halo elements are not written.  Collective over the ranks of the domain; synchronises the
+ * stream.  cs_domain_replay_info: info4 = {elements before, elements after, startIndex, endIndex}. */
+int cs_domain_reapply_sync(cs_domain_t* d, const void* const* before, void* const* after, const int* elemBytes,
+                           int numArrays, void* stream);
+int cs_domain_replay_info(const cs_domain_t* d, uint64_t* info4);
 /* forget all tree state so that the next cs_domain_sync behaves like the first call on a new Domain (device buffers
  * are kept; used by bench.py to time cold syncs without re-allocating) */
 int cs_domain_reset(cs_domain_t* d, void* stream);

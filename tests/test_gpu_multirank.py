@@ -282,3 +282,74 @@ def test_exchange_halos_of_client_fields(combo, P, pbc):
     res = run_ranks(P, rank_body, world)
     assert all(ok for ok, _ in res)
     assert all(nh > 0 for _, nh in res), "the test needs halos to be meaningful"
+
+
+@pytest.mark.parametrize("combo,P,pbc,dist", [("u64d", 1, 0, "uniform"), ("u64d", 2, 0, "uniform"),
+                                              ("u64d", 4, 1, "gaussian"), ("u32f", 3, 0, "uniform"),
+                                              ("u64f", 8, 0, "uniform")])
+def test_reapply_sync_moves_client_fields_with_their_particles(combo, P, pbc, dist):
+    """Domain::reapplySync (domain.hpp:297-329, the ExchangeLog replay of index_ranges.hpp:186-210): fields that did not
+    take part in sync() are sent through the recorded exchange and reordered afterwards.  The fields are functions of
+    the coordinates computed BEFORE the sync (in the old order, on the old owners); after sync + reapplySync every
+    assigned row must equal the same function of the row's new coordinates, which sync() moved itself and which were
+    proven identical with the reference above.  Covers the first sync (input order -> SFC order), later syncs with
+    particles that migrate between ranks, and two replays of the same log."""
+    from test_gpu_domain import drift
+
+    n_per = 6000
+    n = n_per * P
+    x, y, z, lim = make_particles(combo, n, dist, 21)
+    T = real_of(combo)
+    h = const_h(n, 40, T, 8.0 if dist == "gaussian" else 1.0)
+    bnd = (pbc, pbc, pbc)
+    offsets = [n_per * r for r in range(P + 1)]
+    world = capi().LocalWorld(P)
+
+    def make_fields(fx, fy, fz):
+        rho = fx * 2 + fy
+        vel = torch.stack([fz, fx - fy, fy * fz], dim=1).contiguous()
+        tag = (fx * 100000).to(torch.int32)
+        quad = torch.stack([fx, fy, fz, fx + fz], dim=1).contiguous()
+        return rho, vel, tag, quad
+
+    def rank_body(r):
+        c = capi()
+        comm = world.comm(r)
+        dom = c.Domain(r, P, 64, 8, 0.5, lim, bnd, key=key_of(combo), real=combo[-1], device=DEV, comm=comm)
+        sl = slice(offsets[r], offsets[r + 1])
+        to = lambda a: torch.from_numpy(np.ascontiguousarray(a[sl])).to(DEV)  # noqa: E731
+        dx, dy, dz = to(x), to(y), to(z)
+        before = make_fields(dx, dy, dz)
+        dom.sync(dx, dy, dz, to(h))
+        moved = 0
+        for step in range(4):
+            after = dom.reapply_sync(*before)
+            again = dom.reapply_sync(*before[:2])
+            s, e = dom.start_index, dom.end_index
+            want = make_fields(dom.field("x"), dom.field("y"), dom.field("z"))
+            for a, w in zip(after, want):
+                assert a.shape[0] == dom.n_particles_with_halos
+                assert torch.equal(a[s:e], w[s:e]), (r, step)
+            for a, b in zip(after, again):
+                assert torch.equal(a[s:e], b[s:e]), (r, step)
+            if step == 3:
+                break
+            drift(dom, 0.08)
+            # the client's fields in the layout it holds now (assigned + halo rows), changed along with the particles
+            before = make_fields(dom.field("x").clone(), dom.field("y").clone(), dom.field("z").clone())
+            n_before = dom.end_index - dom.start_index
+            dom.sync()
+            moved += abs((dom.end_index - dom.start_index) - n_before)
+        dom.close()
+        comm.close()
+        return moved
+
+    run_ranks(P, rank_body, world)
+
+
+def test_reapply_sync_needs_a_sync_to_replay():
+    c = capi()
+    dom = c.Domain(0, 1, 64, 8, 0.5, (0, 1, 0, 1, 0, 1), (0, 0, 0), key="u64", real="d", device=DEV)
+    with pytest.raises(RuntimeError):
+        dom.reapply_sync(torch.zeros(4, device=DEV))
+    dom.close()
