@@ -74,6 +74,7 @@ enum TuningKnob : int
 {
     TUNE_NB_GROUPS = 1, // findNeighbors target groups: 0 (default) = full groups over runs of sibling leaves,
                         // 1 = leaf aligned
+    TUNE_NB_SEARCH = 2, // findNeighbors: 0 = pick by leaf occupancy, 1 = per-lane walks, 2 = group-steered search
     TUNE_COUNT     = 16
 };
 int tuning(int knob);

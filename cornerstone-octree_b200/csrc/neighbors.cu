@@ -21,6 +21,8 @@
  *  bounding box alone with certified acceptance, and a CTA-cooperative variant with shared staging); both returned
  *  identical lists and both were slower than this kernel, see profiles/r2_notes.md.
  */
+#include <algorithm>
+#include <cmath>
 #include <type_traits>
 
 #include "common.cuh"
@@ -218,13 +220,13 @@ __device__ inline float warpMaxF(float v) { return keyFloat(__reduce_max_sync(0x
 //! the reference's acceptance test (findneighbors.hpp:33-60,134); out of line so that the rare call does not get
 //! if-converted into the hot loop
 template<class T>
-__device__ __noinline__ bool exactInside(const T* __restrict__ x, const T* __restrict__ y, const T* __restrict__ z,
-                                         uint32_t j, T tx, T ty, T tz, T radiusSq)
+__device__ __noinline__ T exactDistSq(const T* __restrict__ x, const T* __restrict__ y, const T* __restrict__ z,
+                                      uint32_t j, T tx, T ty, T tz)
 {
     T ex = x[j] - tx;
     T ey = y[j] - ty;
     T ez = z[j] - tz;
-    return ex * ex + ey * ey + ez * ez < radiusSq;
+    return ex * ex + ey * ey + ez * ez;
 }
 
 __device__ __forceinline__ uint64_t pack2(float lo, float hi)
@@ -304,8 +306,8 @@ __device__ __forceinline__ void appendIf(uint32_t& outLo, uint32_t& outHi, unsig
 //! the reference's acceptance test with the periodic fold of findneighbors.hpp:33-48, applied if the target's search
 //! sphere leaves the box (usePbc, :104-106)
 template<class T>
-__device__ __noinline__ bool exactInsidePbc(const T* __restrict__ x, const T* __restrict__ y, const T* __restrict__ z,
-                                            uint32_t j, T tx, T ty, T tz, T radiusSq, bool usePbc, const Box<T>& box)
+__device__ __noinline__ T exactDistSqPbc(const T* __restrict__ x, const T* __restrict__ y, const T* __restrict__ z,
+                                         uint32_t j, T tx, T ty, T tz, bool usePbc, const Box<T>& box)
 {
     T dx = x[j] - tx;
     T dy = y[j] - ty;
@@ -316,13 +318,27 @@ __device__ __noinline__ bool exactInsidePbc(const T* __restrict__ x, const T* __
         dy = pbcFold(dy, 1, box);
         dz = pbcFold(dz, 2, box);
     }
-    return dx * dx + dy * dy + dz * dz < radiusSq;
+    return dx * dx + dy * dy + dz * dz;
+}
+
+template<class T>
+__device__ __forceinline__ bool exactInside(const T* __restrict__ x, const T* __restrict__ y, const T* __restrict__ z,
+                                            uint32_t j, T tx, T ty, T tz, T radiusSq)
+{
+    return exactDistSq(x, y, z, j, tx, ty, tz) < radiusSq;
+}
+template<class T>
+__device__ __forceinline__ bool exactInsidePbc(const T* __restrict__ x, const T* __restrict__ y,
+                                               const T* __restrict__ z, uint32_t j, T tx, T ty, T tz, T radiusSq,
+                                               bool usePbc, const Box<T>& box)
+{
+    return exactDistSqPbc(x, y, z, j, tx, ty, tz, usePbc, box) < radiusSq;
 }
 
 constexpr int NB_MAX_DEPTH = 23; // >= maxTreeLevel<uint64_t> + 2
 constexpr int NB_STAGE     = 64; // staged candidates per round (two half-rounds of 32 loads)
 
-struct alignas(16) WarpShared
+struct alignas(16) LaneWalkShared
 {
     // staged candidates: x, y, z (relative floats for T = double, the values themselves for T = float) and particle
     // index, padded to a multiple of four entries
@@ -332,13 +348,17 @@ struct alignas(16) WarpShared
     uint8_t mask[NB_MAX_DEPTH][32]; // per tree depth, per lane: which of the 8 siblings this lane's own walk enters
 };
 
+/* ================================================================ search with per-lane walks (the default)
+ * Every lane keeps the exact pruning state of the reference's own walk (a bit per sibling and tree depth); leaves are
+ * staged and tested one at a time for the lanes whose walk enters them. */
+
 /*! The search of ONE warp for the targets [grp.x, grp.y) (at most 32).
  *  PBC = false: the box has no periodic dimension, the fold code is not even compiled in.  PBC = true: whether the
  *  fold is needed is decided per warp (any lane whose search sphere leaves the box); such warps run the reference
  *  expressions directly on broadcast loads, lanes that do not need the fold select the unfolded difference exactly as
  *  the reference picks per particle (findneighbors.hpp:104-106,150-151).  Interior warps take the staged path. */
 template<class T, bool PBC, bool FOLD, class Th>
-__device__ __forceinline__ void warpSearch(WarpShared& sh, const uint2 grp, const T* __restrict__ x, const T* __restrict__ y,
+__device__ __forceinline__ void warpSearchLanes(LaneWalkShared& sh, const uint2 grp, const T* __restrict__ x, const T* __restrict__ y,
                            const T* __restrict__ z, const Th* __restrict__ h, uint32_t first, const Box<T>& box,
                            const int* __restrict__ childOffsets, const int* __restrict__ parents,
                            const int* __restrict__ internalToLeaf, const uint32_t* __restrict__ layout,
@@ -770,9 +790,13 @@ __global__ void __launch_bounds__(NB_THREADS) findNeighborsKernel(const T* __res
                                                                   const T* __restrict__ sizes,
                                                                   uint32_t ngmax,
                                                                   uint32_t* __restrict__ neighbors,
-                                                                  uint32_t* __restrict__ neighborsCount)
+                                                                  uint32_t* __restrict__ neighborsCount,
+                                                                  const uint32_t* __restrict__ numBad,
+                                                                  uint32_t badLimit)
 {
-    __shared__ WarpShared shAll[NB_THREADS / 32];
+    // the group-steered search runs instead (it was launched before this kernel with the same criterion)
+    if (numBad != nullptr && *numBad <= badLimit) { return; }
+    __shared__ LaneWalkShared shAll[NB_THREADS / 32];
     size_t warpId = (size_t(blockIdx.x) * NB_THREADS + threadIdx.x) >> 5;
     if (groupList)
     {
@@ -795,8 +819,702 @@ __global__ void __launch_bounds__(NB_THREADS) findNeighborsKernel(const T* __res
             return;
         }
     }
-    warpSearch<T, PBC, FOLD, Th>(shAll[threadIdx.x >> 5], grp, x, y, z, h, first, box, childOffsets, parents, internalToLeaf,
+    warpSearchLanes<T, PBC, FOLD, Th>(shAll[threadIdx.x >> 5], grp, x, y, z, h, first, box, childOffsets, parents, internalToLeaf,
                              layout, centers, sizes, ngmax, neighbors, neighborsCount);
+}
+
+/* ================================================================ group-steered search (trees with small leaves)
+ * The cost of the search above grows with the number of leaves a warp visits: staging and the per-lane tests of the
+ * nodes are paid per leaf, and the leaf occupancy of a tree jumps by 8x whenever the particle count crosses a power of
+ * 8 times the bucket size (64 Mi particles with bucket 64: 32 per leaf, 128 Mi: ~8, 256 Mi: 16).  This variant keeps no
+ * per-lane walk state at all and stages contiguous particle ranges whatever the leaf boundaries; its run time does not
+ * depend on the leaf occupancy (71 ms at 64 Mi particles for 8 and for 4 particles per leaf, where the per-lane search
+ * takes 106 and 160 ms), but at 32 particles per leaf the per-lane search is faster (52 vs 62 ms).  findNeighbors picks
+ * by the mean leaf occupancy. */
+
+constexpr int NB_CAP            = 96;  // staged candidates per test round (filled in rounds of up to 32 loads)
+constexpr uint32_t NB_COARSE    = 64;  // subtrees with at most this many particles are staged whole
+constexpr double NB_SMALL_LEAVES = 20;  // mean particles per leaf below which the group-steered search is used
+constexpr uint32_t NB_BAD_LEAF  = 0x80000000u; // in NodeRange::y: a particle of this leaf lies outside the leaf's box
+
+struct alignas(16) GroupWalkShared
+{
+    // staged candidates: x, y, z (relative floats for T = double, the values themselves for T = float) and particle
+    // index, padded to a multiple of four entries
+    float cx[NB_CAP + 4], cy[NB_CAP + 4], cz[NB_CAP + 4];
+    uint32_t cj[NB_CAP + 4];
+    uint8_t wm[NB_MAX_DEPTH + 1]; // per tree depth: the siblings the walk of the warp enters
+};
+
+/* ---- preparation: particle range of every node, leaves with stray particles ---- */
+
+//! particles [x, y) below every node (leaves: their layout range)
+__global__ void nodeRangeKernel(const int* __restrict__ childOffsets, const int* __restrict__ internalToLeaf,
+                                const uint32_t* __restrict__ layout, int numNodes, uint2* __restrict__ nodeRange)
+{
+    int node = blockIdx.x * blockDim.x + threadIdx.x;
+    if (node >= numNodes) { return; }
+    int a = node, b = node;
+    for (int c = childOffsets[a]; c != 0; c = childOffsets[a])
+        a = c;
+    for (int c = childOffsets[b]; c != 0; c = childOffsets[b])
+        b = c + 7;
+    nodeRange[node] = make_uint2(layout[internalToLeaf[a]], layout[internalToLeaf[b] + 1]);
+}
+
+/*! Marks the leaves (and all their ancestors) whose particles are not all inside the leaf's box, or whose box is not
+ *  inside the box of every ancestor up to tolNest; 8 lanes per leaf.  Keys are computed from the coordinates, so with
+ *  consistent input only particles within a rounding error of a cell face stray (none in double precision, about one
+ *  leaf in 200 in single), and the rounded boxes of a tree nest up to 3 ulp of the largest coordinate; particles beyond
+ *  the domain box (clamped keys) or arrays that do not belong to the tree are caught as well.  The search evaluates the
+ *  reference expressions directly on marked leaves and does not take marked subtrees whole. */
+template<class T>
+__global__ void leafContainmentKernel(const T* __restrict__ x, const T* __restrict__ y, const T* __restrict__ z,
+                                      const int* __restrict__ childOffsets, uint2* __restrict__ nodeRange,
+                                      const T* __restrict__ centers, const T* __restrict__ sizes, int numNodes,
+                                      T tolNest, const int* __restrict__ parents, uint32_t* __restrict__ numBad)
+{
+    const size_t tid = size_t(blockIdx.x) * blockDim.x + threadIdx.x;
+    const int node   = int(tid >> 3);
+    if (node >= numNodes || childOffsets[node] != 0) { return; }
+    const uint2 r = nodeRange[node];
+    const T cx = centers[3 * node], cy = centers[3 * node + 1], cz = centers[3 * node + 2];
+    const T sx = sizes[3 * node], sy = sizes[3 * node + 1], sz = sizes[3 * node + 2];
+    bool bad = false;
+    for (uint32_t j = r.x + uint32_t(tid & 7); j < (r.y & ~NB_BAD_LEAF); j += 8)
+        bad |= !(rabs(x[j] - cx) <= sx && rabs(y[j] - cy) <= sy && rabs(z[j] - cz) <= sz);
+    if ((tid & 7) == 0)
+    {
+        for (int a = node; a != 0;)
+        {
+            a = parents[(a - 1) >> 3];
+            bad |= !(rabs(cx - centers[3 * a]) + sx <= sizes[3 * a] + tolNest &&
+                     rabs(cy - centers[3 * a + 1]) + sy <= sizes[3 * a + 1] + tolNest &&
+                     rabs(cz - centers[3 * a + 2]) + sz <= sizes[3 * a + 2] + tolNest);
+        }
+    }
+    if (bad && !(atomicOr(&nodeRange[node].y, NB_BAD_LEAF) & NB_BAD_LEAF))
+    {
+        atomicAdd(numBad, 1u);
+        for (int a = node; a != 0;)
+        {
+            a = parents[(a - 1) >> 3];
+            atomicOr(&nodeRange[a].y, NB_BAD_LEAF);
+        }
+    }
+}
+
+/*! The reference's walk for one lane, restricted to the root-to-leaf path of particle j: true if the lane's own
+ *  traversal (findneighbors.hpp:108-112 at every node of the path) reaches the leaf that holds j.  The root has been
+ *  tested by the caller.  Rare: only for candidates in the thin shell below the search radius. */
+template<bool PBC, class T>
+__device__ __noinline__ bool walkReachesLeafOf(uint32_t j, const Target<T>& t, const int* __restrict__ childOffsets,
+                                               const uint2* __restrict__ nodeRange, const T* __restrict__ centers,
+                                               const T* __restrict__ sizes, const Box<T>& box)
+{
+    int node = 0;
+    while (true)
+    {
+        const int child = childOffsets[node];
+        if (child == 0) { return true; }
+        // the child whose particle range holds j (empty children share their start with the next sibling)
+        int k = 0;
+#pragma unroll
+        for (int m = 1; m < 8; ++m)
+            k += int(nodeRange[child + m].x <= j);
+        node = child + k;
+        if (!cellOverlap<PBC>(t, centers, sizes, node, box)) { return false; }
+    }
+}
+
+/*! Search of one warp in a periodic box whose fold cannot be applied once per warp (the group or its search spheres are
+ *  large against the box, or T = float): every lane keeps the exact state of the reference's own walk (a bit per
+ *  sibling and tree depth) and evaluates the reference expressions on broadcast loads. */
+template<class T, class Th>
+__device__ __noinline__ void warpSearchDirect(uint8_t (*mask)[32], const uint2 grp, const T* __restrict__ x,
+                                              const T* __restrict__ y, const T* __restrict__ z,
+                                              const Th* __restrict__ h, uint32_t first, const Box<T>& box,
+                                              const int* __restrict__ childOffsets, const int* __restrict__ parents,
+                                              const uint2* __restrict__ nodeRange, const T* __restrict__ centers,
+                                              const T* __restrict__ sizes, uint32_t ngmax,
+                                              uint32_t* __restrict__ neighbors, uint32_t* __restrict__ neighborsCount)
+{
+    const unsigned lane = threadIdx.x & 31;
+    const bool valid    = grp.x + lane < grp.y;
+    const uint32_t i    = valid ? grp.x + lane : grp.y - 1;
+    Target<T> t;
+    t.x         = x[i];
+    t.y         = y[i];
+    t.z         = z[i];
+    const Th hi = h[i];
+    t.radiusSq  = T(Th(4.0) * hi * hi);
+    {
+        T s         = T(2) * T(hi);
+        bool inside = (t.x - s >= box.lim[0]) && (t.y - s >= box.lim[2]) && (t.z - s >= box.lim[4]) &&
+                      (t.x + s <= box.lim[1]) && (t.y + s <= box.lim[3]) && (t.z + s <= box.lim[5]);
+        t.usePbc    = !inside;
+    }
+    uint32_t* row  = neighbors + size_t(i - first) * size_t(ngmax);
+    uint32_t count = 0;
+
+    auto scanLeaf = [&](int node, bool mine)
+    {
+        const uint2 r     = nodeRange[node];
+        const uint32_t je = r.y & ~NB_BAD_LEAF;
+        for (uint32_t j = r.x; j < je; ++j)
+        {
+            T dx = x[j] - t.x;
+            T dy = y[j] - t.y;
+            T dz = z[j] - t.z;
+            T fx = pbcFold(dx, 0, box);
+            T fy = pbcFold(dy, 1, box);
+            T fz = pbcFold(dz, 2, box);
+            dx   = t.usePbc ? fx : dx;
+            dy   = t.usePbc ? fy : dy;
+            dz   = t.usePbc ? fz : dz;
+            T d2 = dx * dx + dy * dy + dz * dz;
+            if (mine && j != i && d2 < t.radiusSq)
+            {
+                if (count < ngmax) { row[count] = j; }
+                ++count;
+            }
+        }
+    };
+    auto testChildren = [&](int child0, bool mine) -> uint32_t
+    {
+        uint32_t bits = 0;
+        if (mine)
+        {
+#pragma unroll
+            for (int c = 0; c < 8; ++c)
+                bits |= uint32_t(cellOverlap<true>(t, centers, sizes, child0 + c, box)) << c;
+        }
+        return bits;
+    };
+
+    const bool rootMine = valid && cellOverlap<true>(t, centers, sizes, 0, box);
+    if (__any_sync(0xffffffffu, rootMine))
+    {
+        int rootChild = childOffsets[0];
+        if (rootChild == 0) { scanLeaf(0, rootMine); }
+        else
+        {
+            int depth     = 1;
+            int base      = rootChild;
+            uint32_t lm   = testChildren(rootChild, rootMine);
+            mask[1][lane] = uint8_t(lm);
+            uint32_t wm   = __reduce_or_sync(0xffffffffu, lm);
+            while (true)
+            {
+                if (wm == 0)
+                {
+                    if (depth == 1) { break; }
+                    const int up = parents[(base - 1) >> 3];
+                    --depth;
+                    base = ((up - 1) & ~7) + 1;
+                    lm   = mask[depth][lane];
+                    wm   = __reduce_or_sync(0xffffffffu, lm) & ~((2u << ((up - 1) & 7)) - 1u);
+                    continue;
+                }
+                const int c = __ffs(int(wm)) - 1;
+                wm &= wm - 1;
+                const int node  = base + c;
+                const bool mine = (lm >> c) & 1u;
+                const int child = childOffsets[node];
+                if (child == 0) { scanLeaf(node, mine); }
+                else
+                {
+                    ++depth;
+                    lm                = testChildren(child, mine);
+                    mask[depth][lane] = uint8_t(lm);
+                    wm                = __reduce_or_sync(0xffffffffu, lm);
+                    base              = child;
+                }
+            }
+        }
+    }
+    if (valid) { neighborsCount[i - first] = count; }
+}
+
+/*! The search of ONE warp for the targets [grp.x, grp.y) (at most 32), lanes = targets.
+ *
+ *  The walk is steered by the bounding box of the warp's targets alone: 8 lanes test the 8 children of a node against
+ *  it (certified: a child that fails cannot pass the continuation test of any lane), subtrees with few particles are
+ *  taken whole, and the particle ranges of the visited leaves - merged where they are contiguous, whatever the leaf
+ *  boundaries inside - are staged with coalesced loads, culled per candidate against the same bounding box and tested
+ *  by all lanes.  Ranges come in SFC order, so every lane appends in ascending particle index like the CPU walk.
+ *
+ *  What the reference computes for target i is { j : the walk of i reaches the leaf of j, and d2(i,j) < r2 } with its
+ *  own rounded expressions for both conditions.  Each staged pair gets one single-precision sum of squares s:
+ *    s > thrHi        certainly d2 >= r2 in the reference's arithmetic                          -> rejected
+ *    s < thrLo        certainly d2 < (1 - mu) r2, which implies BOTH conditions: the particle lies inside the box of its
+ *                     leaf and of every ancestor up to the tolerance the preparation kernel has checked, so each of
+ *                     those boxes is closer to the target than sqrt(1-mu) r + tau0 < r by more than the rounding of the
+ *                     reference's box test                                                         -> accepted
+ *    in between       (a shell of relative width ~1e-3 below the radius, < 0.5 % of the neighbours) the reference's
+ *                     distance expression and the reference's box tests along the root-to-leaf path of j decide.
+ *  mu = 4 tau0 / r + 2^-18 with tau0 = 64 ulp(largest coordinate of the box) covers the containment tolerance
+ *  (16 ulp), the nesting of the rounded ancestor boxes and the rounding of the box test; lanes whose radius is not
+ *  large against tau0 (or not a normal number) take the exact route for every candidate inside the radius.  Leaves
+ *  with a stray particle (NB_BAD_LEAF) are never merged or staged: the lanes evaluate the reference expressions on
+ *  them directly, and subtrees are not taken whole while such leaves exist.
+ *
+ *  PBC = false: the box has no periodic dimension, the fold code is not even compiled in.  PBC = true: if the group
+ *  and its search spheres are small against the box, every lane sees the same periodic image of a nearby particle or
+ *  node, the fold is applied ONCE while staging (to the coordinates relative to the group origin) and everything above
+ *  runs unchanged (the exact route uses the reference's folded expressions); otherwise, and for float searches (whose
+ *  staged operands must be the reference's), the warp runs warpSearchDirect. */
+template<class T, bool PBC, bool FOLD, class Th>
+__device__ __forceinline__ void warpSearchGroup(GroupWalkShared& sh, const uint2 grp, const T* __restrict__ x, const T* __restrict__ y,
+                           const T* __restrict__ z, const Th* __restrict__ h, uint32_t first, const Box<T>& box,
+                           const int* __restrict__ childOffsets, const int* __restrict__ parents,
+                           const uint2* __restrict__ nodeRange, float tau0, uint32_t coarse,
+                           const T* __restrict__ centers, const T* __restrict__ sizes, uint32_t ngmax,
+                           uint32_t* __restrict__ neighbors, uint32_t* __restrict__ neighborsCount)
+{
+    constexpr bool Filt   = sizeof(T) == 8;
+    const unsigned lane   = threadIdx.x & 31;
+    const unsigned ltMask = (1u << lane) - 1u;
+    const bool valid      = grp.x + lane < grp.y;
+    const uint32_t i = valid ? grp.x + lane : grp.y - 1;
+
+    Target<T> t;
+    t.x        = x[i];
+    t.y        = y[i];
+    t.z        = z[i];
+    // Th may be float with double coordinates: the radius is formed in Th and promoted (findneighbors.hpp:89-99)
+    const Th hi = h[i];
+    t.radiusSq  = T(Th(4.0) * hi * hi);
+    {
+        bool anyPbc = box.pbc(0) || box.pbc(1) || box.pbc(2);
+        T s         = T(2) * T(hi);
+        bool inside = (t.x - s >= box.lim[0]) && (t.y - s >= box.lim[2]) && (t.z - s >= box.lim[4]) &&
+                      (t.x + s <= box.lim[1]) && (t.y + s <= box.lim[3]) && (t.z + s <= box.lim[5]);
+        t.usePbc    = PBC && anyPbc && !inside;
+    }
+    const bool warpPbc = PBC && __any_sync(0xffffffffu, t.usePbc);
+
+    // single-precision frame: relative to the first target of the group for double searches, absolute for float
+    const T ox = Filt ? __shfl_sync(0xffffffffu, t.x, 0) : T(0);
+    const T oy = Filt ? __shfl_sync(0xffffffffu, t.y, 0) : T(0);
+    const T oz = Filt ? __shfl_sync(0xffffffffu, t.z, 0) : T(0);
+    const float txf = float(t.x - ox);
+    const float tyf = float(t.y - oy);
+    const float tzf = float(t.z - oz);
+    const float r2f = float(t.radiusSq);
+
+    // bounding box of the targets, largest radius, and the magnitude bounds of the error terms (group constants)
+    const float lox = warpMinF(txf), hix = warpMaxF(txf);
+    const float loy = warpMinF(tyf), hiy = warpMaxF(tyf);
+    const float loz = warpMinF(tzf), hiz = warpMaxF(tzf);
+    const float DwT = fmaxf(fmaxf(fmaxf(fabsf(lox), fabsf(hix)), fmaxf(fabsf(loy), fabsf(hiy))),
+                            fmaxf(fabsf(loz), fabsf(hiz)));
+    const float r2max = warpMaxF(r2f);
+    const float r2bMax = (r2max > 1e-30f) ? r2max * BAND_KB : __int_as_float(0x7f800000);
+
+    bool foldOk = Filt && FOLD;
+    if (PBC && Filt && FOLD)
+    {
+        const float reach = 1.01f * sqrtf(r2max);
+        const float ext[3] = {hix - lox, hiy - loy, hiz - loz};
+#pragma unroll
+        for (int d = 0; d < 3; ++d)
+            if (box.pbc(d) && !(ext[d] + reach < 0.124f * float(box.len[d]))) { foldOk = false; }
+    }
+    if (PBC && warpPbc && !foldOk)
+    {
+        warpSearchDirect<T, Th>(reinterpret_cast<uint8_t(*)[32]>(&sh), grp, x, y, z, h, first, box, childOffsets,
+                                parents, nodeRange, centers, sizes, ngmax, neighbors, neighborsCount);
+        return;
+    }
+    const bool foldPbc = warpPbc;
+
+    // every staged (un-culled) candidate has |coordinate| <= 1.01 (DwT + sqrt(r2max)), see the cull test
+    const float Dpair = 1.01f * (DwT + sqrtf(r2max));
+    const float Epair = Dpair * Dpair * 0x1p-29f;
+
+    /* per-lane thresholds on the single-precision sum (see above).  A lane whose own walk does not even enter the root
+     * (or that holds no target) accepts nothing. */
+    const bool active = valid && cellOverlap<PBC>(t, centers, sizes, 0, box);
+    float thrLo = -1.0f, thrHi = -1.0f;
+    T sureT     = T(0); // exact route, T = double: d2 < sureT * r2 implies that the walk reaches the leaf
+    if (active)
+    {
+        const float mu    = fmaf(4.0f * tau0, rsqrtf(r2f), 0x1p-18f);
+        const bool normal = r2f > 1e-30f && mu < 0x1p-6f; // false for NaN
+        if (normal) { sureT = T(1.0f - 2.0f * mu); }
+        if (Filt)
+        {
+            thrHi = r2f > 1e-30f ? fmaf(Epair, BAND_SB, r2f * BAND_KB) : __int_as_float(0x7f800000);
+            if (normal) { thrLo = fmaf(-Epair, BAND_SA, (r2f * (1.0f - mu)) * BAND_KA); }
+        }
+        else
+        {
+            // the staged values are the reference's operands and s is the reference's expression: s < r2f decides the
+            // distance, the largest float below r2f is the upper end of the shell
+            if (r2f > 0.0f) { thrHi = __uint_as_float(__float_as_uint(r2f) - 1u); } // +inf -> FLT_MAX; NaN -> stays -1
+            if (normal) { thrLo = (r2f * (1.0f - mu)) * (1.0f - 0x1p-22f); }
+        }
+        if (!(thrHi >= 0.0f)) { thrHi = -1.0f; }
+    }
+    // bit patterns of the shell [thrLo, thrHi] among the non-negative floats (they order like their patterns; NaN sums
+    // lie above +inf and never match: NaN < r2 is false for the reference as well)
+    uint32_t bandLo = 0xffffffffu, bandSpan = 0;
+    if (thrHi >= 0.0f)
+    {
+        const uint32_t lo = __float_as_uint(fmaxf(thrLo, 0.0f)), hi2 = __float_as_uint(thrHi);
+        if (hi2 >= lo)
+        {
+            bandLo   = lo;
+            bandSpan = hi2 - lo;
+        }
+    }
+
+    // out = address of the next list entry; entries at and beyond rowEnd are counted but not stored
+    // (findneighbors.hpp:139-146).  Global-space byte addresses: the stores of the staged path are inline PTX.
+    unsigned long long out          = __cvta_generic_to_global(neighbors + size_t(i - first) * size_t(ngmax));
+    const unsigned long long rowEnd = out + 4ull * ngmax;
+
+    auto append = [&](uint32_t j)
+    {
+        if (out < rowEnd) { asm volatile("st.global.u32 [%0], %1;" ::"l"(out), "r"(j) : "memory"); }
+        out += 4;
+    };
+
+    const uint64_t ntx2 = pack2(-txf, -txf), nty2 = pack2(-tyf, -tyf), ntz2 = pack2(-tzf, -tzf);
+    const uint64_t zero2 = pack2(0.0f, 0.0f);
+
+    /*! tests the `cnt` staged candidates four at a time (cnt is padded to a multiple of four with candidates at
+     *  infinity).  SELF: the batch holds targets of this group, so a candidate can be the target itself (excluded by
+     *  index, findneighbors.hpp:131).  GUARD: a list may reach ngmax during this call. */
+    auto testStaged = [&](uint32_t cnt, auto selfTag, auto guardTag)
+    {
+        constexpr bool SELF  = decltype(selfTag)::value;
+        constexpr bool GUARD = decltype(guardTag)::value;
+        for (uint32_t k = 0; k < cnt; k += 4)
+        {
+            const float4 X = *reinterpret_cast<const float4*>(&sh.cx[k]);
+            const float4 Y = *reinterpret_cast<const float4*>(&sh.cy[k]);
+            const float4 Z = *reinterpret_cast<const float4*>(&sh.cz[k]);
+            const uint4 J  = *reinterpret_cast<const uint4*>(&sh.cj[k]);
+            float s[4];
+#pragma unroll
+            for (int half = 0; half < 2; ++half)
+            {
+                const uint64_t x2 = half ? pack2(X.z, X.w) : pack2(X.x, X.y);
+                const uint64_t y2 = half ? pack2(Y.z, Y.w) : pack2(Y.x, Y.y);
+                const uint64_t z2 = half ? pack2(Z.z, Z.w) : pack2(Z.x, Z.y);
+                const uint64_t dx = add2(x2, ntx2), dy = add2(y2, nty2), dz = add2(z2, ntz2);
+                uint64_t s2;
+                if (Filt) { s2 = fma2(dx, dx, fma2(dy, dy, mul2(dz, dz))); }
+                else
+                {
+                    // the reference's float expression (dx*dx + dy*dy) + dz*dz (findneighbors.hpp:33-60), bit for bit:
+                    // the packed operations round per component like the scalar ones.  The products are formed as
+                    // fma(d, d, +0) = RN(d*d): separate mul.rn / add.rn.f32x2 get contracted to FFMA2 by ptxas even
+                    // under --fmad=false
+                    s2 = add2(add2(fma2(dx, dx, zero2), fma2(dy, dy, zero2)), fma2(dz, dz, zero2));
+                }
+                unpack2(s2, s[2 * half], s[2 * half + 1]);
+            }
+            // a sum in the shell: the reference's own expressions decide.  The branch is warp-uniform.
+            const bool amb = __float_as_uint(s[0]) - bandLo <= bandSpan || __float_as_uint(s[1]) - bandLo <= bandSpan ||
+                             __float_as_uint(s[2]) - bandLo <= bandSpan || __float_as_uint(s[3]) - bandLo <= bandSpan;
+            if (__any_sync(0xffffffffu, amb))
+            {
+                const uint32_t jj[4] = {J.x, J.y, J.z, J.w};
+#pragma unroll
+                for (int c = 0; c < 4; ++c)
+                {
+                    bool in = s[c] < thrLo;
+                    if (!in && s[c] <= thrHi && k + c < cnt)
+                    {
+                        bool sure = false; // inside by more than the margin the walk needs
+                        if (Filt)
+                        {
+                            const T d2 = (PBC && foldPbc)
+                                             ? exactDistSqPbc(x, y, z, jj[c], t.x, t.y, t.z, t.usePbc, box)
+                                             : exactDistSq(x, y, z, jj[c], t.x, t.y, t.z);
+                            in   = d2 < t.radiusSq;
+                            sure = d2 < t.radiusSq * sureT;
+                        }
+                        else { in = true; }
+                        if (in && !sure)
+                        {
+                            in = walkReachesLeafOf<PBC>(jj[c], t, childOffsets, nodeRange, centers, sizes, box);
+                        }
+                    }
+                    if (in && jj[c] != i) { append(jj[c]); }
+                }
+                continue;
+            }
+            uint32_t outLo = uint32_t(out), outHi = uint32_t(out >> 32);
+            appendIf<SELF, GUARD>(outLo, outHi, rowEnd, J.x, s[0], thrLo, i);
+            appendIf<SELF, GUARD>(outLo, outHi, rowEnd, J.y, s[1], thrLo, i);
+            appendIf<SELF, GUARD>(outLo, outHi, rowEnd, J.z, s[2], thrLo, i);
+            appendIf<SELF, GUARD>(outLo, outHi, rowEnd, J.w, s[3], thrLo, i);
+            out = (unsigned long long)(outHi) << 32 | outLo;
+        }
+    };
+
+    uint32_t bcnt = 0;     // candidates staged
+    bool bself    = false; // the staged ranges hold targets of this group
+
+    auto flush = [&]()
+    {
+        // pad to a multiple of four with candidates at infinity: s = +inf is never below thrLo, and on the exact
+        // route the entry index is checked
+        if (lane < 4)
+        {
+            const float inf    = __int_as_float(0x7f800000);
+            sh.cx[bcnt + lane] = inf;
+            sh.cy[bcnt + lane] = inf;
+            sh.cz[bcnt + lane] = inf;
+            sh.cj[bcnt + lane] = i;
+        }
+        __syncwarp();
+        const bool guard = __any_sync(0xffffffffu, out + 4ull * bcnt > rowEnd);
+        if (guard) { testStaged(bcnt, std::true_type{}, std::true_type{}); }
+        else if (bself) { testStaged(bcnt, std::true_type{}, std::false_type{}); }
+        else { testStaged(bcnt, std::false_type{}, std::false_type{}); }
+        __syncwarp();
+        bcnt  = 0;
+        bself = false;
+    };
+
+    //! stage the particles [pb, pe) in rounds of 32 coalesced loads, dropping those no lane can reach; the staged
+    //! candidates are tested whenever another round might not fit and, if `drain`, at the end
+    auto stageRange = [&](uint32_t pb, uint32_t pe, bool drain)
+    {
+        for (uint32_t base = pb;; base += 32)
+        {
+            const bool more = base < pe;
+            if (bcnt && (more ? bcnt + 32 > NB_CAP : drain)) { flush(); }
+            if (!more) { break; }
+            const uint32_t j = base + lane;
+            bool keep        = false;
+            float c0 = 0, c1 = 0, c2 = 0;
+            if (j < pe)
+            {
+                T qx = x[j] - ox, qy = y[j] - oy, qz = z[j] - oz;
+                if (PBC && foldPbc)
+                {
+                    qx = pbcFold(qx, 0, box);
+                    qy = pbcFold(qy, 1, box);
+                    qz = pbcFold(qz, 2, box);
+                }
+                c0 = float(qx);
+                c1 = float(qy);
+                c2 = float(qz);
+                float D  = fmaxf(fmaxf(fabsf(c0), fabsf(c1)), fmaxf(fabsf(c2), DwT));
+                float bc = fmaf(D * D * 0x1p-27f, BAND_SB, r2bMax);
+                float ex = fmaxf(fmaxf(lox - c0, c0 - hix), 0.0f);
+                float ey = fmaxf(fmaxf(loy - c1, c1 - hiy), 0.0f);
+                float ez = fmaxf(fmaxf(loz - c2, c2 - hiz), 0.0f);
+                keep     = !(fmaf(ex, ex, fmaf(ey, ey, ez * ez)) > bc);
+            }
+            const unsigned km = __ballot_sync(0xffffffffu, keep);
+            if (keep)
+            {
+                const uint32_t pos = bcnt + __popc(km & ltMask);
+                sh.cx[pos]         = c0;
+                sh.cy[pos]         = c1;
+                sh.cz[pos]         = c2;
+                sh.cj[pos]         = j;
+            }
+            bcnt += __popc(km);
+            bself |= base < grp.y && base + 32 > grp.x;
+        }
+    };
+
+    //! a leaf with stray particles: the reference expressions on broadcast loads for the lanes whose walk reaches it
+    auto scanLeafDirect = [&](uint32_t pb, uint32_t pe, bool mine)
+    {
+        for (uint32_t j = pb; j < pe; ++j)
+        {
+            T dx = x[j] - t.x;
+            T dy = y[j] - t.y;
+            T dz = z[j] - t.z;
+            if (PBC)
+            {
+                T fx = pbcFold(dx, 0, box);
+                T fy = pbcFold(dy, 1, box);
+                T fz = pbcFold(dz, 2, box);
+                dx   = t.usePbc ? fx : dx;
+                dy   = t.usePbc ? fy : dy;
+                dz   = t.usePbc ? fz : dz;
+            }
+            T d2 = dx * dx + dy * dy + dz * dz;
+            if (mine && j != i && d2 < t.radiusSq) { append(j); }
+        }
+    };
+
+    //! which of the 8 children of a node can hold a neighbour of any target of the warp (lanes 0-7 test one each)
+    auto reachableChildren = [&](int child0) -> uint32_t
+    {
+        bool reach = false;
+        if (lane < 8)
+        {
+            const int node = child0 + int(lane);
+            T rx = centers[3 * node] - ox, ry = centers[3 * node + 1] - oy, rz = centers[3 * node + 2] - oz;
+            const float gx = float(sizes[3 * node]), gy = float(sizes[3 * node + 1]), gz = float(sizes[3 * node + 2]);
+            bool large = false; // a node that is large against the periodic box: the lanes may see different images
+            if (PBC && foldPbc)
+            {
+                rx    = pbcFold(rx, 0, box);
+                ry    = pbcFold(ry, 1, box);
+                rz    = pbcFold(rz, 2, box);
+                large = (box.pbc(0) && !(gx < 0.124f * float(box.len[0]))) ||
+                        (box.pbc(1) && !(gy < 0.124f * float(box.len[1]))) ||
+                        (box.pbc(2) && !(gz < 0.124f * float(box.len[2])));
+            }
+            const float cx = float(rx), cy = float(ry), cz = float(rz);
+            const float D  = fmaxf(fmaxf(fmaxf(fabsf(cx), fabsf(cy)), fmaxf(fabsf(cz), DwT)), fmaxf(gx, fmaxf(gy, gz)));
+            const float E  = D * D * 0x1p-27f;
+            // a child whose box is certainly farther from the targets' bounding box than the largest radius fails the
+            // continuation test of every lane
+            float ex = fmaxf(fmaxf(lox - (cx + gx), (cx - gx) - hix), 0.0f);
+            float ey = fmaxf(fmaxf(loy - (cy + gy), (cy - gy) - hiy), 0.0f);
+            float ez = fmaxf(fmaxf(loz - (cz + gz), (cz - gz) - hiz), 0.0f);
+            reach    = large || !(fmaf(ex, ex, fmaf(ey, ey, ez * ez)) > fmaf(E, BAND_SB, r2bMax));
+        }
+        return __ballot_sync(0xffffffffu, reach) & 0xffu;
+    };
+
+    if (__any_sync(0xffffffffu, active))
+    {
+        const int rootChild = childOffsets[0];
+        if (rootChild == 0)
+        {
+            const uint2 r = nodeRange[0];
+            scanLeafDirect(r.x, r.y & ~NB_BAD_LEAF, active);
+        }
+        else
+        {
+            // depth-first walk in SFC order over the children the warp enters; `wm` = siblings still to visit at the
+            // current depth (the full set is kept per depth in shared memory for the way back up); [pb, pe) = the
+            // contiguous particle range collected from the last leaves, not staged yet
+            uint32_t pb = 0, pe = 0;
+            int depth   = 1;
+            int base    = rootChild;
+            uint32_t wm = reachableChildren(rootChild);
+            if (lane == 0) { sh.wm[1] = uint8_t(wm); }
+            while (true)
+            {
+                uint32_t nb = 0, ne = 0; // the next range, if this step finds one that does not extend [pb, pe)
+                bool done = false, bad = false;
+                if (wm == 0)
+                {
+                    if (depth == 1) { done = true; }
+                    else
+                    {
+                        const int up = parents[(base - 1) >> 3];
+                        --depth;
+                        base = ((up - 1) & ~7) + 1;
+                        __syncwarp();
+                        wm = uint32_t(sh.wm[depth]) & ~((2u << ((up - 1) & 7)) - 1u);
+                        continue;
+                    }
+                }
+                else
+                {
+                    const int c = __ffs(int(wm)) - 1;
+                    wm &= wm - 1;
+                    const int node  = base + c;
+                    const int child = childOffsets[node];
+                    const uint2 r   = nodeRange[node];
+                    ne              = r.y & ~NB_BAD_LEAF;
+                    nb              = r.x;
+                    if (child != 0 && ((r.y & NB_BAD_LEAF) || ne - nb > coarse))
+                    {
+                        ++depth;
+                        wm = reachableChildren(child);
+                        if (lane == 0) { sh.wm[depth] = uint8_t(wm); }
+                        base = child;
+                        continue;
+                    }
+                    if (ne == nb) { continue; }
+                    bad = (r.y & NB_BAD_LEAF) != 0;
+                    if (!bad && pe == nb)
+                    {
+                        pe = ne;
+                        continue;
+                    }
+                }
+                // the collected range ends here: a range that is not contiguous with it, a leaf with stray particles,
+                // or the end of the walk
+                stageRange(pb, pe, done || bad);
+                if (done) { break; }
+                if (bad)
+                {
+                    const bool mine = active && walkReachesLeafOf<PBC>(nb, t, childOffsets, nodeRange, centers, sizes, box);
+                    scanLeafDirect(nb, ne, mine);
+                    pb = pe = 0;
+                }
+                else
+                {
+                    pb = nb;
+                    pe = ne;
+                }
+            }
+        }
+    }
+
+    if (valid) { neighborsCount[i - first] = ngmax - uint32_t((long long)(rowEnd - out) >> 2); }
+}
+
+//! the kernel of the group-steered search; DEFER as in findNeighborsKernel.  Does nothing if too many leaves hold stray
+//! particles (trees over 32-bit keys: the key grid is coarse against the search radius), findNeighborsKernel runs then
+template<class T, bool PBC, bool FOLD, bool DEFER, class Th>
+__global__ void __launch_bounds__(NB_THREADS) findNeighborsGroupKernel(const T* __restrict__ x,
+                                                                  const T* __restrict__ y,
+                                                                  const T* __restrict__ z,
+                                                                  const Th* __restrict__ h,
+                                                                  uint32_t first,
+                                                                  const uint2* __restrict__ groups,
+                                                                  const uint32_t* __restrict__ numGroupsPtr,
+                                                                  const uint32_t* __restrict__ groupList,
+                                                                  uint32_t* __restrict__ deferred,
+                                                                  Box<T> box,
+                                                                  const int* __restrict__ childOffsets,
+                                                                  const int* __restrict__ parents,
+                                                                  const uint2* __restrict__ nodeRange,
+                                                                  float tau0,
+                                                                  uint32_t coarse,
+                                                                  const T* __restrict__ centers,
+                                                                  const T* __restrict__ sizes,
+                                                                  uint32_t ngmax,
+                                                                  uint32_t* __restrict__ neighbors,
+                                                                  uint32_t* __restrict__ neighborsCount,
+                                                                  const uint32_t* __restrict__ numBad,
+                                                                  uint32_t badLimit)
+{
+    if (*numBad > badLimit) { return; }
+    __shared__ GroupWalkShared shAll[NB_THREADS / 32];
+    size_t warpId = (size_t(blockIdx.x) * NB_THREADS + threadIdx.x) >> 5;
+    if (groupList)
+    {
+        if (warpId >= size_t(groupList[0])) { return; }
+        warpId = groupList[1 + warpId];
+    }
+    else if (warpId >= size_t(*numGroupsPtr)) { return; }
+    const uint2 grp = groups[warpId];
+    if (DEFER)
+    {
+        const unsigned lane = threadIdx.x & 31;
+        const uint32_t i    = min(grp.x + lane, grp.y - 1);
+        const T tx = x[i], ty = y[i], tz = z[i], s = T(2) * T(h[i]);
+        // insideBox of findneighbors.hpp:104-106
+        const bool inside = (tx - s >= box.lim[0]) && (ty - s >= box.lim[2]) && (tz - s >= box.lim[4]) &&
+                            (tx + s <= box.lim[1]) && (ty + s <= box.lim[3]) && (tz + s <= box.lim[5]);
+        if (__any_sync(0xffffffffu, !inside))
+        {
+            if (lane == 0) { deferred[1 + atomicAdd(&deferred[0], 1u)] = uint32_t(warpId); }
+            return;
+        }
+    }
+    warpSearchGroup<T, PBC, FOLD, Th>(shAll[threadIdx.x >> 5], grp, x, y, z, h, first, box, childOffsets, parents, nodeRange,
+                                 tau0, coarse, centers, sizes, ngmax, neighbors, neighborsCount);
 }
 
 } // namespace
@@ -834,24 +1552,78 @@ int findNeighbors(const T* x, const T* y, const T* z, const Th* h, uint32_t firs
     CSB_LAUNCH_CHECK();
 
     unsigned grid = iceil(maxGroups * 32, NB_THREADS);
+
+    /* Trees with few particles per leaf (T = double): the group-steered search, preceded by its preparation - the
+     * particle range below every node and the leaves with stray particles (the tolerances scale with the rounding unit
+     * of the largest coordinate of the box, see warpSearchGroup).  It only runs if at most one leaf in 32 holds stray
+     * particles, otherwise the per-lane search below does; both decide from the same device counter, no host
+     * synchronisation.  TUNE_NB_SEARCH: 0 = by leaf occupancy, 1 = per-lane walks always, 2 = group-steered always. */
+    const int searchKnob   = tuning(TUNE_NB_SEARCH);
+    const bool groupSearch = sizeof(T) == 8 && searchKnob != 1 &&
+                             (searchKnob == 2 || double(last - first) < NB_SMALL_LEAVES * double(numLeaves));
+    const uint32_t* numBadGate = nullptr;
+    const uint32_t badLimit    = uint32_t(numLeaves) / 32;
+    if constexpr (sizeof(T) == 8)
+    {
+        if (groupSearch)
+        {
+            double cabs = 0;
+            for (int d = 0; d < 6; ++d)
+                cabs = std::max(cabs, std::fabs(lim[d]));
+            const double eps = 0x1p-52;
+            const T tolNest  = T(4 * eps * cabs);
+            const float tau0 = float(12 * eps * cabs) * (1.0f + 0x1p-20f);
+            CSB_SCRATCH(prep, char*, s, SCRATCH_D, 16 + size_t(numNodes) * sizeof(uint2));
+            uint32_t* numBad = reinterpret_cast<uint32_t*>(prep);
+            uint2* nodeRange = reinterpret_cast<uint2*>(prep + 16);
+            CSB_CHECK(cudaMemsetAsync(numBad, 0, sizeof(uint32_t), s));
+            nodeRangeKernel<<<iceil(numNodes, 256), 256, 0, s>>>(childOffsets, internalToLeaf, layout, numNodes,
+                                                                 nodeRange);
+            CSB_LAUNCH_CHECK();
+            leafContainmentKernel<T><<<iceil(size_t(numNodes) * 8, 256), 256, 0, s>>>(
+                x, y, z, childOffsets, nodeRange, centers, sizes, numNodes, tolNest, parents, numBad);
+            CSB_LAUNCH_CHECK();
+            numBadGate = numBad;
+            if (!pbc)
+            {
+                findNeighborsGroupKernel<T, false, false, false, Th><<<grid, NB_THREADS, 0, s>>>(
+                    x, y, z, h, first, groups, groupOffsets + numLeaves, nullptr, nullptr, box, childOffsets, parents,
+                    nodeRange, tau0, NB_COARSE, centers, sizes, ngmax, neighbors, neighborsCount, numBad, badLimit);
+            }
+            else
+            {
+                CSB_SCRATCH(deferred, uint32_t*, s, SCRATCH_E, (maxGroups + 1) * sizeof(uint32_t));
+                CSB_CHECK(cudaMemsetAsync(deferred, 0, sizeof(uint32_t), s));
+                findNeighborsGroupKernel<T, false, false, true, Th><<<grid, NB_THREADS, 0, s>>>(
+                    x, y, z, h, first, groups, groupOffsets + numLeaves, nullptr, deferred, box, childOffsets, parents,
+                    nodeRange, tau0, NB_COARSE, centers, sizes, ngmax, neighbors, neighborsCount, numBad, badLimit);
+                CSB_LAUNCH_CHECK();
+                findNeighborsGroupKernel<T, true, true, false, Th><<<grid, NB_THREADS, 0, s>>>(
+                    x, y, z, h, first, groups, groupOffsets + numLeaves, deferred, nullptr, box, childOffsets, parents,
+                    nodeRange, tau0, NB_COARSE, centers, sizes, ngmax, neighbors, neighborsCount, numBad, badLimit);
+            }
+            CSB_LAUNCH_CHECK();
+        }
+    }
+
     if (!pbc)
     {
         findNeighborsKernel<T, false, false, false, Th><<<grid, NB_THREADS, 0, s>>>(
             x, y, z, h, first, groups, groupOffsets + numLeaves, nullptr, nullptr, box, childOffsets, parents,
-            internalToLeaf, layout, centers, sizes, ngmax, neighbors, neighborsCount);
+            internalToLeaf, layout, centers, sizes, ngmax, neighbors, neighborsCount, numBadGate, badLimit);
     }
     else
     {
         // interior groups with the open-box code, then the groups at the periodic boundaries
         CSB_SCRATCH(deferred, uint32_t*, s, SCRATCH_E, (maxGroups + 1) * sizeof(uint32_t));
-        CSB_CHECK(cudaMemsetAsync(deferred, 0, sizeof(uint32_t), s));
+        if (!numBadGate) { CSB_CHECK(cudaMemsetAsync(deferred, 0, sizeof(uint32_t), s)); }
         findNeighborsKernel<T, false, false, true, Th><<<grid, NB_THREADS, 0, s>>>(
             x, y, z, h, first, groups, groupOffsets + numLeaves, nullptr, deferred, box, childOffsets, parents,
-            internalToLeaf, layout, centers, sizes, ngmax, neighbors, neighborsCount);
+            internalToLeaf, layout, centers, sizes, ngmax, neighbors, neighborsCount, numBadGate, badLimit);
         CSB_LAUNCH_CHECK();
         findNeighborsKernel<T, true, true, false, Th><<<grid, NB_THREADS, 0, s>>>(
             x, y, z, h, first, groups, groupOffsets + numLeaves, deferred, nullptr, box, childOffsets, parents,
-            internalToLeaf, layout, centers, sizes, ngmax, neighbors, neighborsCount);
+            internalToLeaf, layout, centers, sizes, ngmax, neighbors, neighborsCount, numBadGate, badLimit);
     }
     CSB_LAUNCH_CHECK();
     return 0;

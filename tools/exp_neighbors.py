@@ -22,6 +22,7 @@ ap.add_argument("--only", default="")
 ap.add_argument("--reps", type=int, default=3)
 ap.add_argument("--pbc", type=int, default=0)
 ap.add_argument("--knob3", default="0")
+ap.add_argument("--bucket", type=int, default=0, help="focus bucket size (default: the bench's); 32 / 16 with 64 Mi uniform particles reproduce the leaf occupancy of the 2- / 4-rank bench trees")
 args = ap.parse_args()
 
 dev = torch.device("cuda:0")
@@ -36,7 +37,8 @@ else:
     x, y, z = (torch.rand(n, dtype=torch.float32, device=dev, generator=g).clamp_(max=0.99999994) for _ in range(3))
     h = torch.full((n,), bench.h_for(n, 300), dtype=torch.float32, device=dev)
     ngmax, key, real = 384, "u32", "f"
-dom = capi.Domain(0, 1, bench.BUCKET, bench.BUCKET, 0.5, (0, 1, 0, 1, 0, 1), (args.pbc,) * 3, key=key, real=real,
+bucket = args.bucket or bench.BUCKET
+dom = capi.Domain(0, 1, bucket, bucket, 0.5, (0, 1, 0, 1, 0, 1), (args.pbc,) * 3, key=key, real=real,
                   device="cuda:0")
 dom.sync(x, y, z, h)
 del x, y, z, h
@@ -57,7 +59,8 @@ for kern, grp in [(k3, g) for k3 in [int(v) for v in args.knob3.split(',')] for 
         torch.cuda.synchronize()
         ms.append(e0.elapsed_time(e1))
     out = {"kernel": kern, "groups": grp, "n": n, "config": args.config, "ms": [round(m, 3) for m in ms],
-           "mean_nc": round(float(nc.to(torch.float64).mean()), 3)}
+           "mean_nc": round(float(nc.to(torch.float64).mean()), 3), "bucket": bucket,
+           "leaves": dom.num_focus_leaves}
     if ref_nb is None and len(combos) > 1:
         ref_nb, ref_nc = nb.clone(), nc.clone()
     elif ref_nb is not None:
