@@ -908,7 +908,7 @@ __global__ void leafContainmentKernel(const T* __restrict__ x, const T* __restri
  *  traversal (findneighbors.hpp:108-112 at every node of the path) reaches the leaf that holds j.  The root has been
  *  tested by the caller.  Rare: only for candidates in the thin shell below the search radius. */
 template<bool PBC, class T>
-__device__ __noinline__ bool walkReachesLeafOf(uint32_t j, const Target<T>& t, const int* __restrict__ childOffsets,
+__device__ __forceinline__ bool walkReachesLeafOf(uint32_t j, const Target<T>& t, const int* __restrict__ childOffsets,
                                                const uint2* __restrict__ nodeRange, const T* __restrict__ centers,
                                                const T* __restrict__ sizes, const Box<T>& box)
 {
@@ -1222,29 +1222,38 @@ __device__ __forceinline__ void warpSearchGroup(GroupWalkShared& sh, const uint2
                              __float_as_uint(s[2]) - bandLo <= bandSpan || __float_as_uint(s[3]) - bandLo <= bandSpan;
             if (__any_sync(0xffffffffu, amb))
             {
-                const uint32_t jj[4] = {J.x, J.y, J.z, J.w};
-#pragma unroll
+#pragma unroll 1
                 for (int c = 0; c < 4; ++c)
                 {
-                    bool in = s[c] < thrLo;
-                    if (!in && s[c] <= thrHi && k + c < cnt)
+                    // (selects instead of indexed arrays: the loop is kept rolled, the rare route stays small)
+                    const uint32_t jc = c == 0 ? J.x : c == 1 ? J.y : c == 2 ? J.z : J.w;
+                    const float sc    = c == 0 ? s[0] : c == 1 ? s[1] : c == 2 ? s[2] : s[3];
+                    bool in           = sc < thrLo;
+                    if (!in && sc <= thrHi && k + c < cnt)
                     {
                         bool sure = false; // inside by more than the margin the walk needs
                         if (Filt)
                         {
-                            const T d2 = (PBC && foldPbc)
-                                             ? exactDistSqPbc(x, y, z, jj[c], t.x, t.y, t.z, t.usePbc, box)
-                                             : exactDistSq(x, y, z, jj[c], t.x, t.y, t.z);
+                            // the reference's expression (findneighbors.hpp:33-60,134), folded if the target's
+                            // search sphere leaves the box (:104-106)
+                            T ex = x[jc] - t.x, ey = y[jc] - t.y, ez = z[jc] - t.z;
+                            if (PBC && foldPbc && t.usePbc)
+                            {
+                                ex = pbcFold(ex, 0, box);
+                                ey = pbcFold(ey, 1, box);
+                                ez = pbcFold(ez, 2, box);
+                            }
+                            const T d2 = ex * ex + ey * ey + ez * ez;
                             in   = d2 < t.radiusSq;
                             sure = d2 < t.radiusSq * sureT;
                         }
                         else { in = true; }
                         if (in && !sure)
                         {
-                            in = walkReachesLeafOf<PBC>(jj[c], t, childOffsets, nodeRange, centers, sizes, box);
+                            in = walkReachesLeafOf<PBC>(jc, t, childOffsets, nodeRange, centers, sizes, box);
                         }
                     }
-                    if (in && jj[c] != i) { append(jj[c]); }
+                    if (in && jc != i) { append(jc); }
                 }
                 continue;
             }

@@ -122,3 +122,44 @@ def test_digests_detect_a_single_changed_entry():
     k2 = keys.clone().view(torch.int64)
     k2[77] ^= 1
     assert bench.wsum(keys) != bench.wsum(k2.view(torch.uint64))
+
+
+@pytest.mark.parametrize("bucket_focus,pbc,force_group", [(8, 0, False), (16, 1, False), (64, 0, True)])
+def test_group_steered_search_2mi_bit_identical_vs_reference(bucket_focus, pbc, force_group):
+    """findNeighbors on trees with small leaves takes the group-steered search (csrc/neighbors.cu: no per-lane walk
+    state, contiguous particle ranges staged across leaf boundaries, subtrees taken whole).  Its lists must still be
+    the reference's bit for bit, including the particles that lie up to one cell of the key grid outside the box of
+    their leaf (about 250 of 4 Mi with 64-bit keys; the reference only finds those from targets whose own walk enters
+    the leaf): compared with the unmodified reference through the list digests on 2 Mi uniform particles."""
+    import numpy as np
+    import torch
+
+    import bench
+    from cstone_b200 import capi
+
+    _libs = _ref_or_skip()
+    n, ngmax = 2 * 1024 * 1024, 150
+    x, y, z, h = bench.make_particles("uniform", n, 5)
+    lim, bnd = (0, 1, 0, 1, 0, 1), (pbc, pbc, pbc)
+    want = _libs.ref_bench_run("u64d", 1, 64, bucket_focus, 0.5, lim, bnd, x, y, z, h, [0, n], ngmax=ngmax)[0]["digest"]
+    dev = torch.device("cuda:0")
+    dom = capi.Domain(0, 1, 64, bucket_focus, 0.5, lim, bnd, key="u64", real="d", device="cuda:0")
+    dom.sync(*(torch.from_numpy(a).to(dev) for a in (x, y, z, h)))
+    got = bench.domain_digest(dom)
+    capi.tuning_set(2, 2 if force_group else 0)
+    try:
+        nb, nc = dom.find_neighbors(ngmax)
+        got["nc_sum"], got["lists"] = bench.list_digest(nb.reshape(-1), nc, ngmax)
+        # the per-lane search returns the same lists
+        capi.tuning_set(2, 1)
+        nb2, nc2 = dom.find_neighbors(ngmax)
+        assert torch.equal(nc, nc2) and torch.equal(nb, nb2)
+    finally:
+        capi.tuning_set(2, 0)
+    cmp_ = bench.compare_digests(got, want)
+    assert cmp_["identical"], cmp_
+    assert {"lists", "nc_sum", "layout", "centers"} <= set(cmp_["arrays_compared"])
+    assert 80 < got["nc_sum"] / n < 120
+    if not force_group:
+        assert n / dom.num_focus_leaves < 20, "the test is meant to run on a tree with small leaves"
+    dom.close()
