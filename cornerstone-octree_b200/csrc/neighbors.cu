@@ -17,9 +17,13 @@
  *    walk — truncation at ngmax keeps the same entries — and the distance arithmetic is the reference's, operation by
  *    operation (no FMA contraction; norm2 is the right fold x*x + (y*y + z*z), util/array.hpp:236-240; distanceSq is
  *    (x*x + y*y) + z*z, findneighbors.hpp:33-60).  Self exclusion is by index (j != i) as on the CPU (hazard H2).
- *  Two other organisations of the same search were built and measured in round 2 (a walk steered by the warp's
- *  bounding box alone with certified acceptance, and a CTA-cooperative variant with shared staging); both returned
- *  identical lists and both were slower than this kernel, see profiles/r2_notes.md.
+ *  - Trees whose leaves hold few particles (the occupancy of a uniform tree jumps by 8x whenever the particle count
+ *    crosses a power of 8 times the bucket size) are searched by a second organisation, the group-steered search
+ *    further down: the walk is steered by the bounding box of the warp's targets alone, contiguous particle ranges are
+ *    staged whatever the leaf boundaries, and the reference's per-target pruning is reproduced by a certified
+ *    distance shell plus the reference's own box tests on the rare candidates inside the shell.
+ *  A CTA-cooperative variant with shared staging and a bit-mask batch variant were also built and measured in round 2;
+ *  both returned identical lists and both were slower, see profiles/r2_notes.md.
  */
 #include <algorithm>
 #include <cmath>
@@ -827,14 +831,14 @@ __global__ void __launch_bounds__(NB_THREADS) findNeighborsKernel(const T* __res
  * The cost of the search above grows with the number of leaves a warp visits: staging and the per-lane tests of the
  * nodes are paid per leaf, and the leaf occupancy of a tree jumps by 8x whenever the particle count crosses a power of
  * 8 times the bucket size (64 Mi particles with bucket 64: 32 per leaf, 128 Mi: ~8, 256 Mi: 16).  This variant keeps no
- * per-lane walk state at all and stages contiguous particle ranges whatever the leaf boundaries; its run time does not
- * depend on the leaf occupancy (71 ms at 64 Mi particles for 8 and for 4 particles per leaf, where the per-lane search
- * takes 106 and 160 ms), but at 32 particles per leaf the per-lane search is faster (52 vs 62 ms).  findNeighbors picks
- * by the mean leaf occupancy. */
+ * per-lane walk state at all and stages contiguous particle ranges whatever the leaf boundaries; its run time hardly
+ * depends on the leaf occupancy (64 Mi particles, ng ~ 100: 54.4 / 62.9 / 65 ms at 32 / 8 / 4 particles per leaf, where
+ * the per-lane search takes 51.5 / 106 / 160 ms; at 16 per leaf the two are equal).  findNeighbors picks by the mean
+ * leaf occupancy (NB_SMALL_LEAVES). */
 
-constexpr int NB_CAP            = 96;  // staged candidates per test round (filled in rounds of up to 32 loads)
+constexpr int NB_CAP            = 64;  // staged candidates per test round (filled in rounds of up to 32 loads)
 constexpr uint32_t NB_COARSE    = 64;  // subtrees with at most this many particles are staged whole
-constexpr double NB_SMALL_LEAVES = 20;  // mean particles per leaf below which the group-steered search is used
+constexpr double NB_SMALL_LEAVES = 12;  // mean particles per leaf below which the group-steered search is used
 constexpr uint32_t NB_BAD_LEAF  = 0x80000000u; // in NodeRange::y: a particle of this leaf lies outside the leaf's box
 
 struct alignas(16) GroupWalkShared
