@@ -1185,7 +1185,11 @@ __device__ __forceinline__ void warpSearchGroup(GroupWalkShared& sh, const uint2
         out += 4;
     };
 
-    const uint64_t ntx2 = pack2(-txf, -txf), nty2 = pack2(-tyf, -tyf), ntz2 = pack2(-tzf, -tzf);
+    // through a shuffle with the own lane: the values become opaque to ptxas, which otherwise re-derives them from the
+    // double coordinates (three FP64 subtractions and conversions) in every iteration of the test loop
+    const float txs = __shfl_sync(0xffffffffu, -txf, lane), tys = __shfl_sync(0xffffffffu, -tyf, lane),
+                tzs = __shfl_sync(0xffffffffu, -tzf, lane);
+    const uint64_t ntx2 = pack2(txs, txs), nty2 = pack2(tys, tys), ntz2 = pack2(tzs, tzs);
     const uint64_t zero2 = pack2(0.0f, 0.0f);
 
     /*! tests the `cnt` staged candidates four at a time (cnt is padded to a multiple of four with candidates at
@@ -1479,7 +1483,7 @@ __device__ __forceinline__ void warpSearchGroup(GroupWalkShared& sh, const uint2
 //! the kernel of the group-steered search; DEFER as in findNeighborsKernel.  Does nothing if too many leaves hold stray
 //! particles (trees over 32-bit keys: the key grid is coarse against the search radius), findNeighborsKernel runs then
 template<class T, bool PBC, bool FOLD, bool DEFER, class Th>
-__global__ void __launch_bounds__(NB_THREADS) findNeighborsGroupKernel(const T* __restrict__ x,
+__global__ void __launch_bounds__(NB_THREADS, 8) findNeighborsGroupKernel(const T* __restrict__ x,
                                                                   const T* __restrict__ y,
                                                                   const T* __restrict__ z,
                                                                   const Th* __restrict__ h,
