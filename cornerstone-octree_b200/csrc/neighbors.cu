@@ -775,7 +775,7 @@ __device__ __forceinline__ void warpSearchLanes(LaneWalkShared& sh, const uint2 
  *  but appended to `deferred` ([0] = count, then group numbers); this launch then runs the code of the open-box search
  *  for all interior groups, and a second launch (groupList = deferred) handles the few boundary groups with the
  *  periodic code, whose register footprint would otherwise slow down every warp. */
-template<class T, bool PBC, bool FOLD, bool DEFER, class Th>
+template<class T, bool PBC, bool FOLD, bool DEFER, class Th, bool PERSIST>
 __global__ void __launch_bounds__(NB_THREADS) findNeighborsKernel(const T* __restrict__ x,
                                                                   const T* __restrict__ y,
                                                                   const T* __restrict__ z,
@@ -796,35 +796,48 @@ __global__ void __launch_bounds__(NB_THREADS) findNeighborsKernel(const T* __res
                                                                   uint32_t* __restrict__ neighbors,
                                                                   uint32_t* __restrict__ neighborsCount,
                                                                   const uint32_t* __restrict__ numBad,
-                                                                  uint32_t badLimit)
+                                                                  uint32_t badLimit,
+                                                                  uint32_t* __restrict__ workCounter)
 {
     // the group-steered search runs instead (it was launched before this kernel with the same criterion)
     if (numBad != nullptr && *numBad <= badLimit) { return; }
     __shared__ LaneWalkShared shAll[NB_THREADS / 32];
-    size_t warpId = (size_t(blockIdx.x) * NB_THREADS + threadIdx.x) >> 5;
-    if (groupList)
+    /* PERSIST: groups are handed out through a device counter to one wave of blocks, so the grid does not depend on the
+     * (upper bound of the) number of groups and a kernel that has nothing to do costs next to nothing; otherwise one
+     * group per warp of the grid.  Which is faster depends on the variant (register allocation), see findNeighbors */
+    const unsigned lane  = threadIdx.x & 31;
+    const uint32_t limit = groupList ? groupList[0] : *numGroupsPtr;
+    size_t w             = (size_t(blockIdx.x) * NB_THREADS + threadIdx.x) >> 5;
+    while (true)
     {
-        if (warpId >= size_t(groupList[0])) { return; }
-        warpId = groupList[1 + warpId];
-    }
-    else if (warpId >= size_t(*numGroupsPtr)) { return; }
-    const uint2 grp = groups[warpId];
-    if (DEFER)
-    {
-        const unsigned lane = threadIdx.x & 31;
-        const uint32_t i    = min(grp.x + lane, grp.y - 1);
-        const T tx = x[i], ty = y[i], tz = z[i], s = T(2) * T(h[i]);
-        // insideBox of findneighbors.hpp:104-106
-        const bool inside = (tx - s >= box.lim[0]) && (ty - s >= box.lim[2]) && (tz - s >= box.lim[4]) &&
-                            (tx + s <= box.lim[1]) && (ty + s <= box.lim[3]) && (tz + s <= box.lim[5]);
-        if (__any_sync(0xffffffffu, !inside))
+        if (PERSIST)
         {
-            if (lane == 0) { deferred[1 + atomicAdd(&deferred[0], 1u)] = uint32_t(warpId); }
-            return;
+            uint32_t next = 0;
+            if (lane == 0) { next = atomicAdd(workCounter, 1u); }
+            w = __shfl_sync(0xffffffffu, next, 0);
         }
+        if (w >= limit) { break; }
+        const uint32_t g = groupList ? groupList[1 + w] : uint32_t(w);
+        const uint2 grp  = groups[g];
+        if (DEFER)
+        {
+            const uint32_t i = min(grp.x + lane, grp.y - 1);
+            const T tx = x[i], ty = y[i], tz = z[i], s = T(2) * T(h[i]);
+            // insideBox of findneighbors.hpp:104-106
+            const bool inside = (tx - s >= box.lim[0]) && (ty - s >= box.lim[2]) && (tz - s >= box.lim[4]) &&
+                                (tx + s <= box.lim[1]) && (ty + s <= box.lim[3]) && (tz + s <= box.lim[5]);
+            if (__any_sync(0xffffffffu, !inside))
+            {
+                if (lane == 0) { deferred[1 + atomicAdd(&deferred[0], 1u)] = g; }
+                if (PERSIST) { continue; }
+                break;
+            }
+        }
+        warpSearchLanes<T, PBC, FOLD, Th>(shAll[threadIdx.x >> 5], grp, x, y, z, h, first, box, childOffsets, parents, internalToLeaf,
+                                 layout, centers, sizes, ngmax, neighbors, neighborsCount);
+        if (!PERSIST) { break; }
+        __syncwarp();
     }
-    warpSearchLanes<T, PBC, FOLD, Th>(shAll[threadIdx.x >> 5], grp, x, y, z, h, first, box, childOffsets, parents, internalToLeaf,
-                             layout, centers, sizes, ngmax, neighbors, neighborsCount);
 }
 
 /* ================================================================ group-steered search (trees with small leaves)
@@ -832,13 +845,13 @@ __global__ void __launch_bounds__(NB_THREADS) findNeighborsKernel(const T* __res
  * nodes are paid per leaf, and the leaf occupancy of a tree jumps by 8x whenever the particle count crosses a power of
  * 8 times the bucket size (64 Mi particles with bucket 64: 32 per leaf, 128 Mi: ~8, 256 Mi: 16).  This variant keeps no
  * per-lane walk state at all and stages contiguous particle ranges whatever the leaf boundaries; its run time hardly
- * depends on the leaf occupancy (64 Mi particles, ng ~ 100: 54.4 / 62.9 / 65 ms at 32 / 8 / 4 particles per leaf, where
- * the per-lane search takes 51.5 / 106 / 160 ms; at 16 per leaf the two are equal).  findNeighbors picks by the mean
- * leaf occupancy (NB_SMALL_LEAVES). */
+ * depends on the leaf occupancy (64 Mi particles, ng ~ 100: 53.7 / 61.2 / 64 ms at 32 / 8 / 4 particles per leaf, where
+ * the per-lane search takes 48.0 / 106 / 160 ms; 32 Mi particles at 16 per leaf: 36.5 vs 37.2 ms, in a periodic box 41.2
+ * vs 50 ms).  findNeighbors picks by the mean leaf occupancy (NB_SMALL_LEAVES). */
 
 constexpr int NB_CAP            = 64;  // staged candidates per test round (filled in rounds of up to 32 loads)
 constexpr uint32_t NB_COARSE    = 64;  // subtrees with at most this many particles are staged whole
-constexpr double NB_SMALL_LEAVES = 12;  // mean particles per leaf below which the group-steered search is used
+constexpr double NB_SMALL_LEAVES = 20;  // mean particles per leaf below which the group-steered search is used
 constexpr uint32_t NB_BAD_LEAF  = 0x80000000u; // in NodeRange::y: a particle of this leaf lies outside the leaf's box
 
 struct alignas(16) GroupWalkShared
@@ -1482,7 +1495,7 @@ __device__ __forceinline__ void warpSearchGroup(GroupWalkShared& sh, const uint2
 
 //! the kernel of the group-steered search; DEFER as in findNeighborsKernel.  Does nothing if too many leaves hold stray
 //! particles (trees over 32-bit keys: the key grid is coarse against the search radius), findNeighborsKernel runs then
-template<class T, bool PBC, bool FOLD, bool DEFER, class Th>
+template<class T, bool PBC, bool FOLD, bool DEFER, class Th, bool PERSIST>
 __global__ void __launch_bounds__(NB_THREADS, 8) findNeighborsGroupKernel(const T* __restrict__ x,
                                                                   const T* __restrict__ y,
                                                                   const T* __restrict__ z,
@@ -1504,34 +1517,47 @@ __global__ void __launch_bounds__(NB_THREADS, 8) findNeighborsGroupKernel(const 
                                                                   uint32_t* __restrict__ neighbors,
                                                                   uint32_t* __restrict__ neighborsCount,
                                                                   const uint32_t* __restrict__ numBad,
-                                                                  uint32_t badLimit)
+                                                                  uint32_t badLimit,
+                                                                  uint32_t* __restrict__ workCounter)
 {
     if (*numBad > badLimit) { return; }
     __shared__ GroupWalkShared shAll[NB_THREADS / 32];
-    size_t warpId = (size_t(blockIdx.x) * NB_THREADS + threadIdx.x) >> 5;
-    if (groupList)
+    /* PERSIST: groups are handed out through a device counter to one wave of blocks, so the grid does not depend on the
+     * (upper bound of the) number of groups and a kernel that has nothing to do costs next to nothing; otherwise one
+     * group per warp of the grid.  Which is faster depends on the variant (register allocation), see findNeighbors */
+    const unsigned lane  = threadIdx.x & 31;
+    const uint32_t limit = groupList ? groupList[0] : *numGroupsPtr;
+    size_t w             = (size_t(blockIdx.x) * NB_THREADS + threadIdx.x) >> 5;
+    while (true)
     {
-        if (warpId >= size_t(groupList[0])) { return; }
-        warpId = groupList[1 + warpId];
-    }
-    else if (warpId >= size_t(*numGroupsPtr)) { return; }
-    const uint2 grp = groups[warpId];
-    if (DEFER)
-    {
-        const unsigned lane = threadIdx.x & 31;
-        const uint32_t i    = min(grp.x + lane, grp.y - 1);
-        const T tx = x[i], ty = y[i], tz = z[i], s = T(2) * T(h[i]);
-        // insideBox of findneighbors.hpp:104-106
-        const bool inside = (tx - s >= box.lim[0]) && (ty - s >= box.lim[2]) && (tz - s >= box.lim[4]) &&
-                            (tx + s <= box.lim[1]) && (ty + s <= box.lim[3]) && (tz + s <= box.lim[5]);
-        if (__any_sync(0xffffffffu, !inside))
+        if (PERSIST)
         {
-            if (lane == 0) { deferred[1 + atomicAdd(&deferred[0], 1u)] = uint32_t(warpId); }
-            return;
+            uint32_t next = 0;
+            if (lane == 0) { next = atomicAdd(workCounter, 1u); }
+            w = __shfl_sync(0xffffffffu, next, 0);
         }
+        if (w >= limit) { break; }
+        const uint32_t g = groupList ? groupList[1 + w] : uint32_t(w);
+        const uint2 grp  = groups[g];
+        if (DEFER)
+        {
+            const uint32_t i = min(grp.x + lane, grp.y - 1);
+            const T tx = x[i], ty = y[i], tz = z[i], s = T(2) * T(h[i]);
+            // insideBox of findneighbors.hpp:104-106
+            const bool inside = (tx - s >= box.lim[0]) && (ty - s >= box.lim[2]) && (tz - s >= box.lim[4]) &&
+                                (tx + s <= box.lim[1]) && (ty + s <= box.lim[3]) && (tz + s <= box.lim[5]);
+            if (__any_sync(0xffffffffu, !inside))
+            {
+                if (lane == 0) { deferred[1 + atomicAdd(&deferred[0], 1u)] = g; }
+                if (PERSIST) { continue; }
+                break;
+            }
+        }
+        warpSearchGroup<T, PBC, FOLD, Th>(shAll[threadIdx.x >> 5], grp, x, y, z, h, first, box, childOffsets, parents, nodeRange,
+                                     tau0, coarse, centers, sizes, ngmax, neighbors, neighborsCount);
+        if (!PERSIST) { break; }
+        __syncwarp();
     }
-    warpSearchGroup<T, PBC, FOLD, Th>(shAll[threadIdx.x >> 5], grp, x, y, z, h, first, box, childOffsets, parents, nodeRange,
-                                 tau0, coarse, centers, sizes, ngmax, neighbors, neighborsCount);
 }
 
 } // namespace
@@ -1568,7 +1594,24 @@ int findNeighbors(const T* x, const T* y, const T* z, const Th* h, uint32_t firs
                                                     groupOffsets, groups);
     CSB_LAUNCH_CHECK();
 
-    unsigned grid = iceil(maxGroups * 32, NB_THREADS);
+    // persistent grids (one wave of blocks per kernel); work[k] = next group of the k-th search launch; the list of the
+    // groups deferred to the periodic kernel follows
+    CSB_SCRATCH(work, uint32_t*, s, SCRATCH_E, (maxGroups + 5) * sizeof(uint32_t));
+    CSB_CHECK(cudaMemsetAsync(work, 0, 5 * sizeof(uint32_t), s));
+    uint32_t* deferred = work + 4;
+    int device = 0, numSms = 0;
+    CSB_CHECK(cudaGetDevice(&device));
+    CSB_CHECK(cudaDeviceGetAttribute(&numSms, cudaDevAttrMultiProcessorCount, device));
+    const unsigned fullGrid = iceil(maxGroups * 32, NB_THREADS);
+    auto waveOf = [&](auto kernel) -> unsigned
+    {
+        int perSm = 0;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, kernel, NB_THREADS, 0) != cudaSuccess || perSm < 1)
+        {
+            perSm = 4;
+        }
+        return unsigned(std::min<size_t>(size_t(numSms) * perSm, iceil(maxGroups * 32, NB_THREADS)));
+    };
 
     /* Trees with few particles per leaf (T = double): the group-steered search, preceded by its preparation - the
      * particle range below every node and the leaves with stray particles (the tolerances scale with the rounding unit
@@ -1603,44 +1646,58 @@ int findNeighbors(const T* x, const T* y, const T* z, const Th* h, uint32_t firs
             numBadGate = numBad;
             if (!pbc)
             {
-                findNeighborsGroupKernel<T, false, false, false, Th><<<grid, NB_THREADS, 0, s>>>(
+                auto k0 = findNeighborsGroupKernel<T, false, false, false, Th, false>;
+                k0<<<fullGrid, NB_THREADS, 0, s>>>(
                     x, y, z, h, first, groups, groupOffsets + numLeaves, nullptr, nullptr, box, childOffsets, parents,
-                    nodeRange, tau0, NB_COARSE, centers, sizes, ngmax, neighbors, neighborsCount, numBad, badLimit);
+                    nodeRange, tau0, NB_COARSE, centers, sizes, ngmax, neighbors, neighborsCount, numBad, badLimit, work + 0);
             }
             else
             {
-                CSB_SCRATCH(deferred, uint32_t*, s, SCRATCH_E, (maxGroups + 1) * sizeof(uint32_t));
-                CSB_CHECK(cudaMemsetAsync(deferred, 0, sizeof(uint32_t), s));
-                findNeighborsGroupKernel<T, false, false, true, Th><<<grid, NB_THREADS, 0, s>>>(
+                auto k0 = findNeighborsGroupKernel<T, false, false, true, Th, false>;
+                k0<<<fullGrid, NB_THREADS, 0, s>>>(
                     x, y, z, h, first, groups, groupOffsets + numLeaves, nullptr, deferred, box, childOffsets, parents,
-                    nodeRange, tau0, NB_COARSE, centers, sizes, ngmax, neighbors, neighborsCount, numBad, badLimit);
+                    nodeRange, tau0, NB_COARSE, centers, sizes, ngmax, neighbors, neighborsCount, numBad, badLimit, work + 0);
                 CSB_LAUNCH_CHECK();
-                findNeighborsGroupKernel<T, true, true, false, Th><<<grid, NB_THREADS, 0, s>>>(
+                auto k1 = findNeighborsGroupKernel<T, true, true, false, Th, false>;
+                k1<<<fullGrid, NB_THREADS, 0, s>>>(
                     x, y, z, h, first, groups, groupOffsets + numLeaves, deferred, nullptr, box, childOffsets, parents,
-                    nodeRange, tau0, NB_COARSE, centers, sizes, ngmax, neighbors, neighborsCount, numBad, badLimit);
+                    nodeRange, tau0, NB_COARSE, centers, sizes, ngmax, neighbors, neighborsCount, numBad, badLimit, work + 1);
             }
             CSB_LAUNCH_CHECK();
         }
     }
 
+    /* The per-lane search.  Measured at 64 Mi particles: the open-box kernel for double is faster with persistent warps
+     * (48.0 vs 51.5 ms), the float and periodic variants are faster with one group per warp of the grid (28.5 vs 33.9,
+     * 56.9 vs 62.7 ms); kernels that only run if the group-steered search declined are launched persistent, which makes
+     * the launch that finds nothing to do free. */
+    auto launchLanes = [&](auto kernel, bool persist, const uint32_t* groupList, uint32_t* deferredOut, uint32_t* counter)
+    {
+        kernel<<<persist ? waveOf(kernel) : fullGrid, NB_THREADS, 0, s>>>(
+            x, y, z, h, first, groups, groupOffsets + numLeaves, groupList, deferredOut, box, childOffsets, parents,
+            internalToLeaf, layout, centers, sizes, ngmax, neighbors, neighborsCount, numBadGate, badLimit, counter);
+    };
+    const bool gated = numBadGate != nullptr;
     if (!pbc)
     {
-        findNeighborsKernel<T, false, false, false, Th><<<grid, NB_THREADS, 0, s>>>(
-            x, y, z, h, first, groups, groupOffsets + numLeaves, nullptr, nullptr, box, childOffsets, parents,
-            internalToLeaf, layout, centers, sizes, ngmax, neighbors, neighborsCount, numBadGate, badLimit);
+        if (gated || sizeof(T) == 8)
+        {
+            launchLanes(findNeighborsKernel<T, false, false, false, Th, true>, true, nullptr, nullptr, work + 2);
+        }
+        else { launchLanes(findNeighborsKernel<T, false, false, false, Th, false>, false, nullptr, nullptr, work + 2); }
+    }
+    else if (gated)
+    {
+        launchLanes(findNeighborsKernel<T, false, false, true, Th, true>, true, nullptr, deferred, work + 2);
+        CSB_LAUNCH_CHECK();
+        launchLanes(findNeighborsKernel<T, true, true, false, Th, true>, true, deferred, nullptr, work + 3);
     }
     else
     {
         // interior groups with the open-box code, then the groups at the periodic boundaries
-        CSB_SCRATCH(deferred, uint32_t*, s, SCRATCH_E, (maxGroups + 1) * sizeof(uint32_t));
-        if (!numBadGate) { CSB_CHECK(cudaMemsetAsync(deferred, 0, sizeof(uint32_t), s)); }
-        findNeighborsKernel<T, false, false, true, Th><<<grid, NB_THREADS, 0, s>>>(
-            x, y, z, h, first, groups, groupOffsets + numLeaves, nullptr, deferred, box, childOffsets, parents,
-            internalToLeaf, layout, centers, sizes, ngmax, neighbors, neighborsCount, numBadGate, badLimit);
+        launchLanes(findNeighborsKernel<T, false, false, true, Th, false>, false, nullptr, deferred, work + 2);
         CSB_LAUNCH_CHECK();
-        findNeighborsKernel<T, true, true, false, Th><<<grid, NB_THREADS, 0, s>>>(
-            x, y, z, h, first, groups, groupOffsets + numLeaves, deferred, nullptr, box, childOffsets, parents,
-            internalToLeaf, layout, centers, sizes, ngmax, neighbors, neighborsCount, numBadGate, badLimit);
+        launchLanes(findNeighborsKernel<T, true, true, false, Th, false>, false, deferred, nullptr, work + 3);
     }
     CSB_LAUNCH_CHECK();
     return 0;
