@@ -419,8 +419,22 @@ public:
             CSB_TRY(ordering_.resize(exchangeSize, s, true));
             BufferDescription o1e{start_, end_, exchangeSize};
             const LocalIndex recvStart = receiveStart(o1e, numRecv);
+            /* (x,y,z,h) records of the present particles at their buffer positions: the pack kernels of the exchange
+             * and the gather into the new order read one 32-byte record per particle through the ordering instead of
+             * four scattered elements (a random 8-byte read costs a 128-byte DRAM fetch); the received particles are
+             * added below */
+            CSB_TRY(recBuf_.resize(size_t(exchangeSize) * 4 * sizeof(T), s));
+            {
+                const void* src[4] = {x_.p, y_.p, z_.p, h_.p};
+                CSB_TRY(packRecords4(src, start_, numPart, recBuf_.p, int(sizeof(T)), s));
+            }
             std::vector<uint32_t> recvCounts;
             CSB_TRY(exchangeParticles(sendIdx, recvStart, numRecv, recvCounts, s));
+            if (numRecv)
+            {
+                const void* src[4] = {x_.p, y_.p, z_.p, h_.p};
+                CSB_TRY(packRecords4(src, recvStart, numRecv, recBuf_.p, int(sizeof(T)), s));
+            }
             log_.recvStart  = recvStart;
             log_.numRecv    = numRecv;
             log_.recvCounts = recvCounts;
@@ -498,7 +512,8 @@ public:
         {
             const void* src[4] = {x_.p, y_.p, z_.p, h_.p};
             void* dst[4]       = {sx_.p, sy_.p, sz_.p, sh_.p};
-            CSB_TRY(cs_gather_arrays4(orderView, numAssigned, bufSize_, src, dst, int(sizeof(T)), s));
+            if (P > 1) { CSB_TRY(gatherFromRecords4(orderView, numAssigned, recBuf_.p, dst, int(sizeof(T)), s)); }
+            else { CSB_TRY(cs_gather_arrays4(orderView, numAssigned, bufSize_, src, dst, int(sizeof(T)), s)); }
         }
 
         phase("gatherArrays", s);
@@ -1420,7 +1435,8 @@ private:
     }
 
     /* ------------------------------------------------------------ exchangeParticlesGpu
-     *  (domain/domaindecomp_mpi_gpu.cuh:70-166).  Outgoing ranges are gathered through the ordering into one packed
+     *  (domain/domaindecomp_mpi_gpu.cuh:70-166).  Outgoing ranges are gathered through the ordering (from the particle
+     *  records, recBuf_) into one packed
      *  buffer per destination ([x | y | z | h], each block 16-byte aligned); incoming blocks land directly in the
      *  particle arrays at [recvStart, recvStart + numRecv), sources in ascending rank order (the reference takes
      *  them in arrival order, domaindecomp_mpi.hpp:116-140; the stable key sort that follows makes the final order
@@ -1485,12 +1501,12 @@ private:
                     size_t dstOffset = size_t(recvStarts[r]);
                     for (int src = 0; src < me; ++src)
                         if (src != r) { dstOffset += allCounts[size_t(src) * P + r]; }
-                    const void* src4[4] = {x_.p, y_.p, z_.p, h_.p};
                     void* dst4[4];
                     for (int k = 0; k < 4; ++k)
                         dst4[k] = static_cast<T*>(peers[size_t(r) * 4 + k]) + dstOffset;
                     cudaStream_t ps = pushStreams_[size_t(launched++) % pushStreams_.size()];
-                    CSB_TRY(cs_gather4(ordering_.p + start_ + sendIdx[r], c, src4, dst4, int(sizeof(T)), ps));
+                    CSB_TRY(gatherFromRecords4(ordering_.p + start_ + sendIdx[r], c, recBuf_.p, dst4, int(sizeof(T)),
+                                               ps));
                     comm.bytesSent += 4 * c * sizeof(T);
                 }
                 for (size_t q = 0; q < pushStreams_.size(); ++q)
@@ -1516,10 +1532,9 @@ private:
             size_t c = sendCounts[r];
             if (c == 0) { continue; }
             size_t be          = blockElems(c);
-            const void* src[4] = {x_.p, y_.p, z_.p, h_.p};
             void* dst[4]       = {sendBuf_.p + off, sendBuf_.p + off + be, sendBuf_.p + off + 2 * be,
                                   sendBuf_.p + off + 3 * be};
-            CSB_TRY(cs_gather4(ordering_.p + start_ + sendIdx[r], c, src, dst, int(sizeof(T)), s));
+            CSB_TRY(gatherFromRecords4(ordering_.p + start_ + sendIdx[r], c, recBuf_.p, dst, int(sizeof(T)), s));
             for (int k = 0; k < 4; ++k)
                 sends.push_back({r, dst[k], c * sizeof(T)});
             off += 4 * be;
@@ -1733,7 +1748,7 @@ private:
     DevBuf<uint32_t> peerBuf_, rangeTables_, tlValid_, runStarts_, pickBuf_;
     DevBuf<K> tlKeys_, rejKeys_, reqKeys_;
     DevBuf<T> centers4_, searchCenters_, searchSizes_;
-    DevBuf<char> tlRecv_, rejRecv_, reqRecv_, fieldSendBuf_;
+    DevBuf<char> tlRecv_, rejRecv_, reqRecv_, fieldSendBuf_, recBuf_;
 
     int rank_, numRanks_;
     // exchangeParticles through peer memory; cleared when the transport cannot map it (CSB_NO_PEER_PUSH forces the

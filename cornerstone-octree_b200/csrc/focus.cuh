@@ -83,6 +83,11 @@ int gatherU32(const int* idx, int n, const uint32_t* src, uint32_t* dst, cudaStr
 int scatterU32(const int* idx, int n, const uint32_t* src, uint32_t* dst, cudaStream_t s);
 int gatherRangesWords(const uint32_t* rangeScan, const uint32_t* rangeStart, int numRanges, uint32_t total, int words,
                       const void* src, void* out, cudaStream_t s);
+//! (x,y,z,h) records of the elements [first, first + n) at the same positions of `rec` (sort.cu)
+int packRecords4(const void* const* src4, size_t first, size_t n, void* rec, int elemBytes, cudaStream_t s);
+//! dst4[k][i] = rec[ordering[i]].v[k]; the destination arrays may be peer memory (sort.cu)
+int gatherFromRecords4(const uint32_t* ordering, size_t n, const void* rec, void* const* dst4, int elemBytes,
+                       cudaStream_t s);
 //! out[k] = src[order[k]], elements of `words` 32-bit words
 int gatherWords(const uint32_t* order, uint32_t n, int words, const void* src, void* out, cudaStream_t s);
 //! replay of a recorded particle exchange for one more field (reapplySync, domain/domain.hpp:297-329)

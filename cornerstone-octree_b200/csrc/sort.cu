@@ -655,7 +655,68 @@ int gatherArrays4(const uint32_t* ordering, size_t n, size_t srcCount, const voi
     return 0;
 }
 
+template<class E>
+__global__ void packRec4RangeKernel(size_t first, size_t n, const E* __restrict__ a, const E* __restrict__ b,
+                                    const E* __restrict__ c, const E* __restrict__ d, Rec4<E>* __restrict__ rec)
+{
+    size_t i = size_t(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i < n)
+    {
+        Rec4<E> r;
+        r.v[0]         = a[first + i];
+        r.v[1]         = b[first + i];
+        r.v[2]         = c[first + i];
+        r.v[3]         = d[first + i];
+        rec[first + i] = r;
+    }
+}
+
 } // namespace
+
+/*! records (x,y,z,h) of the elements [first, first + n) of four arrays, stored at the same positions of `rec`: the
+ *  particle exchange and the gather that follows read whole 32-byte records through the ordering instead of four
+ *  scattered elements (a random 8-byte read costs a 128-byte DRAM fetch, see gatherArrays4) */
+int packRecords4(const void* const* src4, size_t first, size_t n, void* rec, int elemBytes, cudaStream_t s)
+{
+    if (n == 0) { return 0; }
+    if (elemBytes == 8)
+    {
+        packRec4RangeKernel<uint64_t><<<iceil(n, 256), 256, 0, s>>>(
+            first, n, static_cast<const uint64_t*>(src4[0]), static_cast<const uint64_t*>(src4[1]),
+            static_cast<const uint64_t*>(src4[2]), static_cast<const uint64_t*>(src4[3]),
+            static_cast<Rec4<uint64_t>*>(rec));
+    }
+    else
+    {
+        packRec4RangeKernel<uint32_t><<<iceil(n, 256), 256, 0, s>>>(
+            first, n, static_cast<const uint32_t*>(src4[0]), static_cast<const uint32_t*>(src4[1]),
+            static_cast<const uint32_t*>(src4[2]), static_cast<const uint32_t*>(src4[3]),
+            static_cast<Rec4<uint32_t>*>(rec));
+    }
+    CSB_LAUNCH_CHECK();
+    return 0;
+}
+
+//! dst4[k][i] = rec[ordering[i]].v[k]; the destination arrays may be peer memory
+int gatherFromRecords4(const uint32_t* ordering, size_t n, const void* rec, void* const* dst4, int elemBytes,
+                       cudaStream_t s)
+{
+    if (n == 0) { return 0; }
+    if (elemBytes == 8)
+    {
+        gatherRec4Kernel<uint64_t, 1><<<iceil(n, 256), 256, 0, s>>>(
+            ordering, n, static_cast<const Rec4<uint64_t>*>(rec), static_cast<uint64_t*>(dst4[0]),
+            static_cast<uint64_t*>(dst4[1]), static_cast<uint64_t*>(dst4[2]), static_cast<uint64_t*>(dst4[3]));
+    }
+    else
+    {
+        gatherRec4Kernel<uint32_t, 1><<<iceil(n, 256), 256, 0, s>>>(
+            ordering, n, static_cast<const Rec4<uint32_t>*>(rec), static_cast<uint32_t*>(dst4[0]),
+            static_cast<uint32_t*>(dst4[1]), static_cast<uint32_t*>(dst4[2]), static_cast<uint32_t*>(dst4[3]));
+    }
+    CSB_LAUNCH_CHECK();
+    return 0;
+}
 
 int sortByKeyU64(uint64_t* keys, uint32_t* values, size_t n, uint64_t* keyBuf, uint32_t* valueBuf, void* tmp,
                  size_t tmpBytes, cudaStream_t stream)
