@@ -428,6 +428,7 @@ public:
                 const void* src[4] = {x_.p, y_.p, z_.p, h_.p};
                 CSB_TRY(packRecords4(src, start_, numPart, recBuf_.p, int(sizeof(T)), s));
             }
+            phase("  pack records", s);
             std::vector<uint32_t> recvCounts;
             CSB_TRY(exchangeParticles(sendIdx, recvStart, numRecv, recvCounts, s));
             if (numRecv)
@@ -1466,7 +1467,9 @@ private:
             std::vector<void*> peers;
             std::vector<uint64_t> recvStarts;
             x_.sharedWithPeers = y_.sharedWithPeers = z_.sharedWithPeers = h_.sharedWithPeers = true;
+            phase("  xp counts", s);
             int st = comm.sharePointers(mine, 4, uint64_t(recvStart), peers, recvStarts, s);
+            phase("  xp sharePointers", s);
             if (st == 2) { peerPush_ = false; }
             else if (st != 0) { return st; }
             else
@@ -1515,7 +1518,10 @@ private:
                     CSB_CHECK(cudaStreamWaitEvent(s, pushDone_[q], 0));
                 }
                 CSB_CHECK(cudaStreamSynchronize(s)); // my stores have landed ...
-                return comm.barrier(s);              // ... and so have everybody else's
+                phase("  xp push", s);
+                int bst = comm.barrier(s); // ... and so have everybody else's
+                phase("  xp barrier", s);
+                return bst;
             }
         }
 

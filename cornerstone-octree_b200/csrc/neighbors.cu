@@ -1560,6 +1560,31 @@ __global__ void __launch_bounds__(NB_THREADS, 8) findNeighborsGroupKernel(const 
     }
 }
 
+/*! periodic boxes: groups whose targets all keep their search spheres inside the box (findneighbors.hpp:104-106) go to
+ *  `interior`, the others to `boundary` ([0] = count, then group numbers): the interior groups are then searched by the
+ *  open-box kernel, the few boundary groups by the periodic one */
+template<class T, class Th>
+__global__ void classifyGroupsKernel(const T* __restrict__ x, const T* __restrict__ y, const T* __restrict__ z,
+                                     const Th* __restrict__ h, const uint2* __restrict__ groups,
+                                     const uint32_t* __restrict__ numGroupsPtr, Box<T> box,
+                                     uint32_t* __restrict__ interior, uint32_t* __restrict__ boundary)
+{
+    const size_t w = (size_t(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+    if (w >= size_t(*numGroupsPtr)) { return; }
+    const unsigned lane = threadIdx.x & 31;
+    const uint2 grp     = groups[w];
+    const uint32_t i    = min(grp.x + lane, grp.y - 1);
+    const T tx = x[i], ty = y[i], tz = z[i], s = T(2) * T(h[i]);
+    const bool inside = (tx - s >= box.lim[0]) && (ty - s >= box.lim[2]) && (tz - s >= box.lim[4]) &&
+                        (tx + s <= box.lim[1]) && (ty + s <= box.lim[3]) && (tz + s <= box.lim[5]);
+    const bool atBoundary = __any_sync(0xffffffffu, !inside);
+    if (lane == 0)
+    {
+        uint32_t* list                 = atBoundary ? boundary : interior;
+        list[1 + atomicAdd(&list[0], 1u)] = uint32_t(w);
+    }
+}
+
 } // namespace
 
 template<class T, class Th>
@@ -1596,9 +1621,10 @@ int findNeighbors(const T* x, const T* y, const T* z, const Th* h, uint32_t firs
 
     // persistent grids (one wave of blocks per kernel); work[k] = next group of the k-th search launch; the list of the
     // groups deferred to the periodic kernel follows
-    CSB_SCRATCH(work, uint32_t*, s, SCRATCH_E, (maxGroups + 5) * sizeof(uint32_t));
+    CSB_SCRATCH(work, uint32_t*, s, SCRATCH_E, (2 * maxGroups + 8) * sizeof(uint32_t));
     CSB_CHECK(cudaMemsetAsync(work, 0, 5 * sizeof(uint32_t), s));
     uint32_t* deferred = work + 4;
+    uint32_t* interior = deferred + maxGroups + 1; // used when the groups are classified up front (see below)
     int device = 0, numSms = 0;
     CSB_CHECK(cudaGetDevice(&device));
     CSB_CHECK(cudaDeviceGetAttribute(&numSms, cudaDevAttrMultiProcessorCount, device));
@@ -1691,6 +1717,17 @@ int findNeighbors(const T* x, const T* y, const T* z, const Th* h, uint32_t firs
         launchLanes(findNeighborsKernel<T, false, false, true, Th, true>, true, nullptr, deferred, work + 2);
         CSB_LAUNCH_CHECK();
         launchLanes(findNeighborsKernel<T, true, true, false, Th, true>, true, deferred, nullptr, work + 3);
+    }
+    else if (sizeof(T) == 8)
+    {
+        // the groups are classified up front, so that the interior ones can take the persistent open-box kernel
+        CSB_CHECK(cudaMemsetAsync(interior, 0, sizeof(uint32_t), s));
+        classifyGroupsKernel<T, Th><<<fullGrid, NB_THREADS, 0, s>>>(x, y, z, h, groups, groupOffsets + numLeaves, box,
+                                                                    interior, deferred);
+        CSB_LAUNCH_CHECK();
+        launchLanes(findNeighborsKernel<T, false, false, false, Th, true>, true, interior, nullptr, work + 2);
+        CSB_LAUNCH_CHECK();
+        launchLanes(findNeighborsKernel<T, true, true, false, Th, false>, false, deferred, nullptr, work + 3);
     }
     else
     {

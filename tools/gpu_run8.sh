@@ -1,5 +1,6 @@
 cd $GRAFT_REPO_ROOT
 mkdir -p gpurun_out
-timeout 900 python -m pytest tests -m gpu -x -q > gpurun_out/r2_pytest_full.log 2>&1; tail -n 4 gpurun_out/r2_pytest_full.log
-CSB_TUNING=2=2 timeout 900 python -m pytest tests -m gpu -x -q > gpurun_out/r2_pytest_full_g.log 2>&1; tail -n 4 gpurun_out/r2_pytest_full_g.log
-CSB_TUNING=2=1 timeout 900 python -m pytest tests -m gpu -x -q > gpurun_out/r2_pytest_full_l.log 2>&1; tail -n 4 gpurun_out/r2_pytest_full_l.log
+rm -f gpurun_out/r2_exp_nb_bucket.*
+timeout 300 python tools/exp_neighbors.py --bucket 64 --pbc 1 --only 0,0 >> gpurun_out/r2_exp_nb_bucket.jsonl 2>> gpurun_out/r2_exp_nb_bucket.err
+timeout 600 python -m pytest tests -m gpu -x -q 2>&1 | tail -n 3
+cut -c1-130 gpurun_out/r2_exp_nb_bucket.jsonl; tail -n 3 gpurun_out/r2_exp_nb_bucket.err
