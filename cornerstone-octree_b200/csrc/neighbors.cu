@@ -850,7 +850,7 @@ __global__ void __launch_bounds__(NB_THREADS) findNeighborsKernel(const T* __res
  * vs 50 ms).  findNeighbors picks by the mean leaf occupancy (NB_SMALL_LEAVES). */
 
 constexpr int NB_CAP            = 64;  // staged candidates per test round (filled in rounds of up to 32 loads)
-constexpr uint32_t NB_COARSE    = 64;  // subtrees with at most this many particles are staged whole
+constexpr uint32_t NB_COARSE    = 64;  // subtrees with at most this many particles are staged whole (lower limit)
 constexpr double NB_SMALL_LEAVES = 20;  // mean particles per leaf below which the group-steered search is used
 constexpr uint32_t NB_BAD_LEAF  = 0x80000000u; // in NodeRange::y: a particle of this leaf lies outside the leaf's box
 
@@ -1670,24 +1670,29 @@ int findNeighbors(const T* x, const T* y, const T* z, const Th* h, uint32_t firs
                 x, y, z, childOffsets, nodeRange, centers, sizes, numNodes, tolNest, parents, numBad);
             CSB_LAUNCH_CHECK();
             numBadGate = numBad;
+            // subtrees up to this size are staged whole: about one level above the leaves (measured: 32 Mi particles at
+            // 16 per leaf in a periodic box 41.2 / 38.6 / 36.3 ms for 64 / 128 / 256, 64 Mi at 8 per leaf 61.3 / 61.2 /
+            // 63.0 ms)
+            const double meanLeaf = double(last - first) / double(numLeaves);
+            const uint32_t coarse = uint32_t(std::min(std::max(12.0 * meanLeaf, double(NB_COARSE)), 256.0));
             if (!pbc)
             {
                 auto k0 = findNeighborsGroupKernel<T, false, false, false, Th, false>;
                 k0<<<fullGrid, NB_THREADS, 0, s>>>(
                     x, y, z, h, first, groups, groupOffsets + numLeaves, nullptr, nullptr, box, childOffsets, parents,
-                    nodeRange, tau0, NB_COARSE, centers, sizes, ngmax, neighbors, neighborsCount, numBad, badLimit, work + 0);
+                    nodeRange, tau0, coarse, centers, sizes, ngmax, neighbors, neighborsCount, numBad, badLimit, work + 0);
             }
             else
             {
                 auto k0 = findNeighborsGroupKernel<T, false, false, true, Th, false>;
                 k0<<<fullGrid, NB_THREADS, 0, s>>>(
                     x, y, z, h, first, groups, groupOffsets + numLeaves, nullptr, deferred, box, childOffsets, parents,
-                    nodeRange, tau0, NB_COARSE, centers, sizes, ngmax, neighbors, neighborsCount, numBad, badLimit, work + 0);
+                    nodeRange, tau0, coarse, centers, sizes, ngmax, neighbors, neighborsCount, numBad, badLimit, work + 0);
                 CSB_LAUNCH_CHECK();
                 auto k1 = findNeighborsGroupKernel<T, true, true, false, Th, false>;
                 k1<<<fullGrid, NB_THREADS, 0, s>>>(
                     x, y, z, h, first, groups, groupOffsets + numLeaves, deferred, nullptr, box, childOffsets, parents,
-                    nodeRange, tau0, NB_COARSE, centers, sizes, ngmax, neighbors, neighborsCount, numBad, badLimit, work + 1);
+                    nodeRange, tau0, coarse, centers, sizes, ngmax, neighbors, neighborsCount, numBad, badLimit, work + 1);
             }
             CSB_LAUNCH_CHECK();
         }
