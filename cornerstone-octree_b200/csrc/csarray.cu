@@ -140,11 +140,13 @@ __global__ void __launch_bounds__(Shape::leaves) nodeCountsPipelinedKernel(const
         m.staged = W <= uint32_t(WINDOW);
         m.shift = 0, m.headEnd = 0, m.tailBegin = W;
         uint32_t bytes = 0;
+        K* dst         = nullptr;
+        uintptr_t lo   = 0;
         if (m.staged && W)
         {
             const uintptr_t base = reinterpret_cast<uintptr_t>(keys), end = base + n * sizeof(K);
             const uintptr_t a = base + A * sizeof(K), e = base + B * sizeof(K);
-            uintptr_t lo      = a & ~uintptr_t(15);          // rounded outwards ...
+            lo                = a & ~uintptr_t(15);          // rounded outwards ...
             uintptr_t hi      = (e + 15) & ~uintptr_t(15);
             if (lo < base) { lo += 16; }                     // ... and clipped to the array
             if (hi > end) { hi -= 16; }
@@ -155,14 +157,16 @@ __global__ void __launch_bounds__(Shape::leaves) nodeCountsPipelinedKernel(const
                 bytes       = uint32_t(hi - lo);
                 m.headEnd   = lo > a ? uint32_t((lo - a) / sizeof(K)) : 0u;
                 m.tailBegin = hi < e ? uint32_t((hi - a) / sizeof(K)) : W;
-                K* dst      = buffers + size_t(b) * BUF + m.shift + (long long)(lo - a) / (long long)sizeof(K);
-                mbarExpectTx(&bar[b], bytes);
-                bulkCopyG2S(dst, reinterpret_cast<const void*>(lo), bytes, &bar[b]);
+                dst         = buffers + size_t(b) * BUF + m.shift + (long long)(lo - a) / (long long)sizeof(K);
             }
             else { m.headEnd = W; } // the whole (tiny) window is loaded normally
         }
+        /* the description of the stage is written BEFORE the barrier is armed: the arrival below releases it to the
+         * threads that wait on the barrier.  (Written after the copy was started, a short copy could complete the phase
+         * before the description was in place - found by compute-sanitizer, which slows this thread down.) */
         meta[b] = m;
-        if (bytes == 0) { mbarExpectTx(&bar[b], 0); }
+        mbarExpectTx(&bar[b], bytes);
+        if (bytes) { bulkCopyG2S(dst, reinterpret_cast<const void*>(lo), bytes, &bar[b]); }
     };
 
     // prologue: the first STAGES - 1 windows of this block

@@ -582,3 +582,54 @@ def test_find_neighbors_double_coordinates_float_h(pbc):
     m = np.arange(ngmax)[None, :] < np.minimum(nc_o, ngmax)[:, None]
     assert np.array_equal(host(nb).reshape(n, ngmax)[m], nb_o.reshape(n, ngmax)[m])
     assert nc_o.max() > 10
+
+
+@pytest.mark.skipif(ref() is None, reason="needs oracle/_ref")
+@pytest.mark.parametrize("pbc,search", [(0, 1), (0, 2), (1, 1), (1, 2)])
+def test_find_neighbors_particles_outside_their_leaf_boxes(pbc, search):
+    """Arrays that do not belong to the tree: 5 % of the particles are moved by up to a search radius AFTER keys, tree
+    and layout were built, so they lie outside the box of their leaf.  The reference still finds such a particle only
+    from targets whose own walk enters its leaf (findneighbors.hpp:108-146), which no longer follows from the
+    distance alone.  Both searches (1 = per-lane walks, 2 = group-steered with its stray-leaf preparation, forced) must
+    return the reference's lists; the unperturbed case on the same tree is checked too."""
+    import ctypes as C
+
+    from _libs import ref_lib
+    n, ngmax = 40000, 128
+    keys, (x, y, z), lim, _ = sorted_keys("u64d", n, "uniform")
+    bnd = (pbc, pbc, pbc)
+    lo, co = oracle().compute_octree("u64", keys, 16)
+    to = oracle().build_octree("u64", lo)
+    cen_o, siz_o = oracle().node_fp_centers("u64d", to["prefixes"], lim, bnd)
+    layout_o = np.zeros(lo.size, dtype=np.uint32)
+    layout_o[1:] = np.cumsum(co)
+    h = const_h(n, 40, np.float64, 8.0)
+    rng = np.random.default_rng(12)
+    P = lambda a: a.ctypes.data_as(C.c_void_p)  # noqa: E731
+    lim_a, bnd_a = np.array(lim, dtype=np.float64), np.array(bnd, dtype=np.int32)
+    tree = capi().Octree(dev(lo))
+    cen, siz = capi().compute_geo_centers(tree.prefixes, torch.float64, lim, bnd)
+    dl = dev(layout_o)
+    capi().tuning_set(2, search)
+    try:
+        for moved in (False, True):
+            xs, ys, zs = x.copy(), y.copy(), z.copy()
+            if moved:
+                pick = rng.random(n) < 0.05
+                for a in (xs, ys, zs):
+                    a[pick] += (rng.random(int(pick.sum())) - 0.5) * 4.0 * h[0]
+                    np.clip(a, lim[0] + 1e-9, lim[1] - 1e-9, out=a)
+            nb_o, nc_o = np.zeros(n * ngmax, dtype=np.uint32), np.zeros(n, dtype=np.uint32)
+            ref_lib().ref_find_neighbors_u64d(P(xs), P(ys), P(zs), P(h), C.c_uint(0), C.c_uint(n), P(lim_a), P(bnd_a),
+                                              C.c_int(to["numLeaves"]), C.c_int(to["numNodes"]), P(to["prefixes"]),
+                                              P(to["childOffsets"]), P(to["parents"]), P(to["internalToLeaf"]),
+                                              P(to["leafToInternal"]), P(to["levelRange"]), P(lo), P(layout_o),
+                                              P(cen_o), P(siz_o), C.c_uint(ngmax), P(nb_o), P(nc_o))
+            nb, nc = capi().find_neighbors(dev(xs), dev(ys), dev(zs), dev(h), 0, n, lim, bnd, tree, dl, cen, siz, ngmax)
+            torch.cuda.synchronize()
+            assert np.array_equal(host(nc), nc_o), (moved, int((host(nc) != nc_o).sum()))
+            m = np.arange(ngmax)[None, :] < np.minimum(nc_o, ngmax)[:, None]
+            assert np.array_equal(host(nb).reshape(n, ngmax)[m], nb_o.reshape(n, ngmax)[m]), moved
+            assert nc_o.max() > 10
+    finally:
+        capi().tuning_set(2, 0)
