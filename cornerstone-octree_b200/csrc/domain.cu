@@ -474,6 +474,7 @@ public:
                     CSB_REQUIRE(runs.back() == size_t(numAssigned), "merge runs do not cover the assigned particles");
                     CSB_TRY(keyBuf_.resize(std::max<size_t>(numAssigned, 1), s));
                     CSB_TRY(valueBuf_.resize(std::max<size_t>(numAssigned, 1), s));
+                    bool inBuffers = false;
                     if (numPresent > numRecv)
                     {
                         // steady state, few particles migrate: merge the small received runs among themselves first,
@@ -482,12 +483,18 @@ public:
                         CSB_TRY(mergeSortedRuns<K>(assignedKeys_.p, assignedOrder_.p, runs.data() + firstRecv, P,
                                                    keyBuf_.p, valueBuf_.p, s));
                         const size_t two[3] = {0, recvFirst ? size_t(numRecv) : size_t(numPresent), size_t(numAssigned)};
-                        CSB_TRY(mergeSortedRuns<K>(assignedKeys_.p, assignedOrder_.p, two, 2, keyBuf_.p, valueBuf_.p, s));
+                        CSB_TRY(mergeSortedRuns<K>(assignedKeys_.p, assignedOrder_.p, two, 2, keyBuf_.p, valueBuf_.p, s,
+                                                   &inBuffers));
                     }
                     else
                     {
                         CSB_TRY(mergeSortedRuns<K>(assignedKeys_.p, assignedOrder_.p, runs.data(), int(runs.size()) - 1,
-                                                   keyBuf_.p, valueBuf_.p, s));
+                                                   keyBuf_.p, valueBuf_.p, s, &inBuffers));
+                    }
+                    if (inBuffers) // an odd number of merge rounds: the result sits in the double buffers
+                    {
+                        assignedKeys_.swap(keyBuf_);
+                        assignedOrder_.swap(valueBuf_);
                     }
                 }
                 keyView   = assignedKeys_.p;

@@ -122,7 +122,7 @@ size_t buildOctreeTempBytesU64(int numLeaves);
 /* merge.cu */
 template<class K>
 int mergeSortedRuns(K* keys, uint32_t* vals, const size_t* runOffsets, int numRuns, K* keyBuf, uint32_t* valBuf,
-                    cudaStream_t s);
+                    cudaStream_t s, bool* resultInBuffers = nullptr);
 
 /* sort.cu */
 int sortByKeyU64(uint64_t*, uint32_t*, size_t, uint64_t*, uint32_t*, void*, size_t, cudaStream_t);
