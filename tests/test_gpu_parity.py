@@ -585,10 +585,13 @@ def test_find_neighbors_double_coordinates_float_h(pbc):
 
 
 @pytest.mark.skipif(ref() is None, reason="needs oracle/_ref")
+@pytest.mark.parametrize("frac", [0.002, 0.05])
 @pytest.mark.parametrize("pbc,search", [(0, 1), (0, 2), (1, 1), (1, 2)])
-def test_find_neighbors_particles_outside_their_leaf_boxes(pbc, search):
-    """Arrays that do not belong to the tree: 5 % of the particles are moved by up to a search radius AFTER keys, tree
-    and layout were built, so they lie outside the box of their leaf.  The reference still finds such a particle only
+def test_find_neighbors_particles_outside_their_leaf_boxes(pbc, search, frac):
+    """Arrays that do not belong to the tree: a fraction of the particles is moved by up to a search radius AFTER keys,
+    tree and layout were built, so they lie outside the box of their leaf (0.2 %: the group-steered search runs and
+    takes its exact route on the marked leaves; 5 %: more than one leaf in 32 is marked, it declines and the per-lane
+    search runs instead).  The reference still finds such a particle only
     from targets whose own walk enters its leaf (findneighbors.hpp:108-146), which no longer follows from the
     distance alone.  Both searches (1 = per-lane walks, 2 = group-steered with its stray-leaf preparation, forced) must
     return the reference's lists; the unperturbed case on the same tree is checked too."""
@@ -615,7 +618,7 @@ def test_find_neighbors_particles_outside_their_leaf_boxes(pbc, search):
         for moved in (False, True):
             xs, ys, zs = x.copy(), y.copy(), z.copy()
             if moved:
-                pick = rng.random(n) < 0.05
+                pick = rng.random(n) < frac
                 for a in (xs, ys, zs):
                     a[pick] += (rng.random(int(pick.sum())) - 0.5) * 4.0 * h[0]
                     np.clip(a, lim[0] + 1e-9, lim[1] - 1e-9, out=a)
