@@ -189,6 +189,8 @@ struct DomainBase
     virtual int reapplySync(const void* const* before, void* const* after, const int* elemBytes, int numArrays,
                             cudaStream_t s)                                                                  = 0;
     virtual int replayInfo(uint64_t* info) const                                                             = 0;
+    //! Domain::setHaloFactor (domain/domain.hpp:365): enlarges the halo search radius of the following syncs
+    float haloFactor_{1.0f};
     int keyBytes{0}, realBytes{0};
 };
 
@@ -998,8 +1000,9 @@ public:
         CSB_CHECK(cudaMemsetAsync(layout_.p + lastNode, 0, sizeof(uint32_t), s));
         CSB_TRY(scanTmp_.resize(scanTempBytes(cnt + 1), s));
         CSB_TRY(exclusiveScanU32(layout_.p + firstNode, layout_.p + firstNode, cnt + 1, scanTmp_.p, s));
-        CSB_TRY((computeBoundingBoxes<T, T>(sx_.p, sy_.p, sz_.p, sh_.p, layout_.p, firstNode, lastNode, T(2),
-                                            searchCenters_.p, searchSizes_.p, s)));
+        // Th(2 * searchExtFact) with a float factor (octree_focus_mpi.hpp:542)
+        CSB_TRY((computeBoundingBoxes<T, T>(sx_.p, sy_.p, sz_.p, sh_.p, layout_.p, firstNode, lastNode,
+                                            T(2 * haloFactor_), searchCenters_.p, searchSizes_.p, s)));
         CSB_CHECK(cudaMemsetAsync(macs_.p, 0, size_t(fTree_.numNodes), s));
         return findHalos<K, T>(fTree_.prefixes.p, fTree_.childOffsets.p, fTree_.parents.p, geoCenters_.p, geoSizes_.p,
                                fLeaves_.p, searchCenters_.p, searchSizes_.p, focusLim_, bnd_, firstNode, lastNode,
@@ -1904,6 +1907,13 @@ int cs_domain_reapply_sync(cs_domain_t* d, const void* const* before, void* cons
 {
     CSB_REQUIRE(d != nullptr, "null domain");
     return csb::impl(d)->reapplySync(before, after, elemBytes, numArrays, cudaStream_t(stream));
+}
+
+int cs_domain_set_halo_factor(cs_domain_t* d, float factor)
+{
+    CSB_REQUIRE(d != nullptr && factor > 0, "cs_domain_set_halo_factor: null domain or non-positive factor");
+    csb::impl(d)->haloFactor_ = factor;
+    return 0;
 }
 
 int cs_domain_replay_info(const cs_domain_t* d, uint64_t* info4)

@@ -481,6 +481,10 @@ class Domain:
             _check(lib().cs_domain_exchange_halos(C.c_void_p(self.handle), ptrs, sizes, C.c_int(n), _stream()),
                    "cs_domain_exchange_halos")
 
+    def set_halo_factor(self, factor):
+        """Domain::setHaloFactor"""
+        _check(lib().cs_domain_set_halo_factor(C.c_void_p(self.handle), C.c_float(factor)), "cs_domain_set_halo_factor")
+
     def reapply_sync(self, *fields):
         """Domain::reapplySync: fields are device tensors in the particle order the last sync() consumed; returns new
         tensors with n_particles_with_halos rows whose assigned rows [start_index, end_index) hold the fields of the

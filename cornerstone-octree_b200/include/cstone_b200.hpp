@@ -297,6 +297,9 @@ public:
         return info[0];
     }
 
+    //! setHaloFactor domain.hpp:365
+    void setHaloFactor(float factor) { csCheck(cs_domain_set_halo_factor(d_, factor), "Domain::setHaloFactor"); }
+
     cs_domain_t* handle() { return d_; }
 
 private:

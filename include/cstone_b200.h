@@ -335,6 +335,9 @@ int cs_domain_exchange_halos(cs_domain_t* d, void* const* arrays, const int* ele
 int cs_domain_reapply_sync(cs_domain_t* d, const void* const* before, void* const* after, const int* elemBytes,
                            int numArrays, void* stream);
 int cs_domain_replay_info(const cs_domain_t* d, uint64_t* info4);
+/* Domain::setHaloFactor (domain/domain.hpp:365): the halo search boxes of the following syncs use factor * 2h instead of
+ * 2h (a deeper ghost layer for trees that are reused over several steps); multi-rank domains only, default 1 */
+int cs_domain_set_halo_factor(cs_domain_t* d, float factor);
 /* forget all tree state so that the next cs_domain_sync behaves like the first call on a new Domain (device buffers
  * are kept; used by bench.py to time cold syncs without re-allocating) */
 int cs_domain_reset(cs_domain_t* d, void* stream);

@@ -223,6 +223,10 @@ struct RankOut
 
 std::vector<RankOut> g_out;
 
+//! halo search radius factor of the Domains built by the drivers below (Domain::setHaloFactor)
+static float g_haloFactor = 1.0f;
+extern "C" void ref_set_halo_factor(float f) { g_haloFactor = f; }
+
 template<class KeyType, class T>
 void domainRank(int rank,
                 int P,
@@ -245,6 +249,7 @@ void domainRank(int rank,
 
     Domain<KeyType, T> domain(execution::cpu, rank, P, bucket, bucketFocus, theta, MPI_COMM_WORLD,
                               makeBox<T>(lim, bnd));
+    domain.setHaloFactor(g_haloFactor); // Domain::setHaloFactor (domain/domain.hpp:365); 1 unless ref_set_halo_factor
     std::vector<T> x(x0, x0 + n), y(y0, y0 + n), z(z0, z0 + n), h(h0, h0 + n);
     std::vector<KeyType> keys(n);
     std::vector<T> s1, s2;

@@ -2,13 +2,14 @@
 communicator (cs_comm_create_local), all on cuda:0, and are compared rank by rank with the UNMODIFIED reference run
 with P ranks (oracle/_ref, thread-backed MPI stand-in).  The same C++ code runs over NCCL with one process per GPU
 (bench.py --gpus N)."""
+import ctypes as C
 import threading
 
 import numpy as np
 import pytest
 import torch
 
-from _libs import key_of, real_of, ref, ref_domain_run
+from _libs import key_of, real_of, ref, ref_domain_run, ref_lib
 from _util import const_h, gaussian_particles, uniform_particles
 
 pytestmark = pytest.mark.gpu
@@ -353,3 +354,50 @@ def test_reapply_sync_needs_a_sync_to_replay():
     with pytest.raises(RuntimeError):
         dom.reapply_sync(torch.zeros(4, device=DEV))
     dom.close()
+
+
+@pytest.mark.skipif(ref() is None, reason="needs oracle/_ref (built where /root/reference exists)")
+@pytest.mark.parametrize("combo,P,pbc,factor", [("u64d", 3, 0, 1.5), ("u64f", 2, 1, 2.0)])
+def test_halo_factor_matches_reference(combo, P, pbc, factor):
+    """Domain::setHaloFactor (domain.hpp:365): the halo search boxes are built with factor * 2h
+    (octree_focus_mpi.hpp:542), so more leaves are flagged and more halo particles arrive.  Start/end/size, halo flags,
+    layout and the complete arrays with halos equal the reference's run with the same factor - and differ from the run
+    with factor 1."""
+    n_per = 5000
+    n = n_per * P
+    x, y, z, lim = make_particles(combo, n, "uniform", 17)
+    T = real_of(combo)
+    h = const_h(n, 40, T, 1.0)
+    bnd = (pbc, pbc, pbc)
+    offsets = [n_per * r for r in range(P + 1)]
+    base = ref_domain_run(combo, P, 64, 8, 0.5, lim, bnd, x, y, z, h, offsets, num_syncs=2)
+    ref_lib().ref_set_halo_factor(C.c_float(factor))
+    try:
+        want = ref_domain_run(combo, P, 64, 8, 0.5, lim, bnd, x, y, z, h, offsets, num_syncs=2)
+    finally:
+        ref_lib().ref_set_halo_factor(C.c_float(1.0))
+    assert any(want[r]["keys"].size > base[r]["keys"].size for r in range(P)), "the factor must deepen the halo layer"
+    world = capi().LocalWorld(P)
+
+    def rank_body(r):
+        c = capi()
+        comm = world.comm(r)
+        dom = c.Domain(r, P, 64, 8, 0.5, lim, bnd, key=key_of(combo), real=combo[-1], device=DEV, comm=comm)
+        dom.set_halo_factor(factor)
+        sl = slice(offsets[r], offsets[r + 1])
+        to = lambda a: torch.from_numpy(np.ascontiguousarray(a[sl])).to(DEV)  # noqa: E731
+        dom.sync(to(x), to(y), to(z), to(h))
+        dom.sync()
+        out = {k: dom.field(k).cpu().numpy() for k in ("keys", "x", "y", "z", "h", "layout", "halo_flags")}
+        out["start"], out["end"], out["size"] = dom.start_index, dom.end_index, dom.n_particles_with_halos
+        dom.close()
+        comm.close()
+        return out
+
+    got = run_ranks(P, rank_body, world)
+    for r in range(P):
+        w, g = want[r], got[r]
+        assert (g["start"], g["end"], g["size"]) == (w["start"], w["end"], w["keys"].size), r
+        assert np.array_equal(g["halo_flags"], w["flags"]), (r, "halo flags")
+        for k in ("layout", "keys", "x", "y", "z", "h"):
+            assert np.array_equal(g[k], w[k]), (r, k)
