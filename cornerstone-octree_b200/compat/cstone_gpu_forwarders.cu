@@ -35,6 +35,7 @@
 #include "cstone/focus/source_center_gpu.h"
 #include "cstone/primitives/primitives_gpu.h"
 #include "cstone/sfc/sfc_gpu.h"
+#include "cstone/traversal/groups_gpu.h"
 #include "cstone/traversal/collisions_gpu.h"
 #include "cstone/tree/csarray_gpu.h"
 #include "cstone/tree/octree_gpu.h"
@@ -928,5 +929,64 @@ template void computeGeoCentersGpu(execution::Gpu, const uint64_t*, TreeNodeInde
                                    const Box<float>&);
 template void computeGeoCentersGpu(execution::Gpu, const uint64_t*, TreeNodeIndex, Vec3<double>*, Vec3<double>*,
                                    const Box<double>&);
+
+/* ------------------------------------------------------------------------------------------------ groups_gpu.h */
+
+void computeFixedGroups(execution::Gpu exec, LocalIndex first, LocalIndex last, unsigned groupSize,
+                        GroupData<execution::Gpu>& groups)
+{
+    LocalIndex numBodies = last - first;
+    LocalIndex numGroups = (numBodies + groupSize - 1) / groupSize;
+    groups.data.resize(numGroups + 1);
+    csCheck(cs_compute_fixed_groups(first, last, groupSize, rawPtr(groups.data), cudaStream_t(exec)),
+            "computeFixedGroups");
+    groups.firstBody  = first;
+    groups.lastBody   = last;
+    groups.numGroups  = numGroups;
+    groups.groupStart = rawPtr(groups.data);
+    groups.groupEnd   = rawPtr(groups.data) + 1;
+}
+
+template<class Tc, class T, class KeyType>
+void computeGroupSplits(execution::Gpu exec, LocalIndex first, LocalIndex last, const Tc* x, const Tc* y, const Tc* z,
+                        const T* h, const KeyType* leaves, TreeNodeIndex numLeaves, const LocalIndex* layout,
+                        const Box<Tc> box, unsigned groupSize, float tolFactor,
+                        DeviceVector<LocalIndex>& /*numSplitsPerGroup: scratch of the reference, not needed*/,
+                        DeviceVector<LocalIndex>& groups)
+{
+    static_assert(sizeof(KeyType) == 8, "computeGroupSplits is instantiated for 64-bit keys only (groups_gpu.cu:148-150)");
+    if (groupSize != 32 && groupSize != 64) { throw std::runtime_error("Unsupported spatial group size\n"); }
+    BoxArgs<Tc> b(box);
+    uint32_t numGroups = 0;
+    const uint64_t* lv = reinterpret_cast<const uint64_t*>(leaves);
+    if constexpr (std::is_same_v<Tc, double> && std::is_same_v<T, double>)
+    {
+        csCheck(cs_group_splits_begin_dd(first, last, x, y, z, h, lv, numLeaves, layout, b.lim, b.bnd, groupSize,
+                                         tolFactor, &numGroups, cudaStream_t(exec)),
+                "computeGroupSplits");
+    }
+    else if constexpr (std::is_same_v<Tc, double>)
+    {
+        csCheck(cs_group_splits_begin_df(first, last, x, y, z, h, lv, numLeaves, layout, b.lim, b.bnd, groupSize,
+                                         tolFactor, &numGroups, cudaStream_t(exec)),
+                "computeGroupSplits");
+    }
+    else
+    {
+        csCheck(cs_group_splits_begin_ff(first, last, x, y, z, h, lv, numLeaves, layout, b.lim, b.bnd, groupSize,
+                                         tolFactor, &numGroups, cudaStream_t(exec)),
+                "computeGroupSplits");
+    }
+    groups.resize(numGroups + 1);
+    csCheck(cs_group_splits_finish(first, last, groupSize, rawPtr(groups), cudaStream_t(exec)), "computeGroupSplits");
+}
+
+#define CS_GROUP_SPLITS(Tc, T, KeyType)                                                                                \
+    template void computeGroupSplits(execution::Gpu, LocalIndex, LocalIndex, const Tc*, const Tc*, const Tc*, const T*,  \
+                                     const KeyType*, TreeNodeIndex, const LocalIndex*, const Box<Tc>, unsigned, float,  \
+                                     DeviceVector<LocalIndex>&, DeviceVector<LocalIndex>&);
+CS_GROUP_SPLITS(double, double, uint64_t)
+CS_GROUP_SPLITS(double, float, uint64_t)
+CS_GROUP_SPLITS(float, float, uint64_t)
 
 } // namespace cstone

@@ -344,6 +344,31 @@ int cs_domain_reset(cs_domain_t* d, void* stream);
 /* device -> host copy of the synchronised arrays (NULL pointers are skipped); asynchronous on the stream */
 int cs_domain_download(cs_domain_t* d, void* x, void* y, void* z, void* h, void* keys, void* stream);
 
+/* ---- target particle groups (traversal/groups_gpu.h:33-78) ----
+ * computeFixedGroups(exec, first, last, groupSize, GroupData&): groups[g] = first + g * groupSize for the
+ * ceil((last-first)/groupSize) groups, groups[numGroups] = last. */
+int cs_compute_fixed_groups(uint32_t first, uint32_t last, uint32_t groupSize, uint32_t* groups, void* stream);
+/* computeGroupSplits<Tc, T, KeyType>(exec, first, last, x, y, z, h, leaves, numLeaves, layout, box, groupSize, tolFactor,
+ * numSplitsPerGroup, groups) for (double,double), (double,float), (float,float) and 64-bit keys: fixed groups of 32 or
+ * 64 particles are cut wherever consecutive particles are further apart than min(tolFactor * cbrt(smallest leaf volume
+ * of the group), 2h / minExtent) in unit-box coordinates.  In two calls, because the number of groups is only known on
+ * the device: _begin returns it in *numGroupsOut (host memory; synchronises the stream, like the reference's read-back),
+ * _finish then writes the numGroups + 1 ascending boundaries (groups[0] = first, groups[numGroups] = last).  Both calls
+ * must come from the same host thread on the same stream, with nothing of this library in between on that stream. */
+int cs_group_splits_begin_dd(uint32_t first, uint32_t last, const double* x, const double* y, const double* z,
+                             const double* h, const uint64_t* leaves, int numLeaves, const uint32_t* layout,
+                             const double* lim, const int* bnd, uint32_t groupSize, float tolFactor,
+                             uint32_t* numGroupsOut, void* stream);
+int cs_group_splits_begin_df(uint32_t first, uint32_t last, const double* x, const double* y, const double* z,
+                             const float* h, const uint64_t* leaves, int numLeaves, const uint32_t* layout,
+                             const double* lim, const int* bnd, uint32_t groupSize, float tolFactor,
+                             uint32_t* numGroupsOut, void* stream);
+int cs_group_splits_begin_ff(uint32_t first, uint32_t last, const float* x, const float* y, const float* z,
+                             const float* h, const uint64_t* leaves, int numLeaves, const uint32_t* layout,
+                             const double* lim, const int* bnd, uint32_t groupSize, float tolFactor,
+                             uint32_t* numGroupsOut, void* stream);
+int cs_group_splits_finish(uint32_t first, uint32_t last, uint32_t groupSize, uint32_t* groups, void* stream);
+
 /* tuning hook: L2 fetch granularity hint in bytes (32, 64, 128) for the current device */
 int cs_set_l2_fetch_granularity(int bytes);
 

@@ -306,3 +306,39 @@ def test_sort_by_key_and_gather_vectors(kt):
     probe = values.copy()
     probe[2:12] = values[2:][order]                           # gatherCpu(ordering, values + 2, probe + 2)
     assert probe.tolist() == [-2, -1, 0, 2, 4, 6, 8, 1, 3, 5, 7, 9, 10, 11]
+
+
+def test_groups_oracle_reference_known_answers():
+    """oracle/groups_oracle.py pinned to test/unit_cuda/traversal/groups.cu: fixed groups :27-41, the two split counts
+    {2, 2} and {64, 60} of groupSplitsKernel :252-271, and the boundaries (4, 6, 68, 75, 128) of computeGroupSplits
+    :273-281"""
+    import os
+    import sys
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "oracle"))
+    import groups_oracle
+
+    assert groups_oracle.fixed_groups(4, 34, 8).tolist() == [4, 12, 20, 28, 34]
+    r = np.uint64(1) << np.uint64(63)
+    o = r >> np.uint64(3)
+    leaves = [np.uint64(0), o, np.uint64(2) * o]
+    leaves += [np.uint64(2) * o + np.uint64(k) * (o >> np.uint64(3)) for k in range(1, 8)]
+    leaves += [np.uint64(k) * o for k in range(3, 8)] + [r]
+    leaves = np.array(leaves, dtype=np.uint64)
+    first, last, G = 4, 128, 64
+    counts = np.array([4, 1, 8, 8, 8, 8, 31, 8, 8, 8, 16, 16, 16, 0, 0], dtype=np.uint32)
+    layout = np.concatenate([[0], np.cumsum(counts)]).astype(np.uint32)
+    x = np.arange(last, dtype=np.float64)
+    y, z = x.copy(), x.copy()
+    h = np.full(last, float(last))
+    h[first + G + 6] = 0.99 * np.sqrt(3.0) / 2
+    h[first + G + 7] = 1.01 * np.sqrt(3.0) / 2
+    for a in (x, y, z):
+        a[5] -= 0.01
+    lim = (0, last, 0, last, 0, last)
+    dist_crit = np.cbrt(float(last) ** 3 / 64)
+    loose = groups_oracle.group_splits(first, last, x, y, z, h, leaves, layout, lim, G,
+                                       np.float32(np.sqrt(3.0) / dist_crit * 1.01))
+    assert loose.tolist() == [4, 6, 68, 75, 128]
+    tight = groups_oracle.group_splits(first, last, x, y, z, h, leaves, layout, lim, G,
+                                       np.float32(np.sqrt(3.0) / dist_crit * 0.99))
+    assert int((tight < 68).sum()) == 64 and int((tight >= 68).sum()) - 1 == 60
