@@ -145,6 +145,6 @@ int findNeighbors(const T* x, const T* y, const T* z, const Th* h, uint32_t firs
                   const int* bnd, int numLeaves, const int* childOffsets, const int* parents,
                   const int* internalToLeaf, const uint32_t* layout, const T* centers, const T* sizes, uint32_t ngmax,
                   uint32_t* neighbors,
-                  uint32_t* neighborsCount, cudaStream_t s);
+                  uint32_t* neighborsCount, cudaStream_t s, float searchExtFactor = 1.0f);
 
 } // namespace csb

@@ -155,6 +155,7 @@ struct Target
 {
     T x, y, z;
     T radiusSq;
+    T cellRadiusSq; // radiusSq * searchExtFactor^2: the radius of the continuation test (findneighbors.hpp:100)
     bool usePbc;
 };
 
@@ -185,7 +186,7 @@ __device__ inline bool cellOverlap(const Target<T>& t, const T* __restrict__ cen
     dy *= T(0.5);
     dz *= T(0.5);
     T n2 = dx * dx + (dy * dy + dz * dz);
-    return n2 < t.radiusSq; // cellRadiusSq == radiusSq for searchExtFactor == 1
+    return n2 < t.cellRadiusSq;
 }
 
 /* ---- certified single-precision pre-filter for double-precision searches ----
@@ -361,13 +362,14 @@ struct alignas(16) LaneWalkShared
  *  fold is needed is decided per warp (any lane whose search sphere leaves the box); such warps run the reference
  *  expressions directly on broadcast loads, lanes that do not need the fold select the unfolded difference exactly as
  *  the reference picks per particle (findneighbors.hpp:104-106,150-151).  Interior warps take the staged path. */
-template<class T, bool PBC, bool FOLD, class Th>
+template<class T, bool PBC, bool FOLD, class Th, bool EXT>
 __device__ __forceinline__ void warpSearchLanes(LaneWalkShared& sh, const uint2 grp, const T* __restrict__ x, const T* __restrict__ y,
                            const T* __restrict__ z, const Th* __restrict__ h, uint32_t first, const Box<T>& box,
                            const int* __restrict__ childOffsets, const int* __restrict__ parents,
                            const int* __restrict__ internalToLeaf, const uint32_t* __restrict__ layout,
                            const T* __restrict__ centers, const T* __restrict__ sizes, uint32_t ngmax,
-                           uint32_t* __restrict__ neighbors, uint32_t* __restrict__ neighborsCount)
+                           uint32_t* __restrict__ neighbors, uint32_t* __restrict__ neighborsCount,
+                           float searchExt)
 {
     constexpr bool Filt   = sizeof(T) == 8;
     const unsigned lane   = threadIdx.x & 31;
@@ -381,7 +383,11 @@ __device__ __forceinline__ void warpSearchLanes(LaneWalkShared& sh, const uint2 
     t.z        = z[i];
     // Th may be float with double coordinates: the radius is formed in Th and promoted (findneighbors.hpp:89-99)
     const Th hi = h[i];
-    t.radiusSq  = T(Th(4.0) * hi * hi);
+    {
+        const Th radiusSq = Th(4.0) * hi * hi;
+        t.radiusSq        = T(radiusSq);
+        t.cellRadiusSq    = EXT ? T(radiusSq * searchExt * searchExt) : t.radiusSq; // findneighbors.hpp:99-100
+    }
     {
         bool anyPbc = box.pbc(0) || box.pbc(1) || box.pbc(2);
         T s         = T(2) * T(hi);
@@ -415,6 +421,20 @@ __device__ __forceinline__ void warpSearchLanes(LaneWalkShared& sh, const uint2 
         r2a = -1.0f;
         r2b = __int_as_float(0x7f800000);
     }
+    // the same for the radius of the continuation tests (differs from the search radius only if searchExtFactor != 1)
+    const float c2f    = EXT ? float(t.cellRadiusSq) : r2f;
+    const float c2max  = EXT ? warpMaxF(c2f) : r2max;
+    const float c2bMax = EXT ? ((c2max > 1e-30f) ? c2max * BAND_KB : __int_as_float(0x7f800000)) : r2bMax;
+    float c2a = r2a, c2b = r2b;
+    if (EXT)
+    {
+        c2a = c2f * BAND_KA, c2b = c2f * BAND_KB;
+        if (!(c2f > 1e-30f))
+        {
+            c2a = -1.0f;
+            c2b = __int_as_float(0x7f800000);
+        }
+    }
     // every staged (un-culled) candidate has |coordinate| <= 1.01 (DwT + sqrt(r2max)), see the cull test
     /* Warps that touch a periodic boundary: if the group and its search spheres are small against the box (they always
      * are unless the box holds only a few leaves), every lane sees the same periodic image of a nearby particle or node,
@@ -425,7 +445,7 @@ __device__ __forceinline__ void warpSearchLanes(LaneWalkShared& sh, const uint2 
     bool foldOk = Filt && FOLD;
     if (PBC && Filt && FOLD)
     {
-        const float reach = 1.01f * sqrtf(r2max);
+        const float reach = 1.01f * sqrtf(fmaxf(r2max, c2max));
         const float ext[3] = {hix - lox, hiy - loy, hiz - loz};
 #pragma unroll
         for (int d = 0; d < 3; ++d)
@@ -679,7 +699,7 @@ __device__ __forceinline__ void warpSearchLanes(LaneWalkShared& sh, const uint2 
             float ex = fmaxf(fmaxf(lox - (gc.x + gs.x), (gc.x - gs.x) - hix), 0.0f);
             float ey = fmaxf(fmaxf(loy - (gc.y + gs.y), (gc.y - gs.y) - hiy), 0.0f);
             float ez = fmaxf(fmaxf(loz - (gc.z + gs.z), (gc.z - gs.z) - hiz), 0.0f);
-            reach    = !(fmaf(ex, ex, fmaf(ey, ey, ez * ez)) > fmaf(gs.w, BAND_SB, r2bMax));
+            reach    = !(fmaf(ex, ex, fmaf(ey, ey, ez * ez)) > fmaf(gs.w, BAND_SB, c2bMax));
         }
         const unsigned reachable = __ballot_sync(0xffffffffu, reach);
         if (mine)
@@ -697,8 +717,8 @@ __device__ __forceinline__ void warpSearchLanes(LaneWalkShared& sh, const uint2 
                     float dy = fmaxf(fabsf(gc.y - tyf) - gs.y, 0.0f);
                     float dz = fmaxf(fabsf(gc.z - tzf) - gs.z, 0.0f);
                     float s2 = fmaf(dx, dx, fmaf(dy, dy, dz * dz));
-                    pass     = s2 < fmaf(-gs.w, BAND_SA, r2a);
-                    if (!pass && !(s2 > fmaf(gs.w, BAND_SB, r2b)))
+                    pass     = s2 < fmaf(-gs.w, BAND_SA, c2a);
+                    if (!pass && !(s2 > fmaf(gs.w, BAND_SB, c2b)))
                     {
                         pass = cellOverlap<PBC>(t, centers, sizes, child0 + c, box);
                     }
@@ -715,7 +735,7 @@ __device__ __forceinline__ void warpSearchLanes(LaneWalkShared& sh, const uint2 
                     dx *= T(0.5);
                     dy *= T(0.5);
                     dz *= T(0.5);
-                    pass = dx * dx + (dy * dy + dz * dz) < t.radiusSq;
+                    pass = dx * dx + (dy * dy + dz * dz) < t.cellRadiusSq;
                 }
                 bits |= uint32_t(pass) << c;
             }
@@ -775,7 +795,7 @@ __device__ __forceinline__ void warpSearchLanes(LaneWalkShared& sh, const uint2 
  *  but appended to `deferred` ([0] = count, then group numbers); this launch then runs the code of the open-box search
  *  for all interior groups, and a second launch (groupList = deferred) handles the few boundary groups with the
  *  periodic code, whose register footprint would otherwise slow down every warp. */
-template<class T, bool PBC, bool FOLD, bool DEFER, class Th, bool PERSIST>
+template<class T, bool PBC, bool FOLD, bool DEFER, class Th, bool PERSIST, bool EXT>
 __global__ void __launch_bounds__(NB_THREADS) findNeighborsKernel(const T* __restrict__ x,
                                                                   const T* __restrict__ y,
                                                                   const T* __restrict__ z,
@@ -797,7 +817,8 @@ __global__ void __launch_bounds__(NB_THREADS) findNeighborsKernel(const T* __res
                                                                   uint32_t* __restrict__ neighborsCount,
                                                                   const uint32_t* __restrict__ numBad,
                                                                   uint32_t badLimit,
-                                                                  uint32_t* __restrict__ workCounter)
+                                                                  uint32_t* __restrict__ workCounter,
+                                                                  float searchExt)
 {
     // the group-steered search runs instead (it was launched before this kernel with the same criterion)
     if (numBad != nullptr && *numBad <= badLimit) { return; }
@@ -833,8 +854,8 @@ __global__ void __launch_bounds__(NB_THREADS) findNeighborsKernel(const T* __res
                 break;
             }
         }
-        warpSearchLanes<T, PBC, FOLD, Th>(shAll[threadIdx.x >> 5], grp, x, y, z, h, first, box, childOffsets, parents, internalToLeaf,
-                                 layout, centers, sizes, ngmax, neighbors, neighborsCount);
+        warpSearchLanes<T, PBC, FOLD, Th, EXT>(shAll[threadIdx.x >> 5], grp, x, y, z, h, first, box, childOffsets, parents, internalToLeaf,
+                                 layout, centers, sizes, ngmax, neighbors, neighborsCount, searchExt);
         if (!PERSIST) { break; }
         __syncwarp();
     }
@@ -954,7 +975,8 @@ __device__ __noinline__ void warpSearchDirect(uint8_t (*mask)[32], const uint2 g
                                               const int* __restrict__ childOffsets, const int* __restrict__ parents,
                                               const uint2* __restrict__ nodeRange, const T* __restrict__ centers,
                                               const T* __restrict__ sizes, uint32_t ngmax,
-                                              uint32_t* __restrict__ neighbors, uint32_t* __restrict__ neighborsCount)
+                                              uint32_t* __restrict__ neighbors, uint32_t* __restrict__ neighborsCount,
+                                              float searchExt)
 {
     const unsigned lane = threadIdx.x & 31;
     const bool valid    = grp.x + lane < grp.y;
@@ -964,7 +986,11 @@ __device__ __noinline__ void warpSearchDirect(uint8_t (*mask)[32], const uint2 g
     t.y         = y[i];
     t.z         = z[i];
     const Th hi = h[i];
-    t.radiusSq  = T(Th(4.0) * hi * hi);
+    {
+        const Th radiusSq = Th(4.0) * hi * hi;
+        t.radiusSq        = T(radiusSq);
+        t.cellRadiusSq    = searchExt == 1.0f ? t.radiusSq : T(radiusSq * searchExt * searchExt);
+    }
     {
         T s         = T(2) * T(hi);
         bool inside = (t.x - s >= box.lim[0]) && (t.y - s >= box.lim[2]) && (t.z - s >= box.lim[4]) &&
@@ -1081,13 +1107,14 @@ __device__ __noinline__ void warpSearchDirect(uint8_t (*mask)[32], const uint2 g
  *  node, the fold is applied ONCE while staging (to the coordinates relative to the group origin) and everything above
  *  runs unchanged (the exact route uses the reference's folded expressions); otherwise, and for float searches (whose
  *  staged operands must be the reference's), the warp runs warpSearchDirect. */
-template<class T, bool PBC, bool FOLD, class Th>
+template<class T, bool PBC, bool FOLD, class Th, bool EXT>
 __device__ __forceinline__ void warpSearchGroup(GroupWalkShared& sh, const uint2 grp, const T* __restrict__ x, const T* __restrict__ y,
                            const T* __restrict__ z, const Th* __restrict__ h, uint32_t first, const Box<T>& box,
                            const int* __restrict__ childOffsets, const int* __restrict__ parents,
                            const uint2* __restrict__ nodeRange, float tau0, uint32_t coarse,
                            const T* __restrict__ centers, const T* __restrict__ sizes, uint32_t ngmax,
-                           uint32_t* __restrict__ neighbors, uint32_t* __restrict__ neighborsCount)
+                           uint32_t* __restrict__ neighbors, uint32_t* __restrict__ neighborsCount,
+                           float searchExt)
 {
     constexpr bool Filt   = sizeof(T) == 8;
     const unsigned lane   = threadIdx.x & 31;
@@ -1101,7 +1128,11 @@ __device__ __forceinline__ void warpSearchGroup(GroupWalkShared& sh, const uint2
     t.z        = z[i];
     // Th may be float with double coordinates: the radius is formed in Th and promoted (findneighbors.hpp:89-99)
     const Th hi = h[i];
-    t.radiusSq  = T(Th(4.0) * hi * hi);
+    {
+        const Th radiusSq = Th(4.0) * hi * hi;
+        t.radiusSq        = T(radiusSq);
+        t.cellRadiusSq    = EXT ? T(radiusSq * searchExt * searchExt) : t.radiusSq; // findneighbors.hpp:99-100
+    }
     {
         bool anyPbc = box.pbc(0) || box.pbc(1) || box.pbc(2);
         T s         = T(2) * T(hi);
@@ -1128,11 +1159,15 @@ __device__ __forceinline__ void warpSearchGroup(GroupWalkShared& sh, const uint2
                             fmaxf(fabsf(loz), fabsf(hiz)));
     const float r2max = warpMaxF(r2f);
     const float r2bMax = (r2max > 1e-30f) ? r2max * BAND_KB : __int_as_float(0x7f800000);
+    // the radius of the continuation tests (differs from the search radius only if searchExtFactor != 1)
+    const float c2f    = EXT ? float(t.cellRadiusSq) : r2f;
+    const float c2max  = EXT ? warpMaxF(c2f) : r2max;
+    const float c2bMax = EXT ? ((c2max > 1e-30f) ? c2max * BAND_KB : __int_as_float(0x7f800000)) : r2bMax;
 
     bool foldOk = Filt && FOLD;
     if (PBC && Filt && FOLD)
     {
-        const float reach = 1.01f * sqrtf(r2max);
+        const float reach = 1.01f * sqrtf(fmaxf(r2max, c2max));
         const float ext[3] = {hix - lox, hiy - loy, hiz - loz};
 #pragma unroll
         for (int d = 0; d < 3; ++d)
@@ -1141,7 +1176,7 @@ __device__ __forceinline__ void warpSearchGroup(GroupWalkShared& sh, const uint2
     if (PBC && warpPbc && !foldOk)
     {
         warpSearchDirect<T, Th>(reinterpret_cast<uint8_t(*)[32]>(&sh), grp, x, y, z, h, first, box, childOffsets,
-                                parents, nodeRange, centers, sizes, ngmax, neighbors, neighborsCount);
+                                parents, nodeRange, centers, sizes, ngmax, neighbors, neighborsCount, searchExt);
         return;
     }
     const bool foldPbc = warpPbc;
@@ -1157,20 +1192,26 @@ __device__ __forceinline__ void warpSearchGroup(GroupWalkShared& sh, const uint2
     T sureT     = T(0); // exact route, T = double: d2 < sureT * r2 implies that the walk reaches the leaf
     if (active)
     {
-        const float mu    = fmaf(4.0f * tau0, rsqrtf(r2f), 0x1p-18f);
-        const bool normal = r2f > 1e-30f && mu < 0x1p-6f; // false for NaN
-        if (normal) { sureT = T(1.0f - 2.0f * mu); }
+        // the walk is certain to reach the leaf if the particle is inside BOTH radii by the margin mu
+        const float own2f = EXT ? fminf(r2f, c2f) : r2f;
+        const float mu    = fmaf(4.0f * tau0, rsqrtf(own2f), 0x1p-18f);
+        const bool normal = own2f > 1e-30f && mu < 0x1p-6f; // false for NaN
+        if (normal)
+        {
+            sureT = T(1.0f - 2.0f * mu);
+            if (EXT && t.cellRadiusSq < t.radiusSq) { sureT *= t.cellRadiusSq / t.radiusSq * T(1.0 - 0x1p-20); }
+        }
         if (Filt)
         {
             thrHi = r2f > 1e-30f ? fmaf(Epair, BAND_SB, r2f * BAND_KB) : __int_as_float(0x7f800000);
-            if (normal) { thrLo = fmaf(-Epair, BAND_SA, (r2f * (1.0f - mu)) * BAND_KA); }
+            if (normal) { thrLo = fmaf(-Epair, BAND_SA, (own2f * (1.0f - mu)) * BAND_KA); }
         }
         else
         {
             // the staged values are the reference's operands and s is the reference's expression: s < r2f decides the
             // distance, the largest float below r2f is the upper end of the shell
             if (r2f > 0.0f) { thrHi = __uint_as_float(__float_as_uint(r2f) - 1u); } // +inf -> FLT_MAX; NaN -> stays -1
-            if (normal) { thrLo = (r2f * (1.0f - mu)) * (1.0f - 0x1p-22f); }
+            if (normal) { thrLo = (own2f * (1.0f - mu)) * (1.0f - 0x1p-22f); }
         }
         if (!(thrHi >= 0.0f)) { thrHi = -1.0f; }
     }
@@ -1406,7 +1447,7 @@ __device__ __forceinline__ void warpSearchGroup(GroupWalkShared& sh, const uint2
             float ex = fmaxf(fmaxf(lox - (cx + gx), (cx - gx) - hix), 0.0f);
             float ey = fmaxf(fmaxf(loy - (cy + gy), (cy - gy) - hiy), 0.0f);
             float ez = fmaxf(fmaxf(loz - (cz + gz), (cz - gz) - hiz), 0.0f);
-            reach    = large || !(fmaf(ex, ex, fmaf(ey, ey, ez * ez)) > fmaf(E, BAND_SB, r2bMax));
+            reach    = large || !(fmaf(ex, ex, fmaf(ey, ey, ez * ez)) > fmaf(E, BAND_SB, c2bMax));
         }
         return __ballot_sync(0xffffffffu, reach) & 0xffu;
     };
@@ -1495,7 +1536,7 @@ __device__ __forceinline__ void warpSearchGroup(GroupWalkShared& sh, const uint2
 
 //! the kernel of the group-steered search; DEFER as in findNeighborsKernel.  Does nothing if too many leaves hold stray
 //! particles (trees over 32-bit keys: the key grid is coarse against the search radius), findNeighborsKernel runs then
-template<class T, bool PBC, bool FOLD, bool DEFER, class Th, bool PERSIST>
+template<class T, bool PBC, bool FOLD, bool DEFER, class Th, bool PERSIST, bool EXT>
 __global__ void __launch_bounds__(NB_THREADS, 8) findNeighborsGroupKernel(const T* __restrict__ x,
                                                                   const T* __restrict__ y,
                                                                   const T* __restrict__ z,
@@ -1518,7 +1559,8 @@ __global__ void __launch_bounds__(NB_THREADS, 8) findNeighborsGroupKernel(const 
                                                                   uint32_t* __restrict__ neighborsCount,
                                                                   const uint32_t* __restrict__ numBad,
                                                                   uint32_t badLimit,
-                                                                  uint32_t* __restrict__ workCounter)
+                                                                  uint32_t* __restrict__ workCounter,
+                                                                  float searchExt)
 {
     if (*numBad > badLimit) { return; }
     __shared__ GroupWalkShared shAll[NB_THREADS / 32];
@@ -1553,8 +1595,8 @@ __global__ void __launch_bounds__(NB_THREADS, 8) findNeighborsGroupKernel(const 
                 break;
             }
         }
-        warpSearchGroup<T, PBC, FOLD, Th>(shAll[threadIdx.x >> 5], grp, x, y, z, h, first, box, childOffsets, parents, nodeRange,
-                                     tau0, coarse, centers, sizes, ngmax, neighbors, neighborsCount);
+        warpSearchGroup<T, PBC, FOLD, Th, EXT>(shAll[threadIdx.x >> 5], grp, x, y, z, h, first, box, childOffsets, parents, nodeRange,
+                                     tau0, coarse, centers, sizes, ngmax, neighbors, neighborsCount, searchExt);
         if (!PERSIST) { break; }
         __syncwarp();
     }
@@ -1587,11 +1629,11 @@ __global__ void classifyGroupsKernel(const T* __restrict__ x, const T* __restric
 
 } // namespace
 
-template<class T, class Th>
-int findNeighbors(const T* x, const T* y, const T* z, const Th* h, uint32_t first, uint32_t last, const double* lim,
-                  const int* bnd, int numLeaves, const int* childOffsets, const int* parents, const int* internalToLeaf,
-                  const uint32_t* layout, const T* centers, const T* sizes, uint32_t ngmax, uint32_t* neighbors,
-                  uint32_t* neighborsCount, cudaStream_t s)
+template<class T, class Th, bool EXT>
+int findNeighborsImpl(const T* x, const T* y, const T* z, const Th* h, uint32_t first, uint32_t last, const double* lim,
+                      const int* bnd, int numLeaves, const int* childOffsets, const int* parents,
+                      const int* internalToLeaf, const uint32_t* layout, const T* centers, const T* sizes,
+                      uint32_t ngmax, uint32_t* neighbors, uint32_t* neighborsCount, cudaStream_t s, float searchExt)
 {
     CSB_REQUIRE(last >= first, "invalid particle range");
     CSB_REQUIRE(numLeaves >= 1, "empty tree");
@@ -1677,22 +1719,22 @@ int findNeighbors(const T* x, const T* y, const T* z, const Th* h, uint32_t firs
             const uint32_t coarse = uint32_t(std::min(std::max(12.0 * meanLeaf, double(NB_COARSE)), 256.0));
             if (!pbc)
             {
-                auto k0 = findNeighborsGroupKernel<T, false, false, false, Th, false>;
+                auto k0 = findNeighborsGroupKernel<T, false, false, false, Th, false, EXT>;
                 k0<<<fullGrid, NB_THREADS, 0, s>>>(
                     x, y, z, h, first, groups, groupOffsets + numLeaves, nullptr, nullptr, box, childOffsets, parents,
-                    nodeRange, tau0, coarse, centers, sizes, ngmax, neighbors, neighborsCount, numBad, badLimit, work + 0);
+                    nodeRange, tau0, coarse, centers, sizes, ngmax, neighbors, neighborsCount, numBad, badLimit, work + 0, searchExt);
             }
             else
             {
-                auto k0 = findNeighborsGroupKernel<T, false, false, true, Th, false>;
+                auto k0 = findNeighborsGroupKernel<T, false, false, true, Th, false, EXT>;
                 k0<<<fullGrid, NB_THREADS, 0, s>>>(
                     x, y, z, h, first, groups, groupOffsets + numLeaves, nullptr, deferred, box, childOffsets, parents,
-                    nodeRange, tau0, coarse, centers, sizes, ngmax, neighbors, neighborsCount, numBad, badLimit, work + 0);
+                    nodeRange, tau0, coarse, centers, sizes, ngmax, neighbors, neighborsCount, numBad, badLimit, work + 0, searchExt);
                 CSB_LAUNCH_CHECK();
-                auto k1 = findNeighborsGroupKernel<T, true, true, false, Th, false>;
+                auto k1 = findNeighborsGroupKernel<T, true, true, false, Th, false, EXT>;
                 k1<<<fullGrid, NB_THREADS, 0, s>>>(
                     x, y, z, h, first, groups, groupOffsets + numLeaves, deferred, nullptr, box, childOffsets, parents,
-                    nodeRange, tau0, coarse, centers, sizes, ngmax, neighbors, neighborsCount, numBad, badLimit, work + 1);
+                    nodeRange, tau0, coarse, centers, sizes, ngmax, neighbors, neighborsCount, numBad, badLimit, work + 1, searchExt);
             }
             CSB_LAUNCH_CHECK();
         }
@@ -1706,22 +1748,23 @@ int findNeighbors(const T* x, const T* y, const T* z, const Th* h, uint32_t firs
     {
         kernel<<<persist ? waveOf(kernel) : fullGrid, NB_THREADS, 0, s>>>(
             x, y, z, h, first, groups, groupOffsets + numLeaves, groupList, deferredOut, box, childOffsets, parents,
-            internalToLeaf, layout, centers, sizes, ngmax, neighbors, neighborsCount, numBadGate, badLimit, counter);
+            internalToLeaf, layout, centers, sizes, ngmax, neighbors, neighborsCount, numBadGate, badLimit, counter,
+            searchExt);
     };
     const bool gated = numBadGate != nullptr;
     if (!pbc)
     {
         if (gated || sizeof(T) == 8)
         {
-            launchLanes(findNeighborsKernel<T, false, false, false, Th, true>, true, nullptr, nullptr, work + 2);
+            launchLanes(findNeighborsKernel<T, false, false, false, Th, true, EXT>, true, nullptr, nullptr, work + 2);
         }
-        else { launchLanes(findNeighborsKernel<T, false, false, false, Th, false>, false, nullptr, nullptr, work + 2); }
+        else { launchLanes(findNeighborsKernel<T, false, false, false, Th, false, EXT>, false, nullptr, nullptr, work + 2); }
     }
     else if (gated)
     {
-        launchLanes(findNeighborsKernel<T, false, false, true, Th, true>, true, nullptr, deferred, work + 2);
+        launchLanes(findNeighborsKernel<T, false, false, true, Th, true, EXT>, true, nullptr, deferred, work + 2);
         CSB_LAUNCH_CHECK();
-        launchLanes(findNeighborsKernel<T, true, true, false, Th, true>, true, deferred, nullptr, work + 3);
+        launchLanes(findNeighborsKernel<T, true, true, false, Th, true, EXT>, true, deferred, nullptr, work + 3);
     }
     else if (sizeof(T) == 8)
     {
@@ -1730,33 +1773,54 @@ int findNeighbors(const T* x, const T* y, const T* z, const Th* h, uint32_t firs
         classifyGroupsKernel<T, Th><<<fullGrid, NB_THREADS, 0, s>>>(x, y, z, h, groups, groupOffsets + numLeaves, box,
                                                                     interior, deferred);
         CSB_LAUNCH_CHECK();
-        launchLanes(findNeighborsKernel<T, false, false, false, Th, true>, true, interior, nullptr, work + 2);
+        launchLanes(findNeighborsKernel<T, false, false, false, Th, true, EXT>, true, interior, nullptr, work + 2);
         CSB_LAUNCH_CHECK();
-        launchLanes(findNeighborsKernel<T, true, true, false, Th, false>, false, deferred, nullptr, work + 3);
+        launchLanes(findNeighborsKernel<T, true, true, false, Th, false, EXT>, false, deferred, nullptr, work + 3);
     }
     else
     {
         // interior groups with the open-box code, then the groups at the periodic boundaries
-        launchLanes(findNeighborsKernel<T, false, false, true, Th, false>, false, nullptr, deferred, work + 2);
+        launchLanes(findNeighborsKernel<T, false, false, true, Th, false, EXT>, false, nullptr, deferred, work + 2);
         CSB_LAUNCH_CHECK();
-        launchLanes(findNeighborsKernel<T, true, true, false, Th, false>, false, deferred, nullptr, work + 3);
+        launchLanes(findNeighborsKernel<T, true, true, false, Th, false, EXT>, false, deferred, nullptr, work + 3);
     }
     CSB_LAUNCH_CHECK();
     return 0;
 }
 
+/*! findNeighbors (findneighbors.hpp:156-177).  searchExtFactor (OctreeNsView, tree/octree.hpp:279-282): the
+ *  continuation tests of the walk use the radius 2h * searchExtFactor (findneighbors.hpp:100), acceptance stays at 2h;
+ *  the code for factors other than 1 is a separate instantiation so that the default path is unchanged */
+template<class T, class Th>
+int findNeighbors(const T* x, const T* y, const T* z, const Th* h, uint32_t first, uint32_t last, const double* lim,
+                  const int* bnd, int numLeaves, const int* childOffsets, const int* parents, const int* internalToLeaf,
+                  const uint32_t* layout, const T* centers, const T* sizes, uint32_t ngmax, uint32_t* neighbors,
+                  uint32_t* neighborsCount, cudaStream_t s, float searchExtFactor)
+{
+    CSB_REQUIRE(searchExtFactor > 0, "findNeighbors: searchExtFactor must be positive");
+    if (searchExtFactor == 1.0f)
+    {
+        return findNeighborsImpl<T, Th, false>(x, y, z, h, first, last, lim, bnd, numLeaves, childOffsets, parents,
+                                               internalToLeaf, layout, centers, sizes, ngmax, neighbors, neighborsCount,
+                                               s, 1.0f);
+    }
+    return findNeighborsImpl<T, Th, true>(x, y, z, h, first, last, lim, bnd, numLeaves, childOffsets, parents,
+                                          internalToLeaf, layout, centers, sizes, ngmax, neighbors, neighborsCount, s,
+                                          searchExtFactor);
+}
+
 template int findNeighbors<float, float>(const float*, const float*, const float*, const float*, uint32_t, uint32_t,
                                          const double*, const int*, int, const int*, const int*, const int*,
                                          const uint32_t*, const float*, const float*, uint32_t, uint32_t*, uint32_t*,
-                                         cudaStream_t);
+                                         cudaStream_t, float);
 template int findNeighbors<double, double>(const double*, const double*, const double*, const double*, uint32_t,
                                            uint32_t, const double*, const int*, int, const int*, const int*, const int*,
                                            const uint32_t*, const double*, const double*, uint32_t, uint32_t*,
-                                           uint32_t*, cudaStream_t);
+                                           uint32_t*, cudaStream_t, float);
 template int findNeighbors<double, float>(const double*, const double*, const double*, const float*, uint32_t, uint32_t,
                                           const double*, const int*, int, const int*, const int*, const int*,
                                           const uint32_t*, const double*, const double*, uint32_t, uint32_t*, uint32_t*,
-                                          cudaStream_t);
+                                          cudaStream_t, float);
 
 } // namespace csb
 
@@ -1770,7 +1834,7 @@ int cs_find_neighbors_f(const float* x, const float* y, const float* z, const fl
 {
     return csb::findNeighbors<float, float>(x, y, z, h, firstId, lastId, lim, bnd, numLeaves, childOffsets, parents,
                                      internalToLeaf, layout, centers, sizes, ngmax, neighbors, neighborsCount,
-                                     cudaStream_t(stream));
+                                     cudaStream_t(stream), 1.0f);
 }
 
 int cs_find_neighbors_d(const double* x, const double* y, const double* z, const double* h, uint32_t firstId,
@@ -1781,7 +1845,7 @@ int cs_find_neighbors_d(const double* x, const double* y, const double* z, const
 {
     return csb::findNeighbors<double, double>(x, y, z, h, firstId, lastId, lim, bnd, numLeaves, childOffsets, parents,
                                       internalToLeaf, layout, centers, sizes, ngmax, neighbors, neighborsCount,
-                                      cudaStream_t(stream));
+                                      cudaStream_t(stream), 1.0f);
 }
 
 /* double coordinates, float smoothing lengths (Th != Tc, findneighbors.hpp:89-99): radiusSq is formed in float */
@@ -1793,7 +1857,42 @@ int cs_find_neighbors_df(const double* x, const double* y, const double* z, cons
 {
     return csb::findNeighbors<double, float>(x, y, z, h, firstId, lastId, lim, bnd, numLeaves, childOffsets, parents,
                                              internalToLeaf, layout, centers, sizes, ngmax, neighbors, neighborsCount,
-                                             cudaStream_t(stream));
+                                             cudaStream_t(stream), 1.0f);
+}
+
+/* the same with OctreeNsView::searchExtFactor (tree/octree.hpp:279-282): node continuation tests with the radius
+ * 2h * searchExtFactor (findneighbors.hpp:100) */
+int cs_find_neighbors_ext_f(const float* x, const float* y, const float* z, const float* h, uint32_t firstId,
+                            uint32_t lastId, const double* lim, const int* bnd, int numLeaves, const int* childOffsets,
+                            const int* parents, const int* internalToLeaf, const uint32_t* layout, const float* centers,
+                            const float* sizes, uint32_t ngmax, uint32_t* neighbors, uint32_t* neighborsCount,
+                            float searchExtFactor, void* stream)
+{
+    return csb::findNeighbors<float, float>(x, y, z, h, firstId, lastId, lim, bnd, numLeaves, childOffsets, parents,
+                                            internalToLeaf, layout, centers, sizes, ngmax, neighbors, neighborsCount,
+                                            cudaStream_t(stream), searchExtFactor);
+}
+
+int cs_find_neighbors_ext_d(const double* x, const double* y, const double* z, const double* h, uint32_t firstId,
+                            uint32_t lastId, const double* lim, const int* bnd, int numLeaves, const int* childOffsets,
+                            const int* parents, const int* internalToLeaf, const uint32_t* layout,
+                            const double* centers, const double* sizes, uint32_t ngmax, uint32_t* neighbors,
+                            uint32_t* neighborsCount, float searchExtFactor, void* stream)
+{
+    return csb::findNeighbors<double, double>(x, y, z, h, firstId, lastId, lim, bnd, numLeaves, childOffsets, parents,
+                                              internalToLeaf, layout, centers, sizes, ngmax, neighbors, neighborsCount,
+                                              cudaStream_t(stream), searchExtFactor);
+}
+
+int cs_find_neighbors_ext_df(const double* x, const double* y, const double* z, const float* h, uint32_t firstId,
+                             uint32_t lastId, const double* lim, const int* bnd, int numLeaves, const int* childOffsets,
+                             const int* parents, const int* internalToLeaf, const uint32_t* layout,
+                             const double* centers, const double* sizes, uint32_t ngmax, uint32_t* neighbors,
+                             uint32_t* neighborsCount, float searchExtFactor, void* stream)
+{
+    return csb::findNeighbors<double, float>(x, y, z, h, firstId, lastId, lim, bnd, numLeaves, childOffsets, parents,
+                                             internalToLeaf, layout, centers, sizes, ngmax, neighbors, neighborsCount,
+                                             cudaStream_t(stream), searchExtFactor);
 }
 
 } // extern "C"

@@ -278,7 +278,7 @@ def find_halos(tree, centers, sizes, sc, ss, lim, bnd, first, last, flags=None):
 
 # ---------------------------------------------------------------- neighbours
 def find_neighbors(x, y, z, h, first, last, lim, bnd, tree, layout, centers, sizes, ngmax, neighbors=None,
-                   counts=None):
+                   counts=None, search_ext_factor=1.0):
     sfx = real_suffix(x)
     nloc = last - first
     if neighbors is None:
@@ -286,6 +286,13 @@ def find_neighbors(x, y, z, h, first, last, lim, bnd, tree, layout, centers, siz
     if counts is None:
         counts = torch.zeros(nloc, dtype=torch.uint32, device=x.device)
     lim_a, bnd_a = _box(lim, bnd)
+    if search_ext_factor != 1.0:  # OctreeNsView::searchExtFactor
+        f = getattr(lib(), "cs_find_neighbors_ext_" + sfx)
+        _check(f(_ptr(x), _ptr(y), _ptr(z), _ptr(h), C.c_uint32(first), C.c_uint32(last), lim_a, bnd_a,
+                 C.c_int(tree.num_leaves), _ptr(tree.child_offsets), _ptr(tree.parents), _ptr(tree.internal_to_leaf),
+                 _ptr(layout), _ptr(centers), _ptr(sizes), C.c_uint32(ngmax), _ptr(neighbors), _ptr(counts),
+                 C.c_float(search_ext_factor), _stream()), "cs_find_neighbors_ext_" + sfx)
+        return neighbors, counts
     f = getattr(lib(), "cs_find_neighbors_" + sfx)
     _check(f(_ptr(x), _ptr(y), _ptr(z), _ptr(h), C.c_uint32(first), C.c_uint32(last), lim_a, bnd_a,
              C.c_int(tree.num_leaves), _ptr(tree.child_offsets), _ptr(tree.parents), _ptr(tree.internal_to_leaf), _ptr(layout), _ptr(centers),

@@ -192,6 +192,23 @@ int cs_find_neighbors_df(const double* x, const double* y, const double* z, cons
                          const int* parents, const int* internalToLeaf, const uint32_t* layout, const double* centers,
                          const double* sizes, uint32_t ngmax, uint32_t* neighbors, uint32_t* neighborsCount,
                          void* stream);
+/* the same with OctreeNsView::searchExtFactor (tree/octree.hpp:279-282): the continuation tests of the walk use the
+ * radius 2h * searchExtFactor (findneighbors.hpp:100), acceptance stays at 2h */
+int cs_find_neighbors_ext_f(const float* x, const float* y, const float* z, const float* h, uint32_t firstId,
+                            uint32_t lastId, const double* lim, const int* bnd, int numLeaves, const int* childOffsets,
+                            const int* parents, const int* internalToLeaf, const uint32_t* layout, const float* centers,
+                            const float* sizes, uint32_t ngmax, uint32_t* neighbors, uint32_t* neighborsCount,
+                            float searchExtFactor, void* stream);
+int cs_find_neighbors_ext_d(const double* x, const double* y, const double* z, const double* h, uint32_t firstId,
+                            uint32_t lastId, const double* lim, const int* bnd, int numLeaves, const int* childOffsets,
+                            const int* parents, const int* internalToLeaf, const uint32_t* layout,
+                            const double* centers, const double* sizes, uint32_t ngmax, uint32_t* neighbors,
+                            uint32_t* neighborsCount, float searchExtFactor, void* stream);
+int cs_find_neighbors_ext_df(const double* x, const double* y, const double* z, const float* h, uint32_t firstId,
+                             uint32_t lastId, const double* lim, const int* bnd, int numLeaves, const int* childOffsets,
+                             const int* parents, const int* internalToLeaf, const uint32_t* layout,
+                             const double* centers, const double* sizes, uint32_t ngmax, uint32_t* neighbors,
+                             uint32_t* neighborsCount, float searchExtFactor, void* stream);
 
 /* ---- focus-tree (LET) rebalance decisions: focus/rebalance_gpu.h:27-79 ----
  * rebalanceDecisionEssentialGpu: nodeOps[numNodes] from node counts and MAC flags of the fully linked tree, for the focus

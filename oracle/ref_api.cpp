@@ -117,6 +117,10 @@ void fpCenters(const KeyType* prefixes, size_t n, T* centers, T* sizes, const do
                            reinterpret_cast<Vec3<T>*>(sizes), box);
 }
 
+//! OctreeNsView::searchExtFactor of the standalone neighbour searches below
+static float g_searchExtFactor = 1.0f;
+extern "C" void ref_set_search_ext_factor(float f) { g_searchExtFactor = f; }
+
 template<class KeyType, class T, class Th = T>
 void neighbors(const T* x,
                const T* y,
@@ -155,6 +159,7 @@ void neighbors(const T* x,
                                   layout,
                                   reinterpret_cast<const Vec3<T>*>(centers),
                                   reinterpret_cast<const Vec3<T>*>(sizes)};
+    view.searchExtFactor = g_searchExtFactor; // tree/octree.hpp:279-282; 1 unless ref_set_search_ext_factor
     findNeighbors(x, y, z, h, first, last, box, view, ngmax, nb, nc);
 }
 

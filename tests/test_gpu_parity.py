@@ -636,3 +636,63 @@ def test_find_neighbors_particles_outside_their_leaf_boxes(pbc, search, frac):
             assert nc_o.max() > 10
     finally:
         capi().tuning_set(2, 0)
+
+
+@pytest.mark.skipif(ref() is None, reason="needs oracle/_ref")
+@pytest.mark.parametrize("combo,factor,pbc,search", [("u64d", 1.3, 0, 1), ("u64d", 1.3, 1, 2), ("u64d", 0.8, 0, 2),
+                                                     ("u64d", 0.8, 1, 1), ("u32f", 1.5, 0, 1), ("u32f", 0.7, 1, 1),
+                                                     ("u64f", 2.0, 0, 1)])
+def test_find_neighbors_search_ext_factor(combo, factor, pbc, search):
+    """OctreeNsView::searchExtFactor (tree/octree.hpp:279-282): the continuation tests of the walk use the radius
+    2h * factor, acceptance stays at 2h (findneighbors.hpp:99-146).  Particles are moved off their leaves so that the
+    factor changes the result (a larger factor reaches strays that factor 1 misses, a smaller one drops neighbours
+    whose leaf box is no longer entered); lists and counts equal the reference's for both searches."""
+    import ctypes as C
+
+    from _libs import ref_lib
+    kt, T = key_of(combo), real_of(combo)
+    n, ngmax = 30000, 128
+    keys, (x, y, z), lim, _ = sorted_keys(combo, n, "uniform")
+    bnd = (pbc, pbc, pbc)
+    lo, co = oracle().compute_octree(kt, keys, 16)
+    to = oracle().build_octree(kt, lo)
+    cen_o, siz_o = oracle().node_fp_centers(combo, to["prefixes"], lim, bnd)
+    layout_o = np.zeros(lo.size, dtype=np.uint32)
+    layout_o[1:] = np.cumsum(co)
+    h = const_h(n, 40, T, 8.0)
+    rng = np.random.default_rng(21)
+    pick = rng.random(n) < 0.01
+    for a in (x, y, z):
+        a[pick] += ((rng.random(int(pick.sum())) - 0.5) * 2.0 * h[0]).astype(T)
+        np.clip(a, T(lim[0] + 1e-3), T(lim[1] - 1e-3), out=a)
+    P = lambda a: a.ctypes.data_as(C.c_void_p)  # noqa: E731
+    lim_a, bnd_a = np.array(lim, dtype=np.float64), np.array(bnd, dtype=np.int32)
+
+    def reference(f):
+        nb_o, nc_o = np.zeros(n * ngmax, dtype=np.uint32), np.zeros(n, dtype=np.uint32)
+        ref_lib().ref_set_search_ext_factor(C.c_float(f))
+        try:
+            getattr(ref_lib(), "ref_find_neighbors_" + combo)(
+                P(x), P(y), P(z), P(h), C.c_uint(0), C.c_uint(n), P(lim_a), P(bnd_a), C.c_int(to["numLeaves"]),
+                C.c_int(to["numNodes"]), P(to["prefixes"]), P(to["childOffsets"]), P(to["parents"]),
+                P(to["internalToLeaf"]), P(to["leafToInternal"]), P(to["levelRange"]), P(lo), P(layout_o), P(cen_o),
+                P(siz_o), C.c_uint(ngmax), P(nb_o), P(nc_o))
+        finally:
+            ref_lib().ref_set_search_ext_factor(C.c_float(1.0))
+        return nb_o, nc_o
+
+    nb_o, nc_o = reference(factor)
+    _, nc_1 = reference(1.0)
+    assert not np.array_equal(nc_o, nc_1), "the factor must change the result for the test to mean anything"
+    tree = capi().Octree(dev(lo))
+    cen, siz = capi().compute_geo_centers(tree.prefixes, torch.float32 if T == np.float32 else torch.float64, lim, bnd)
+    capi().tuning_set(2, search)
+    try:
+        nb, nc = capi().find_neighbors(dev(x), dev(y), dev(z), dev(h), 0, n, lim, bnd, tree, dev(layout_o), cen, siz,
+                                       ngmax, search_ext_factor=factor)
+        torch.cuda.synchronize()
+    finally:
+        capi().tuning_set(2, 0)
+    assert np.array_equal(host(nc), nc_o), int((host(nc) != nc_o).sum())
+    m = np.arange(ngmax)[None, :] < np.minimum(nc_o, ngmax)[:, None]
+    assert np.array_equal(host(nb).reshape(n, ngmax)[m], nb_o.reshape(n, ngmax)[m])
