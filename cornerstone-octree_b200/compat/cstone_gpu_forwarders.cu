@@ -36,6 +36,7 @@
 #include "cstone/primitives/primitives_gpu.h"
 #include "cstone/sfc/sfc_gpu.h"
 #include "cstone/traversal/groups_gpu.h"
+#include "cstone/halos/gather_halos_gpu.h"
 #include "cstone/traversal/collisions_gpu.h"
 #include "cstone/tree/csarray_gpu.h"
 #include "cstone/tree/octree_gpu.h"
@@ -988,5 +989,84 @@ void computeGroupSplits(execution::Gpu exec, LocalIndex first, LocalIndex last, 
 CS_GROUP_SPLITS(double, double, uint64_t)
 CS_GROUP_SPLITS(double, float, uint64_t)
 CS_GROUP_SPLITS(float, float, uint64_t)
+
+/* ------------------------------------------------------------------------------------------------ collisions_gpu.h
+ *                                                                                                  (markMacsGpu) */
+
+template<class T, class KeyType>
+void markMacsGpu(execution::Gpu exec, const KeyType* prefixes, const TreeNodeIndex* childOffsets,
+                 const TreeNodeIndex* parents, const Vec4<T>* centers, const Box<T>& box, const KeyType* focusNodes,
+                 TreeNodeIndex numFocusNodes, bool limitSource, uint8_t* markings)
+{
+    BoxArgs<T> b(box);
+    const T* c4 = reinterpret_cast<const T*>(centers);
+    if constexpr (sizeof(KeyType) == 4)
+    {
+        csCheck(cs_mark_macs_u32f(reinterpret_cast<const uint32_t*>(prefixes), childOffsets, parents, c4, b.lim, b.bnd,
+                                  reinterpret_cast<const uint32_t*>(focusNodes), numFocusNodes, int(limitSource),
+                                  markings, cudaStream_t(exec)),
+                "markMacsGpu");
+    }
+    else if constexpr (std::is_same_v<T, float>)
+    {
+        csCheck(cs_mark_macs_u64f(reinterpret_cast<const uint64_t*>(prefixes), childOffsets, parents, c4, b.lim, b.bnd,
+                                  reinterpret_cast<const uint64_t*>(focusNodes), numFocusNodes, int(limitSource),
+                                  markings, cudaStream_t(exec)),
+                "markMacsGpu");
+    }
+    else
+    {
+        csCheck(cs_mark_macs_u64d(reinterpret_cast<const uint64_t*>(prefixes), childOffsets, parents, c4, b.lim, b.bnd,
+                                  reinterpret_cast<const uint64_t*>(focusNodes), numFocusNodes, int(limitSource),
+                                  markings, cudaStream_t(exec)),
+                "markMacsGpu");
+    }
+}
+
+#define CS_MARK_MACS(T, KeyType)                                                                                       \
+    template void markMacsGpu(execution::Gpu, const KeyType*, const TreeNodeIndex*, const TreeNodeIndex*,              \
+                              const Vec4<T>*, const Box<T>&, const KeyType*, TreeNodeIndex, bool, uint8_t*);
+CS_MARK_MACS(float, uint32_t)
+CS_MARK_MACS(float, uint64_t)
+CS_MARK_MACS(double, uint64_t)
+
+/* ------------------------------------------------------------------------------------------------ gather_halos_gpu.h */
+
+template<class T, class IndexType>
+void gatherRanges(execution::Gpu exec, const IndexType* rangeScan, const IndexType* rangeOffsets, int numRanges,
+                  const T* src, T* buffer, size_t bufferSize)
+{
+    static_assert(sizeof(IndexType) == 4 && sizeof(T) % 4 == 0);
+    csCheck(cs_gather_ranges(reinterpret_cast<const uint32_t*>(rangeScan), reinterpret_cast<const uint32_t*>(rangeOffsets),
+                             numRanges, src, buffer, bufferSize, int(sizeof(T)), cudaStream_t(exec)),
+            "gatherRanges");
+}
+
+#define CS_GATHER_RANGES(T, IndexType)                                                                                 \
+    template void gatherRanges(execution::Gpu, const IndexType*, const IndexType*, int, const T*, T*, size_t);
+CS_GATHER_RANGES(int, unsigned)
+using ArrF1 = util::array<float, 1>;
+using ArrF2 = util::array<float, 2>;
+CS_GATHER_RANGES(ArrF1, unsigned)
+CS_GATHER_RANGES(ArrF2, unsigned)
+CS_GATHER_RANGES(ArrF3, unsigned)
+CS_GATHER_RANGES(ArrF4, unsigned)
+
+/* ------------------------------------------------------------------------------------------------ primitives_gpu.h
+ *                                                                                                  (minMax) */
+
+template<class T>
+std::tuple<T, T> minMax(execution::Gpu exec, const T* first, const T* last)
+{
+    T mn{}, mx{};
+    const size_t n = size_t(last - first);
+    if constexpr (std::is_same_v<T, double>) { csCheck(cs_min_max_d(first, n, &mn, &mx, cudaStream_t(exec)), "minMax"); }
+    else if constexpr (std::is_same_v<T, float>) { csCheck(cs_min_max_f(first, n, &mn, &mx, cudaStream_t(exec)), "minMax"); }
+    else { csCheck(cs_min_max_u32(first, n, &mn, &mx, cudaStream_t(exec)), "minMax"); }
+    return std::make_tuple(mn, mx);
+}
+template std::tuple<double, double> minMax(execution::Gpu, const double*, const double*);
+template std::tuple<float, float> minMax(execution::Gpu, const float*, const float*);
+template std::tuple<unsigned, unsigned> minMax(execution::Gpu, const unsigned*, const unsigned*);
 
 } // namespace cstone

@@ -4,6 +4,9 @@
  * focus/inject.hpp:50-84), with the arithmetic of focus/rebalance.hpp:31-252 and sfc/common.hpp:360-470.
  * Integer-only: bit-exact.
  */
+#include <algorithm>
+#include <vector>
+
 #include "common.cuh"
 #include "cstone_b200.h"
 #include "focus.cuh"
@@ -498,6 +501,29 @@ template int gatherVec3<float>(const int*, int, const float*, float*, cudaStream
 template int gatherVec3<double>(const int*, int, const double*, double*, cudaStream_t);
 template int minMaxPartials<float>(const float*, size_t, float*, int, cudaStream_t);
 template int minMaxPartials<double>(const double*, size_t, double*, int, cudaStream_t);
+template int minMaxPartials<uint32_t>(const uint32_t*, size_t, uint32_t*, int, cudaStream_t);
+
+//! minMax (primitives/primitives_gpu.h:72-73): per-block partial results, folded on the host
+template<class T>
+int minMaxHost(const T* first, size_t n, T* minOut, T* maxOut, cudaStream_t s)
+{
+    CSB_REQUIRE(n > 0, "minMax of an empty range");
+    const int blocks = int(std::min<size_t>(592, (n + 511) / 512));
+    CSB_SCRATCH(partial, T*, s, SCRATCH_A, size_t(2) * blocks * sizeof(T));
+    if (int e = minMaxPartials<T>(first, n, partial, blocks, s)) { return e; }
+    std::vector<T> host(size_t(2) * blocks);
+    CSB_CHECK(cudaMemcpyAsync(host.data(), partial, host.size() * sizeof(T), cudaMemcpyDeviceToHost, s));
+    CSB_CHECK(cudaStreamSynchronize(s));
+    T mn = host[0], mx = host[1];
+    for (int b = 1; b < blocks; ++b)
+    {
+        mn = std::min(mn, host[2 * b]);
+        mx = std::max(mx, host[2 * b + 1]);
+    }
+    *minOut = mn;
+    *maxOut = mx;
+    return 0;
+}
 
 } // namespace csb
 
@@ -563,5 +589,20 @@ int cs_fill_sfc_gaps_u64(const uint64_t* tree, int numNodes, const int* nodeOps,
 CSB_FOCUS_ABI(u32, uint32_t)
 CSB_FOCUS_ABI(u64, uint64_t)
 #undef CSB_FOCUS_ABI
+
+/* minMax (primitives/primitives_gpu.h:72-73): smallest and largest element of a device array, returned on the host
+ * (synchronises the stream like the reference) */
+int cs_min_max_f(const float* first, size_t n, float* minOut, float* maxOut, void* stream)
+{
+    return csb::minMaxHost<float>(first, n, minOut, maxOut, cudaStream_t(stream));
+}
+int cs_min_max_d(const double* first, size_t n, double* minOut, double* maxOut, void* stream)
+{
+    return csb::minMaxHost<double>(first, n, minOut, maxOut, cudaStream_t(stream));
+}
+int cs_min_max_u32(const uint32_t* first, size_t n, uint32_t* minOut, uint32_t* maxOut, void* stream)
+{
+    return csb::minMaxHost<uint32_t>(first, n, minOut, maxOut, cudaStream_t(stream));
+}
 
 } // extern "C"

@@ -52,7 +52,7 @@ template<class T>
 int minMacCenters(const T* geoCenters, const T* geoSizes, int numNodes, float invThetaEff, T* centers4, cudaStream_t s);
 template<class K, class T>
 int markMacs(const K* prefixes, const int* childOffsets, const int* parents, const T* centers4, const double* lim,
-             const int* bnd, const K* focusNodes, int numFocusNodes, uint8_t* markings, cudaStream_t s);
+             const int* bnd, const K* focusNodes, int numFocusNodes, uint8_t* markings, cudaStream_t s, bool limitSource = false);
 template<class K>
 int rangeCount(const K* gLeaves, int numGlobalLeaves, const uint64_t* gCountScan, const K* fLeaves, const int* idx,
                int numIdx, uint32_t* leafCounts, cudaStream_t s);

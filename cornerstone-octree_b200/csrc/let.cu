@@ -48,6 +48,7 @@ __global__ void __launch_bounds__(128) markMacsKernel(const K* __restrict__ pref
                                                       Box<T> box,
                                                       const K* __restrict__ focusNodes,
                                                       int numFocusNodes,
+                                                      bool limitSource,
                                                       uint8_t* markings)
 {
     __shared__ unsigned char hilbertTables[hilbertTableBytes];
@@ -65,6 +66,8 @@ __global__ void __launch_bounds__(128) markMacsKernel(const K* __restrict__ pref
     const K a = focusNodes[leaf], b = focusNodes[leaf + 1];
 
     unsigned level      = treeLevel<K>(b - a);
+    // limitSource: sources deeper than one level above the target are neither marked nor entered (macs.hpp:221-222)
+    const int maxSourceLevel = limitSource ? max(int(level) - 1, 0) : int(KeyTraits<K>::maxLevel);
     unsigned cubeLength = unsigned(maxCoord) >> level;
     unsigned mask       = ~(cubeLength - 1);
     unsigned ix, iy, iz;
@@ -176,7 +179,7 @@ __global__ void __launch_bounds__(128) markMacsKernel(const K* __restrict__ pref
     constexpr T cullMargin = sizeof(T) == 8 ? T(1e-9) : T(1e-3);
 
     //! this lane's decisions for the 8 children starting at child0 (bit c: the lane's walk marks and enters child c)
-    auto testChildren = [&](int child0, bool mine) -> unsigned
+    auto testChildren = [&](int child0, bool mine, int sourceLevel) -> unsigned
     {
         __syncwarp();
         bool test = false;
@@ -206,7 +209,7 @@ __global__ void __launch_bounds__(128) markMacsKernel(const K* __restrict__ pref
         }
         const unsigned testMask = __ballot_sync(FULL, test);
         unsigned bits           = 0;
-        if (mine)
+        if (mine && sourceLevel <= maxSourceLevel)
         {
 #pragma unroll
             for (int c = 0; c < 8; ++c)
@@ -223,7 +226,7 @@ __global__ void __launch_bounds__(128) markMacsKernel(const K* __restrict__ pref
     if (base == 0) { return; }
 
     int depth     = 1;
-    unsigned lm   = testChildren(base, viol);
+    unsigned lm   = testChildren(base, viol, 1);
     unsigned wm   = __reduce_or_sync(FULL, lm);
     laneMask[warp][1][lane] = uint8_t(lm);
     if (lane < 8 && ((wm >> lane) & 1u) && !markings[base + lane]) { markings[base + lane] = 1; }
@@ -258,7 +261,7 @@ __global__ void __launch_bounds__(128) markMacsKernel(const K* __restrict__ pref
         const int child = g.child[c];
         ++depth;
         base = child;
-        lm   = testChildren(child, mine);
+        lm   = testChildren(child, mine, depth); // the children of a node at tree level depth - 1
         wm   = __reduce_or_sync(FULL, lm);
         laneMask[warp][depth][lane] = uint8_t(lm);
         if (lane < 8 && ((wm >> lane) & 1u) && !markings[base + lane]) { markings[base + lane] = 1; }
@@ -666,12 +669,12 @@ int minMacCenters(const T* geoCenters, const T* geoSizes, int numNodes, float in
 
 template<class K, class T>
 int markMacs(const K* prefixes, const int* childOffsets, const int* parents, const T* centers4, const double* lim,
-             const int* bnd, const K* focusNodes, int numFocusNodes, uint8_t* markings, cudaStream_t s)
+             const int* bnd, const K* focusNodes, int numFocusNodes, uint8_t* markings, cudaStream_t s, bool limitSource)
 {
     if (numFocusNodes <= 0) { return 0; }
     Box<T> box = makeBox<T>(lim, bnd);
     markMacsKernel<K, T><<<iceil(numFocusNodes, 128), 128, 0, s>>>(prefixes, childOffsets, parents, centers4, box,
-                                                                   focusNodes, numFocusNodes, markings);
+                                                                   focusNodes, numFocusNodes, limitSource, markings);
     CSB_LAUNCH_CHECK();
     return 0;
 }
@@ -747,11 +750,11 @@ int gatherRanges4(const uint32_t* rangeScan, const uint32_t* rangeStart, int num
 template int minMacCenters<float>(const float*, const float*, int, float, float*, cudaStream_t);
 template int minMacCenters<double>(const double*, const double*, int, float, double*, cudaStream_t);
 template int markMacs<uint32_t, float>(const uint32_t*, const int*, const int*, const float*, const double*, const int*,
-                                       const uint32_t*, int, uint8_t*, cudaStream_t);
+                                       const uint32_t*, int, uint8_t*, cudaStream_t, bool);
 template int markMacs<uint64_t, float>(const uint64_t*, const int*, const int*, const float*, const double*, const int*,
-                                       const uint64_t*, int, uint8_t*, cudaStream_t);
+                                       const uint64_t*, int, uint8_t*, cudaStream_t, bool);
 template int markMacs<uint64_t, double>(const uint64_t*, const int*, const int*, const double*, const double*,
-                                        const int*, const uint64_t*, int, uint8_t*, cudaStream_t);
+                                        const int*, const uint64_t*, int, uint8_t*, cudaStream_t, bool);
 template int rangeCount<uint32_t>(const uint32_t*, int, const uint64_t*, const uint32_t*, const int*, int, uint32_t*,
                                   cudaStream_t);
 template int rangeCount<uint64_t>(const uint64_t*, int, const uint64_t*, const uint64_t*, const int*, int, uint32_t*,
@@ -809,5 +812,42 @@ extern "C"
 CSB_EXTRACT_ABI(u32, uint32_t)
 CSB_EXTRACT_ABI(u64, uint64_t)
 #undef CSB_EXTRACT_ABI
+
+/* markMacsGpu (traversal/collisions_gpu.h:62-71, macs.hpp:185-229): markings[i] = 1 for every node of the linked tree
+ * that fails the MAC against one of the numFocusNodes leaves focusNodes[0..numFocusNodes] (and is not contained in
+ * their key range); centers4 = (x, y, z, mac^2) per node; limitSource: nodes deeper than one level above the target leaf
+ * are neither marked nor entered.  Marks are only set, never cleared. */
+int cs_mark_macs_u32f(const uint32_t* prefixes, const int* childOffsets, const int* parents, const float* centers4,
+                      const double* lim, const int* bnd, const uint32_t* focusNodes, int numFocusNodes, int limitSource,
+                      uint8_t* markings, void* stream)
+{
+    return csb::markMacs<uint32_t, float>(prefixes, childOffsets, parents, centers4, lim, bnd, focusNodes, numFocusNodes,
+                                          markings, cudaStream_t(stream), limitSource != 0);
+}
+int cs_mark_macs_u64f(const uint64_t* prefixes, const int* childOffsets, const int* parents, const float* centers4,
+                      const double* lim, const int* bnd, const uint64_t* focusNodes, int numFocusNodes, int limitSource,
+                      uint8_t* markings, void* stream)
+{
+    return csb::markMacs<uint64_t, float>(prefixes, childOffsets, parents, centers4, lim, bnd, focusNodes, numFocusNodes,
+                                          markings, cudaStream_t(stream), limitSource != 0);
+}
+int cs_mark_macs_u64d(const uint64_t* prefixes, const int* childOffsets, const int* parents, const double* centers4,
+                      const double* lim, const int* bnd, const uint64_t* focusNodes, int numFocusNodes, int limitSource,
+                      uint8_t* markings, void* stream)
+{
+    return csb::markMacs<uint64_t, double>(prefixes, childOffsets, parents, centers4, lim, bnd, focusNodes,
+                                           numFocusNodes, markings, cudaStream_t(stream), limitSource != 0);
+}
+
+/* gatherRanges (halos/gather_halos_gpu.h:23-30): buffer[rangeScan[r] + k] = src[rangeOffsets[r] + k] for the numRanges
+ * ranges whose lengths are the differences of rangeScan (the last one ends at bufferSize); elements of elemBytes bytes
+ * (a multiple of 4: int, util::array<float, 1..4>) */
+int cs_gather_ranges(const uint32_t* rangeScan, const uint32_t* rangeOffsets, int numRanges, const void* src,
+                     void* buffer, size_t bufferSize, int elemBytes, void* stream)
+{
+    CSB_REQUIRE(elemBytes > 0 && elemBytes % 4 == 0, "gatherRanges: element sizes must be positive multiples of 4 bytes");
+    return csb::gatherRangesWords(rangeScan, rangeOffsets, numRanges, uint32_t(bufferSize), elemBytes / 4, src, buffer,
+                                  cudaStream_t(stream));
+}
 
 } // extern "C"

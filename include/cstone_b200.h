@@ -361,6 +361,29 @@ int cs_domain_reset(cs_domain_t* d, void* stream);
 /* device -> host copy of the synchronised arrays (NULL pointers are skipped); asynchronous on the stream */
 int cs_domain_download(cs_domain_t* d, void* x, void* y, void* z, void* h, void* keys, void* stream);
 
+/* markMacsGpu (traversal/collisions_gpu.h:62-71, macs.hpp:185-229): markings[i] = 1 for every node of the linked tree that
+ * fails the MAC against one of the numFocusNodes leaves focusNodes[0..numFocusNodes] and is not contained in their key
+ * range; centers4 = (x, y, z, mac^2) per node; limitSource != 0: nodes deeper than one level above the target leaf are
+ * neither marked nor entered.  Marks are only set, never cleared. */
+int cs_mark_macs_u32f(const uint32_t* prefixes, const int* childOffsets, const int* parents, const float* centers4,
+                      const double* lim, const int* bnd, const uint32_t* focusNodes, int numFocusNodes, int limitSource,
+                      uint8_t* markings, void* stream);
+int cs_mark_macs_u64f(const uint64_t* prefixes, const int* childOffsets, const int* parents, const float* centers4,
+                      const double* lim, const int* bnd, const uint64_t* focusNodes, int numFocusNodes, int limitSource,
+                      uint8_t* markings, void* stream);
+int cs_mark_macs_u64d(const uint64_t* prefixes, const int* childOffsets, const int* parents, const double* centers4,
+                      const double* lim, const int* bnd, const uint64_t* focusNodes, int numFocusNodes, int limitSource,
+                      uint8_t* markings, void* stream);
+/* gatherRanges (halos/gather_halos_gpu.h:23-30): buffer[rangeScan[r] + k] = src[rangeOffsets[r] + k]; elements of
+ * elemBytes bytes (a multiple of 4: int, util::array<float, 1..4>) */
+int cs_gather_ranges(const uint32_t* rangeScan, const uint32_t* rangeOffsets, int numRanges, const void* src,
+                     void* buffer, size_t bufferSize, int elemBytes, void* stream);
+/* minMax (primitives/primitives_gpu.h:72-73): smallest and largest element of a device array, returned on the host
+ * (synchronises the stream like the reference); n > 0 */
+int cs_min_max_f(const float* first, size_t n, float* minOut, float* maxOut, void* stream);
+int cs_min_max_d(const double* first, size_t n, double* minOut, double* maxOut, void* stream);
+int cs_min_max_u32(const uint32_t* first, size_t n, uint32_t* minOut, uint32_t* maxOut, void* stream);
+
 /* ---- target particle groups (traversal/groups_gpu.h:33-78) ----
  * computeFixedGroups(exec, first, last, groupSize, GroupData&): groups[g] = first + g * groupSize for the
  * ceil((last-first)/groupSize) groups, groups[numGroups] = last. */

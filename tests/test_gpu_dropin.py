@@ -1,6 +1,7 @@
 """Drop-in check against the REAL reference headers: oracle/_ref/ref_gpu_unit_tests is the reference's own CUDA unit
 tests (test/unit_cuda/{cuda/device_vector, primitives/gather, tree/csarray, tree/octree, focus/inject,
-domain/domaindecomp_gpu, traversal/groups}.cu, compiled unmodified where they lie under /root/reference) linked against
+domain/domaindecomp_gpu, traversal/groups, traversal/macs, halos/gather_halos_gpu,
+primitives/primitives_gpu}.cu, compiled unmodified where they lie under /root/reference) linked against
 cornerstone-octree_b200/compat/cstone_gpu_forwarders.cu -> libcstone_b200.so instead of the reference's cstone_gpu
 library (recipe: oracle/Makefile; GoogleTest replaced by tests/compat/gtest/gtest.h).  Among others this runs
 test/unit_cuda/tree/csarray.cu:164-185 (GPU tree == CPU tree) and test/unit_cuda/tree/octree.cu:25-72 (linked octree
@@ -27,5 +28,6 @@ def test_reference_cuda_unit_tests_pass_against_this_library():
     expected = {"DeviceVector.Construct", "SortByKey.minimal", "CsArrayGpu.computeNodeCountsGpu",
                 "CsArrayGpu.rebalanceDecision", "CsArrayGpu.rebalanceTree", "CsArrayGpu.computeOctreeRandom",
                 "CsArrayGpu.distributedMockUp", "OctreeGpu.irregularL3", "OctreeGpu.regularL6", "FocusGpu.injectKeysGpu",
-                "DomainDecomposition.createSendListGpu", "TargetGroups.t0", "TargetGroups.groupVolumes"}
+                "DomainDecomposition.createSendListGpu", "TargetGroups.t0", "TargetGroups.groupVolumes",
+                "Macs.limitSource4x4_matchCPU", "Halos.gatherRanges", "PrimitivesGpu.MinMax"}
     assert expected <= ran, sorted(expected - ran)
