@@ -1195,7 +1195,11 @@ __device__ __forceinline__ void warpSearchGroup(GroupWalkShared& sh, const uint2
         // the walk is certain to reach the leaf if the particle is inside BOTH radii by the margin mu
         const float own2f = EXT ? fminf(r2f, c2f) : r2f;
         const float mu    = fmaf(4.0f * tau0, rsqrtf(own2f), 0x1p-18f);
-        const bool normal = own2f > 1e-30f && mu < 0x1p-6f; // false for NaN
+        // (tau0 = 12 ulp of the largest box coordinate also bounds the rounding of the reference's box tests only for
+        // targets that are not far outside the box themselves: others take the exact route)
+        const float tmax  = float(fmax(fmax(fabs(t.x), fabs(t.y)), fabs(t.z)));
+        const bool normal = own2f > 1e-30f && mu < 0x1p-6f && tmax * 12.0f * float(sizeof(T) == 8 ? 0x1p-52 : 0x1p-23) <=
+                                                                   2.0f * tau0; // false for NaN
         if (normal)
         {
             sureT = T(1.0f - 2.0f * mu);
