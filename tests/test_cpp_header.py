@@ -30,6 +30,13 @@ int main()
         cstone_b200::Domain<uint64_t, double> dom(0, 1, 64, 8, 0.5f, nullptr, Box{});
         float* rho = nullptr; double* vel = nullptr;
         dom.exchangeHalos(nullptr, rho, vel);
+        // reapplySync / setHaloFactor (domain.hpp:297-329, :365)
+        const double* uBefore = nullptr; double* uAfter = nullptr;
+        const float* tBefore = nullptr; float* tAfter = nullptr;
+        dom.setHaloFactor(1.2f);
+        dom.reapplySync(nullptr, std::pair<const double*, double*>{uBefore, uAfter},
+                        std::pair<const float*, float*>{tBefore, tAfter});
+        (void)dom.replaySizeBefore();
     }
     return 0;
 }
